@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- conjunctive queries scored/sec on synthetic Bio-shaped batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path over one batch: every query of the batch
+is scored against its positive and one negative target and folded into the
+margin loss (what reference model.py:112-127 computes per batch).  At N=1 the
+default workload is BASELINE.json configs[3] (Bio KG full mix, d=256,
+batch=65536) -- the metric string names no single config, so the largest
+single-GPU configuration is used; --workload selects configs[0..2].
+
+`value`    whole-job throughput with row-index arrays already resident in HBM,
+           timed with CUDA events on the launching stream, L2 flushed before
+           every step, max over ranks.
+`e2e`      same metric through the C-ABI *_host entry point: pinned HOST index
+           buffers in, HOST loss out, copies + stream sync inside the timed call.
+`roofline` algorithmic bytes / measured duration of the fused
+           kernel vs MEASURED_PEAKS.json; the tensor-core view is reported too.
+`cpu_baseline` the oracle port of the reference path timed on this box's cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "conjunctive queries scored/sec"
+UNIT = "queries/s"
+HBM_FALLBACK_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
+BF16_FALLBACK_TFLOPS = 1590.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("native", "reference"), default="native")
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--formulas-per-structure", type=int, default=1)
+    ap.add_argument("--cpu-sample", type=int, default=12288, help="queries in the CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline time budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured"}
+    return {"hbm_gbs": HBM_FALLBACK_GBS, "bf16_tflops": BF16_FALLBACK_TFLOPS, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons via NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.active, self._stop_evt = index, [], False, threading.Event()
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # honour CUDA_VISIBLE_DEVICES remapping when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((self.active, mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        under = [s for s in self.samples if s[0]] or self.samples
+        mhz = sorted(s[1] for s in under)
+        mask = 0
+        for s in under:
+            mask |= s[2]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(under)}
+
+
+# ---------------------------------------------------------------------------
+def device_parameters(wl, torch, device, seed):
+    """Random-init parameters of the reference's architecture, on the device:
+    tables N(0, 1/d) (bio/data_utils.py:17-19), xavier-uniform relation / pre /
+    post matrices (decoders.py:139,282,285)."""
+    import math
+    g = torch.Generator(device=device).manual_seed(seed)
+    d, kg = wl.d, wl.kg
+    tables = [torch.randn(kg.sizes[m] + 2, d, generator=g, device=device) * (1.0 / d) for m in kg.modes]
+    bound = math.sqrt(6.0 / (2 * d))
+    uni = lambda *shape: (torch.rand(*shape, generator=g, device=device) * 2 - 1) * bound
+    rels = [uni(d, d) for _ in kg.rel_keys]
+    pre = [uni(d, d) for _ in kg.modes]
+    post = [uni(d, d) for _ in kg.modes]
+    return tables, rels, pre, post
+
+
+def run_native(args):
+    import numpy as np
+    import torch
+
+    import graphqembed_b200 as gqe
+    from graphqembed_b200 import _lib
+    from graphqembed_b200.workloads import DEFAULT_WORKLOAD, WORKLOADS, make_workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    name = args.workload or DEFAULT_WORKLOAD
+    wl = make_workload(name, seed=rank, formulas_per_structure=args.formulas_per_structure)
+    tables, rels, pre, post = device_parameters(wl, torch, device, seed=1234)
+    lookup = gqe.RowLookup(wl.kg.node_ids)
+    mode_ids = {m: i for i, m in enumerate(wl.kg.modes)}
+    rel_ids = {r: i for i, r in enumerate(wl.kg.rel_keys)}
+    segs, anchor_rows, pair_rows = wl.lower(lookup, mode_ids, rel_ids)
+
+    stream = torch.cuda.current_stream(device)
+    ctx = gqe.Context(local_rank, stream.cuda_stream)
+    ctx.bind_tables([t.data_ptr() for t in tables], [t.size(0) for t in tables], wl.d)
+    ctx.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
+    ctx.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
+
+    # host buffers are pinned; the device copies are what `value` is timed on
+    h_anchor = torch.from_numpy(anchor_rows).pin_memory()
+    h_pairs = torch.from_numpy(pair_rows).pin_memory()
+    h_loss = torch.zeros(1).pin_memory()
+    d_anchor = h_anchor.to(device)
+    d_pairs = h_pairs.to(device)
+    d_loss = torch.zeros(1, device=device)
+    nq = wl.n_queries
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+
+    def step_device():
+        ctx.score_grouped_device(segs, nq, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, None, 1.0, d_loss.data_ptr())
+
+    def step_host():
+        ctx._check(ctx._lib.gqe_score_grouped_host(ctx._h, segs, len(segs), nq, h_anchor.data_ptr(), h_pairs.data_ptr(),
+                                                   2, None, 1.0, h_loss.data_ptr()))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_device()
+    barrier()
+    loss_ref = float(d_loss.item())
+
+    # ---- device-resident timing: K steps, L2 flushed before each, CUDA events ----
+    launches0 = ctx.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.active = True
+    for e0, e1 in evs:
+        flush.zero_()
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+    barrier()
+    sampler.active = False
+    launches = ctx.launch_count() - launches0
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    assert float(d_loss.item()) == loss_ref, "non-deterministic loss"
+
+    # ---- end to end through the host-buffer C-ABI call ----------------------------
+    for _ in range(3):
+        step_host()
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        step_host()
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    assert abs(float(h_loss[0]) - loss_ref) == 0.0, "host entry point disagrees with the device one"
+    sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    line = None
+    if rank == 0:
+        pk = peaks()
+        ms_per_step = dev_ms / args.steps
+        value = world * nq / (ms_per_step * 1e-3)
+        kern_s = ms_per_step * 1e-3 / max(1, launches // args.steps)
+        bytes_alg, flops_alg = wl.algorithmic_bytes(), wl.algorithmic_flops()
+        gbs = bytes_alg / (ms_per_step * 1e-3) / 1e9
+        tfl = flops_alg / (ms_per_step * 1e-3) / 1e12
+        t_hbm = bytes_alg / (pk["hbm_gbs"] * 1e9)
+        t_tc = flops_alg / (pk["bf16_tflops"] * 1e12)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(name)
+        bound = "hbm" if t_hbm >= t_tc else "tensor"
+        roof = {"bound": bound,
+                "achieved": round(gbs if bound == "hbm" else tfl, 3),
+                "peak": pk["hbm_gbs"] if bound == "hbm" else pk["bf16_tflops"],
+                "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                "frac": round((gbs / pk["hbm_gbs"]) if bound == "hbm" else (tfl / pk["bf16_tflops"]), 4),
+                "traffic": traffic, "peak_source": pk["source"],
+                "kernel": "gqe_fused (grouped, one launch per step)",
+                "kernel_ms": round(kern_s * 1e3, 4),
+                "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_flops_per_launch": flops_alg,
+                "hbm": {"achieved_gbs": round(gbs, 2), "frac": round(gbs / pk["hbm_gbs"], 4)},
+                "tensor": {"achieved_tflops": round(tfl, 3), "peak_tflops": pk["bf16_tflops"],
+                           "frac": round(tfl / pk["bf16_tflops"], 4),
+                           "note": "d x d contractions; peak = measured bf16 dense"}}
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[name][0], "name": name, "queries_per_step_per_gpu": nq,
+                       "targets_per_query": 2, "decoder": wl.decoder, "intersection": wl.inter, "d": wl.d,
+                       "formulas": len(wl.batches), "tables": "replicated per GPU (Bio-size)",
+                       "l2": "flushed before every step (256 MiB write)"},
+            "e2e": {"value": round(world * nq / (e2e_ms * 1e-3 / args.steps), 1), "unit": UNIT,
+                    "h2d_bytes_per_step": int(anchor_rows.nbytes + pair_rows.nbytes), "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(e2e_ms / args.steps, 5),
+                    "call": "gqe_score_grouped_host (pinned int32 row indices in, fp32 loss out)"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": roof,
+            "loss": loss_ref,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(args, name, tables=[t.cpu() for t in tables],
+                                                 rels=[r.cpu() for r in rels], pre=[p.cpu() for p in pre],
+                                                 post=[p.cpu() for p in post], steps=None)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def cpu_reference(args, name, tables=None, rels=None, pre=None, post=None, steps=None, warmup=2):
+    """Time the oracle port of the reference path on this box's host cores on a
+    bounded sample of the workload.  Includes the reference's own Python index
+    building (list comprehensions + node_maps dict lookups): that is its real
+    path (model.py:75-92, bio/data_utils.py:20-21)."""
+    import numpy as np
+    import torch
+
+    from graphqembed_b200.synth import SynthKG
+    from graphqembed_b200.workloads import WORKLOADS, make_workload
+    from oracle import netquery_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = min(args.cpu_sample, WORKLOADS[name][2])
+    wl = make_workload(name, seed=0, total=sample, formulas_per_structure=args.formulas_per_structure)
+    kg = wl.kg
+    if tables is None:
+        import math
+        g = torch.Generator().manual_seed(1234)
+        d = wl.d
+        bound = math.sqrt(6.0 / (2 * d))
+        uni = lambda *s: (torch.rand(*s, generator=g) * 2 - 1) * bound
+        tables = [torch.randn(kg.sizes[m] + 2, d, generator=g) * (1.0 / d) for m in kg.modes]
+        rels = [uni(d, d) for _ in kg.rel_keys]
+        pre = [uni(d, d) for _ in kg.modes]
+        post = [uni(d, d) for _ in kg.modes]
+    orc = O.OracleScorer(dict(zip(kg.modes, tables)), kg.node_maps(), dict(zip(kg.rel_keys, rels)), wl.decoder,
+                         wl.inter, dict(zip(kg.modes, pre)), dict(zip(kg.modes, post)))
+    work = []
+    for b in wl.batches:
+        s = b.formula.query_type
+        f = O.Formula(s, b.formula.rels)
+        pairs = b.targets.reshape(-1, 2)
+        qs = [O.Query(SynthKG.query_graph(s, f.rels, pairs[i, 0], b.anchors[:, i]), None, None)
+              for i in range(b.n_queries)]
+        work.append((f, qs, [int(x) for x in pairs[:, 1]]))
+
+    def one_pass():
+        tot = 0.0
+        with torch.no_grad():
+            for f, qs, negs in work:
+                tot += float(orc.margin_loss(f, qs, neg_nodes=negs)) * len(qs)
+        return tot / wl.n_queries
+
+    for _ in range(warmup):
+        one_pass()
+    times = []
+    if steps is None:
+        t_end = time.perf_counter() + args.cpu_seconds
+        while time.perf_counter() < t_end or len(times) < 3:
+            t0 = time.perf_counter()
+            one_pass()
+            times.append(time.perf_counter() - t0)
+    else:
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            one_pass()
+            times.append(time.perf_counter() - t0)
+    mean_s = sum(times) / len(times)
+    return {"value": round(wl.n_queries / mean_s, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d queries of %s (same mix), %d passes, torch %s CPU, %d threads; oracle/netquery_oracle.py "
+                      "margin_loss incl. Python index building" % (wl.n_queries, name, len(times), torch.__version__,
+                                                                    cores),
+            "ms_per_pass": round(mean_s * 1e3, 3)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.
+    The reference is Python and cannot travel to the GPU box, so this arm times
+    its oracle port (bit-identical to the reference, see tests/) with all host
+    threads; each step is one pass over a bounded sample of the workload."""
+    from graphqembed_b200.workloads import DEFAULT_WORKLOAD, WORKLOADS
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    name = args.workload or DEFAULT_WORKLOAD
+    base = cpu_reference(args, name, steps=args.steps, warmup=max(args.warmup, 1))
+    desc, d, total, structures, decoder, inter = WORKLOADS[name]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": base["ms_per_pass"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "name": name, "targets_per_query": 2, "decoder": decoder, "intersection": inter,
+                   "d": d, "sample_queries_per_step": min(args.cpu_sample, total)},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -1,0 +1,37 @@
+"""graphqembed_b200 -- B200-native conjunctive-query embedding scorer.
+
+A from-scratch sm_100a implementation of ONE path of williamleif/graphqembed
+(``netquery``): the batched forward scoring of conjunctive graph queries and
+its margin loss, behind the reference's own operator surface.  See DESIGN.md
+for the path and its boundary, INTEGRATION.md for how it plugs into netquery.
+
+Importing this package does not need a GPU; creating a context (any scoring
+call) does, and raises if the CUDA library or an sm_100 device is missing.
+"""
+from . import _lib
+from ._lib import Context, GqeError, Plan, Segment, build, load, make_segments
+from .lowering import RowLookup, lower_formula, relation_order
+from .query import Formula, Query, QueryBatch, reverse_relation
+
+__all__ = ["Context", "GqeError", "Plan", "Segment", "build", "load", "make_segments", "RowLookup", "lower_formula",
+           "relation_order", "Formula", "Query", "QueryBatch", "reverse_relation", "DirectEncoder",
+           "BilinearMetapathDecoder", "TransEMetapathDecoder", "BilinearDiagMetapathDecoder", "SetIntersection",
+           "SimpleSetIntersection", "QueryEncoderDecoder", "get_encoder", "get_metapath_decoder",
+           "get_intersection_decoder"]
+
+_TORCH_SIDE = {
+    "DirectEncoder": "operators", "BilinearMetapathDecoder": "operators", "TransEMetapathDecoder": "operators",
+    "BilinearDiagMetapathDecoder": "operators", "SetIntersection": "operators", "SimpleSetIntersection": "operators",
+    "get_encoder": "operators", "get_metapath_decoder": "operators", "get_intersection_decoder": "operators",
+    "cosine_similarity_dim0": "operators", "QueryEncoderDecoder": "scorer",
+}
+
+
+def __getattr__(name):
+    # torch-facing classes are imported lazily so that the pure C-ABI users
+    # (bench, ctypes hosts) do not pay the torch import.
+    mod = _TORCH_SIDE.get(name)
+    if mod is None:
+        raise AttributeError(name)
+    import importlib
+    return getattr(importlib.import_module("." + mod, __name__), name)

@@ -1,0 +1,240 @@
+"""ctypes binding of the C ABI in ``include/gqe.h`` (libgqe_b200.so).
+
+The shared library is built in-tree by ``build()`` (``nvcc`` for sm_100a) and
+loaded from the package directory.  There is no fallback: if the library is
+missing, or no sm_100 device is present, every entry point raises.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_NAME = "libgqe_b200.so"
+LIB_PATH = os.path.join(_PKG, LIB_NAME)
+SOURCES = [os.path.join(_PKG, "csrc", "gqe_capi.cu")]
+HEADERS = [os.path.join(_PKG, "csrc", "gqe_simt.cuh"), os.path.join(_ROOT, "include", "gqe.h")]
+
+GQE_MAX_ANCHORS = 3
+GQE_MAX_RELS = 3
+
+STRUCTURE_ID = {"1-chain": 0, "2-chain": 1, "3-chain": 2, "2-inter": 3, "3-inter": 4,
+                "3-inter_chain": 5, "3-chain_inter": 6}
+DECODER_ID = {"bilinear": 0, "transe": 1, "bilinear-diag": 2}
+INTER_ID = {"mean": 0, "min": 1, "mean-simple": 2, "min-simple": 3}
+
+
+class GqeError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "gqe error %d: %s" % (code, message))
+        self.code = code
+
+
+class Plan(C.Structure):
+    _fields_ = [("structure", C.c_int32), ("target_mode", C.c_int32),
+                ("anchor_mode", C.c_int32 * GQE_MAX_ANCHORS), ("inter_mode", C.c_int32),
+                ("rel", C.c_int32 * GQE_MAX_RELS)]
+
+    def as_tuple(self):
+        return (self.structure, self.target_mode, tuple(self.anchor_mode), self.inter_mode, tuple(self.rel))
+
+
+class Segment(C.Structure):
+    _fields_ = [("plan", Plan), ("query_begin", C.c_int64), ("query_end", C.c_int64)]
+
+
+# name -> (restype, argtypes); every symbol include/gqe.h declares.
+_P = C.c_void_p
+_SIGNATURES = {
+    "gqe_abi_version": (C.c_int, []),
+    "gqe_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "gqe_destroy": (None, [_P]),
+    "gqe_set_stream": (C.c_int, [_P, _P]),
+    "gqe_last_error": (C.c_char_p, [_P]),
+    "gqe_launch_count": (C.c_int64, [_P]),
+    "gqe_bind_tables": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64), C.c_int32]),
+    "gqe_bind_relations": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.c_int32]),
+    "gqe_bind_intersection": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(_P), C.c_int32, C.c_int32]),
+    "gqe_score_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, C.c_int64, _P, _P, _P]),
+    "gqe_margin_loss_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_score_grouped_device": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.c_int64, _P, _P, C.c_int32, _P,
+                                           C.c_float, _P]),
+    "gqe_score_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, C.c_int64, _P, _P, _P]),
+    "gqe_margin_loss_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_score_grouped_host": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.c_int64, _P, _P, C.c_int32, _P,
+                                         C.c_float, _P]),
+    "gqe_encode_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
+    "gqe_project_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
+    "gqe_path_score_device": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int64, _P, _P, C.c_int32, _P]),
+    "gqe_intersect_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, _P]),
+    "gqe_cosine_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA sources for sm_100a into the in-tree shared library."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed (%d):\n%s\n%s" % (proc.returncode, " ".join(cmd), proc.stdout))
+    if verbose:
+        sys.stderr.write(proc.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load libgqe_b200.so and declare every prototype.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "%s is not built; run `python -c \"import __graft_entry__ as g; g.build()\"` "
+            "(there is no CPU fallback for the CUDA path)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gqe_abi_version() != 1:
+        raise RuntimeError("libgqe_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr_array(ptrs):
+    arr = (_P * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+class Context(object):
+    """A gqe_ctx: one device, one stream, one set of bound parameters."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = load()
+        handle = _P()
+        rc = self._lib.gqe_create(int(device), _P(stream or 0), C.byref(handle))
+        if rc != 0:
+            raise GqeError(rc, self._lib.gqe_last_error(None).decode())
+        self._h = handle
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gqe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GqeError(rc, self._lib.gqe_last_error(self._h).decode())
+
+    def set_stream(self, stream):
+        self._check(self._lib.gqe_set_stream(self._h, _P(stream or 0)))
+
+    def launch_count(self):
+        return int(self._lib.gqe_launch_count(self._h))
+
+    # -- binding ------------------------------------------------------------
+    def bind_tables(self, table_ptrs, rows, d):
+        n = len(table_ptrs)
+        rows_arr = (C.c_int64 * n)(*[int(r) for r in rows])
+        self._check(self._lib.gqe_bind_tables(self._h, n, _ptr_array(table_ptrs), rows_arr, int(d)))
+
+    def bind_relations(self, decoder, param_ptrs, d):
+        self._check(self._lib.gqe_bind_relations(self._h, int(decoder), len(param_ptrs), _ptr_array(param_ptrs), int(d)))
+
+    def bind_intersection(self, inter, pre_ptrs, post_ptrs, d, d_expand=None):
+        n = len(pre_ptrs or [])
+        pre = _ptr_array(pre_ptrs) if n else None
+        post = _ptr_array(post_ptrs) if n else None
+        self._check(self._lib.gqe_bind_intersection(self._h, int(inter), n, pre, post, int(d),
+                                                    int(d if d_expand is None else d_expand)))
+
+    # -- fused path, device buffers (raw device pointers as ints) -----------------
+    def score_device(self, plan, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, out_scores):
+        self._check(self._lib.gqe_score_device(self._h, C.byref(plan), n_queries, anchor_rows, n_pairs, target_rows,
+                                               target_offsets, out_scores))
+
+    def margin_loss_device(self, plan, n_queries, anchor_rows, pair_rows, margin, out_loss, out_scores=None):
+        self._check(self._lib.gqe_margin_loss_device(self._h, C.byref(plan), n_queries, anchor_rows, pair_rows,
+                                                     float(margin), out_loss, out_scores))
+
+    def score_grouped_device(self, segments, n_queries_total, anchor_rows, target_rows, targets_per_query,
+                             out_scores, margin=1.0, out_loss=None):
+        self._check(self._lib.gqe_score_grouped_device(self._h, segments, len(segments), n_queries_total, anchor_rows,
+                                                       target_rows, targets_per_query, out_scores, float(margin),
+                                                       out_loss))
+
+    # -- fused path, host buffers (numpy arrays) -----------------------------------
+    def score_host(self, plan, anchor_rows, target_rows, target_offsets, out_scores):
+        nq = anchor_rows.shape[1]
+        off = None if target_offsets is None else target_offsets.ctypes.data
+        self._check(self._lib.gqe_score_host(self._h, C.byref(plan), nq, anchor_rows.ctypes.data, target_rows.size,
+                                             target_rows.ctypes.data, off, out_scores.ctypes.data))
+
+    def margin_loss_host(self, plan, anchor_rows, pair_rows, margin, out_loss, out_scores=None):
+        nq = anchor_rows.shape[1]
+        sc = None if out_scores is None else out_scores.ctypes.data
+        self._check(self._lib.gqe_margin_loss_host(self._h, C.byref(plan), nq, anchor_rows.ctypes.data,
+                                                   pair_rows.ctypes.data, float(margin), out_loss.ctypes.data, sc))
+
+    def score_grouped_host(self, segments, anchor_rows, target_rows, targets_per_query, out_scores, margin=1.0,
+                           out_loss=None):
+        nq = anchor_rows.shape[1]
+        sc = None if out_scores is None else out_scores.ctypes.data
+        ls = None if out_loss is None else out_loss.ctypes.data
+        self._check(self._lib.gqe_score_grouped_host(self._h, segments, len(segments), nq, anchor_rows.ctypes.data,
+                                                     target_rows.ctypes.data, targets_per_query, sc, float(margin), ls))
+
+    # -- operator level ---------------------------------------------------------------
+    def encode_device(self, mode, n, rows, out):
+        self._check(self._lib.gqe_encode_device(self._h, mode, n, rows, out))
+
+    def project_device(self, rel, n, src, out):
+        self._check(self._lib.gqe_project_device(self._h, rel, n, src, out))
+
+    def path_score_device(self, rels, n, embeds1, embeds2, mutate, out):
+        arr = (C.c_int32 * len(rels))(*rels)
+        self._check(self._lib.gqe_path_score_device(self._h, len(rels), arr, n, embeds1, embeds2, int(mutate), out))
+
+    def intersect_device(self, mode, n, e1, e2, e3, out):
+        self._check(self._lib.gqe_intersect_device(self._h, mode, n, e1, e2, e3, out))
+
+    def cosine_device(self, d, n, x, y, out):
+        self._check(self._lib.gqe_cosine_device(self._h, d, n, x, y, out))
+
+
+def make_segments(items):
+    """[(Plan, begin, end), ...] -> ctypes array of gqe_segment."""
+    arr = (Segment * len(items))()
+    for i, (plan, b, e) in enumerate(items):
+        arr[i].plan = plan
+        arr[i].query_begin = int(b)
+        arr[i].query_end = int(e)
+    return arr

@@ -1,0 +1,612 @@
+// gqe_capi.cu -- host side of the C ABI declared in include/gqe.h.
+//
+// Owns the context (bound parameter pointers, stream, scratch buffers),
+// validates and resolves lowered formulas to device pointers, sizes grids and
+// launches the fused kernels.  No torch types, no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gqe.h"
+#include "gqe_simt.cuh"
+
+using namespace gqe;
+
+struct gqe_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  int d = 0;
+  std::vector<const float*> tables;
+  std::vector<int64_t> table_rows;
+
+  int decoder = -1;
+  int rel_d = 0;
+  std::vector<const float*> rels;
+
+  int inter = -1;
+  int inter_d = 0;
+  std::vector<const float*> pre, post;
+
+  // margin-loss reduction scratch
+  double* partials = nullptr;
+  int64_t partials_cap = 0;
+  double* loss_acc = nullptr;
+  unsigned int* ticket = nullptr;
+
+  // staging for the *_host entry points (grow on demand)
+  void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t stage_cap[6] = {0, 0, 0, 0, 0, 0};
+};
+
+static std::string g_create_error;
+
+static int fail(gqe_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define GQE_CUDA(c, call)                                                                        \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail((c), GQE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static bool dim_supported(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
+
+static int n_anchors_of(int structure) {
+  switch (structure) {
+    case GQE_CHAIN1: case GQE_CHAIN2: case GQE_CHAIN3: return 1;
+    case GQE_INTER2: case GQE_INTER_CHAIN3: case GQE_CHAIN_INTER3: return 2;
+    case GQE_INTER3: return 3;
+    default: return -1;
+  }
+}
+static int n_rels_of(int structure) {
+  switch (structure) {
+    case GQE_CHAIN1: return 1;
+    case GQE_CHAIN2: case GQE_INTER2: return 2;
+    case GQE_CHAIN3: case GQE_INTER3: case GQE_INTER_CHAIN3: case GQE_CHAIN_INTER3: return 3;
+    default: return -1;
+  }
+}
+
+extern "C" int gqe_abi_version(void) { return GQE_ABI_VERSION; }
+
+extern "C" int gqe_create(int device, void* stream, gqe_ctx** out) {
+  if (!out) return fail(nullptr, GQE_ERR_INVALID, "gqe_create: out is null");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, GQE_ERR_CUDA, "gqe_create: no CUDA device (%s); this library has no CPU path",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(nullptr, GQE_ERR_INVALID, "gqe_create: device %d out of range", device);
+  cudaDeviceProp prop;
+  GQE_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, GQE_ERR_UNSUPPORTED, "gqe_create: device %d is sm_%d%d; this build targets sm_100a only",
+                device, prop.major, prop.minor);
+  GQE_CUDA(nullptr, cudaSetDevice(device));
+  gqe_ctx* c = new gqe_ctx();
+  c->device = device;
+  c->stream = (cudaStream_t)stream;
+  if (cudaMalloc(&c->loss_acc, sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&c->ticket, sizeof(unsigned int)) != cudaSuccess) {
+    delete c;
+    return fail(nullptr, GQE_ERR_NOMEM, "gqe_create: cudaMalloc failed");
+  }
+  cudaMemset(c->loss_acc, 0, sizeof(double));
+  cudaMemset(c->ticket, 0, sizeof(unsigned int));
+  *out = c;
+  return GQE_OK;
+}
+
+extern "C" void gqe_destroy(gqe_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->partials);
+  cudaFree(c->loss_acc);
+  cudaFree(c->ticket);
+  for (void* p : c->stage) cudaFree(p);
+  delete c;
+}
+
+extern "C" int gqe_set_stream(gqe_ctx* c, void* stream) {
+  if (!c) return GQE_ERR_INVALID;
+  c->stream = (cudaStream_t)stream;
+  return GQE_OK;
+}
+
+extern "C" const char* gqe_last_error(const gqe_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+extern "C" int64_t gqe_launch_count(const gqe_ctx* c) { return c ? c->launches : 0; }
+
+// ---- binding ---------------------------------------------------------------
+extern "C" int gqe_bind_tables(gqe_ctx* c, int32_t n_modes, const float* const* tables, const int64_t* rows,
+                               int32_t d) {
+  if (!c) return GQE_ERR_INVALID;
+  if (n_modes <= 0 || !tables || !rows) return fail(c, GQE_ERR_INVALID, "gqe_bind_tables: bad arguments");
+  if (!dim_supported(d))
+    return fail(c, GQE_ERR_UNSUPPORTED, "gqe_bind_tables: embedding dimension %d not supported (32/64/128/256)", d);
+  for (int m = 0; m < n_modes; ++m)
+    if (!tables[m] || rows[m] <= 0) return fail(c, GQE_ERR_INVALID, "gqe_bind_tables: mode %d has no table", m);
+  c->tables.assign(tables, tables + n_modes);
+  c->table_rows.assign(rows, rows + n_modes);
+  c->d = d;
+  return GQE_OK;
+}
+
+extern "C" int gqe_bind_relations(gqe_ctx* c, int32_t decoder, int32_t n_rels, const float* const* params,
+                                  int32_t d) {
+  if (!c) return GQE_ERR_INVALID;
+  if (decoder < GQE_DEC_BILINEAR || decoder > GQE_DEC_DISTMULT)
+    return fail(c, GQE_ERR_INVALID, "gqe_bind_relations: unknown decoder %d", decoder);
+  if (n_rels <= 0 || !params) return fail(c, GQE_ERR_INVALID, "gqe_bind_relations: bad arguments");
+  if (!dim_supported(d)) return fail(c, GQE_ERR_UNSUPPORTED, "gqe_bind_relations: dimension %d not supported", d);
+  for (int r = 0; r < n_rels; ++r)
+    if (!params[r]) return fail(c, GQE_ERR_INVALID, "gqe_bind_relations: relation %d has no parameter", r);
+  c->rels.assign(params, params + n_rels);
+  c->decoder = decoder;
+  c->rel_d = d;
+  return GQE_OK;
+}
+
+extern "C" int gqe_bind_intersection(gqe_ctx* c, int32_t inter, int32_t n_modes, const float* const* pre,
+                                     const float* const* post, int32_t d, int32_t d_expand) {
+  if (!c) return GQE_ERR_INVALID;
+  if (inter < GQE_INTER_DEEPSETS_MEAN || inter > GQE_INTER_SIMPLE_MIN)
+    return fail(c, GQE_ERR_INVALID, "gqe_bind_intersection: unknown kind %d", inter);
+  const bool deepsets = inter <= GQE_INTER_DEEPSETS_MIN;
+  c->pre.clear();
+  c->post.clear();
+  if (deepsets) {
+    if (n_modes <= 0 || !pre || !post) return fail(c, GQE_ERR_INVALID, "gqe_bind_intersection: pre/post required");
+    if (d_expand != d)
+      return fail(c, GQE_ERR_UNSUPPORTED, "gqe_bind_intersection: expand dim %d != embed dim %d not supported", d_expand, d);
+    if (!dim_supported(d)) return fail(c, GQE_ERR_UNSUPPORTED, "gqe_bind_intersection: dimension %d not supported", d);
+    for (int m = 0; m < n_modes; ++m)
+      if (!pre[m] || !post[m]) return fail(c, GQE_ERR_INVALID, "gqe_bind_intersection: mode %d has no matrices", m);
+    c->pre.assign(pre, pre + n_modes);
+    c->post.assign(post, post + n_modes);
+  }
+  c->inter = inter;
+  c->inter_d = d;
+  return GQE_OK;
+}
+
+// ---- plan resolution ---------------------------------------------------------
+static int resolve(gqe_ctx* c, const gqe_plan& pl, SegDev* s) {
+  const int na = n_anchors_of(pl.structure), nr = n_rels_of(pl.structure);
+  if (na < 0) return fail(c, GQE_ERR_INVALID, "unknown query structure %d", pl.structure);
+  if (c->tables.empty()) return fail(c, GQE_ERR_UNBOUND, "embedding tables are not bound");
+  if (c->rels.empty()) return fail(c, GQE_ERR_UNBOUND, "relation parameters are not bound");
+  if (c->rel_d != c->d) return fail(c, GQE_ERR_UNSUPPORTED, "relation dim %d != table dim %d", c->rel_d, c->d);
+  const int nm = (int)c->tables.size();
+  if (pl.target_mode < 0 || pl.target_mode >= nm) return fail(c, GQE_ERR_INVALID, "target mode %d out of range", pl.target_mode);
+  std::memset(s, 0, sizeof *s);
+  s->structure = pl.structure;
+  s->n_anchor = na;
+  s->tgt_table = c->tables[pl.target_mode];
+  for (int k = 0; k < na; ++k) {
+    if (pl.anchor_mode[k] < 0 || pl.anchor_mode[k] >= nm)
+      return fail(c, GQE_ERR_INVALID, "anchor %d mode %d out of range", k, pl.anchor_mode[k]);
+    s->anc_table[k] = c->tables[pl.anchor_mode[k]];
+  }
+  for (int k = 0; k < nr; ++k) {
+    if (pl.rel[k] < 0 || pl.rel[k] >= (int)c->rels.size())
+      return fail(c, GQE_ERR_INVALID, "relation id %d out of range", pl.rel[k]);
+    s->rel[k] = c->rels[pl.rel[k]];
+  }
+  if (pl.structure >= GQE_INTER2) {
+    if (c->inter < 0) return fail(c, GQE_ERR_UNBOUND, "intersection operator is not bound");
+    if (c->inter <= GQE_INTER_DEEPSETS_MIN) {
+      if (c->inter_d != c->d) return fail(c, GQE_ERR_UNSUPPORTED, "intersection dim %d != table dim %d", c->inter_d, c->d);
+      if (pl.inter_mode < 0 || pl.inter_mode >= (int)c->pre.size())
+        return fail(c, GQE_ERR_INVALID, "intersection mode %d out of range", pl.inter_mode);
+      s->pre = c->pre[pl.inter_mode];
+      s->post = c->post[pl.inter_mode];
+    }
+  }
+  return GQE_OK;
+}
+
+// cudaFuncSetAttribute is per device: remember which devices were configured.
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 63;
+}
+
+template <int D, int STRUCT>
+static cudaError_t launch_one(const LaunchParams& lp, int64_t grid, cudaStream_t st) {
+  static bool configured[64] = {false};
+  auto kern = gqe_fused_simt<D, STRUCT>;
+  const int dev = current_device();
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<D>));
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  kern<<<(unsigned)grid, kThreads, sizeof(TileSmem<D>), st>>>(lp);
+  return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t launch_struct(int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {
+  switch (structure) {
+    case GQE_CHAIN1: return launch_one<D, GQE_CHAIN1>(lp, grid, st);
+    case GQE_CHAIN2: return launch_one<D, GQE_CHAIN2>(lp, grid, st);
+    case GQE_CHAIN3: return launch_one<D, GQE_CHAIN3>(lp, grid, st);
+    case GQE_INTER2: return launch_one<D, GQE_INTER2>(lp, grid, st);
+    case GQE_INTER3: return launch_one<D, GQE_INTER3>(lp, grid, st);
+    case GQE_INTER_CHAIN3: return launch_one<D, GQE_INTER_CHAIN3>(lp, grid, st);
+    case GQE_CHAIN_INTER3: return launch_one<D, GQE_CHAIN_INTER3>(lp, grid, st);
+    default: return launch_one<D, -1>(lp, grid, st);
+  }
+}
+
+static cudaError_t launch_dim(int d, int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {
+  switch (d) {
+    case 32: return launch_struct<32>(structure, lp, grid, st);
+    case 64: return launch_struct<64>(structure, lp, grid, st);
+    case 128: return launch_struct<128>(structure, lp, grid, st);
+    case 256: return launch_struct<256>(structure, lp, grid, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static int ensure_partials(gqe_ctx* c, int64_t n) {
+  if (n <= c->partials_cap) return GQE_OK;
+  // the old buffer may still be read by a kernel in flight on the stream
+  GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->partials);
+  c->partials = nullptr;
+  c->partials_cap = 0;
+  const int64_t cap = std::max<int64_t>(n, 4096);
+  GQE_CUDA(c, cudaMalloc(&c->partials, cap * sizeof(double)));
+  c->partials_cap = cap;
+  return GQE_OK;
+}
+
+// The one launcher behind every fused entry point.
+static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_t nq_total,
+                     const int32_t* anchor_rows, int64_t n_pairs, const int32_t* target_rows,
+                     const int64_t* target_offsets, int32_t T, float* out_scores, float margin, float* out_loss) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!segs || n_segs <= 0) return fail(c, GQE_ERR_INVALID, "no segments");
+  if (nq_total < 0 || n_pairs < 0) return fail(c, GQE_ERR_INVALID, "negative size");
+  if (!out_scores && !out_loss) return fail(c, GQE_ERR_INVALID, "no output requested");
+  if (target_offsets && n_segs != 1) return fail(c, GQE_ERR_INVALID, "ragged targets need a single formula");
+  if (target_offsets && out_loss) return fail(c, GQE_ERR_INVALID, "margin loss needs the regular (pos,neg) layout");
+  if (out_loss && T != 2) return fail(c, GQE_ERR_INVALID, "margin loss needs exactly 2 targets per query");
+  if (!target_offsets && T <= 0 && nq_total > 0) return fail(c, GQE_ERR_INVALID, "targets per query must be positive");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+
+  if (out_loss) {
+    GQE_CUDA(c, cudaMemsetAsync(c->loss_acc, 0, sizeof(double), c->stream));
+    // mean over an empty batch is NaN in the reference (torch mean of an empty tensor)
+    if (nq_total == 0) GQE_CUDA(c, cudaMemsetAsync(out_loss, 0xFF, sizeof(float), c->stream));
+  }
+  if (nq_total == 0) return GQE_OK;
+  if (!anchor_rows || !target_rows) return fail(c, GQE_ERR_INVALID, "index arrays are null");
+
+  LaunchParams lp;
+  std::memset(&lp, 0, sizeof lp);
+  lp.decoder = c->decoder;
+  lp.inter = c->inter < 0 ? 0 : c->inter;
+  lp.anchor_rows = anchor_rows;
+  lp.anchor_stride = nq_total;
+  lp.target_rows = target_rows;
+  lp.target_offsets = target_offsets;
+  lp.n_pairs = n_pairs;
+  lp.T = T;
+  lp.out_scores = out_scores;
+  lp.out_loss = out_loss;
+  lp.margin = margin;
+  lp.inv_q = 1.0 / (double)nq_total;
+  lp.loss_acc = c->loss_acc;
+  lp.ticket = c->ticket;
+
+  int32_t i = 0;
+  while (i < n_segs) {
+    int n = 0;
+    int64_t tiles = 0;
+    int first_structure = -1;
+    bool uniform = true;
+    while (i < n_segs && n < kMaxSegs) {
+      const gqe_segment& g = segs[i++];
+      if (g.query_begin < 0 || g.query_end < g.query_begin || g.query_end > nq_total)
+        return fail(c, GQE_ERR_INVALID, "segment query range [%lld,%lld) outside [0,%lld)", (long long)g.query_begin,
+                    (long long)g.query_end, (long long)nq_total);
+      if (g.query_end == g.query_begin) continue;
+      SegDev* s = &lp.seg[n];
+      int rc = resolve(c, g.plan, s);
+      if (rc != GQE_OK) return rc;
+      s->q_begin = g.query_begin;
+      s->q_end = g.query_end;
+      s->tile_begin = tiles;
+      const int64_t nq = g.query_end - g.query_begin;
+      const int64_t rows = g.plan.structure <= GQE_CHAIN3 ? (target_offsets ? n_pairs : nq * T) : nq;
+      tiles += (rows + kTileRows - 1) / kTileRows;
+      if (first_structure < 0) first_structure = g.plan.structure;
+      else if (first_structure != g.plan.structure) uniform = false;
+      ++n;
+    }
+    if (n == 0 || tiles == 0) continue;
+    if (tiles > 0x7fffffffLL) return fail(c, GQE_ERR_UNSUPPORTED, "batch too large for one launch (%lld tiles)", (long long)tiles);
+    lp.n_segs = n;
+    if (out_loss) {
+      int rc = ensure_partials(c, tiles);
+      if (rc != GQE_OK) return rc;
+      lp.partials = c->partials;
+    }
+    // single formula -> that structure's own kernel; otherwise the grouped kernel
+    const int structure = (n == 1 && uniform) ? first_structure : -1;
+    GQE_CUDA(c, launch_dim(c->d, structure, lp, tiles, c->stream));
+    c->launches += 1;
+  }
+  return GQE_OK;
+}
+
+static int regular_T(gqe_ctx* c, int64_t nq, int64_t n_pairs, const int64_t* offsets, int32_t* T) {
+  *T = 0;
+  if (offsets) return GQE_OK;
+  if (nq == 0) return n_pairs == 0 ? GQE_OK : fail(c, GQE_ERR_INVALID, "pairs without queries");
+  if (n_pairs % nq != 0 || n_pairs / nq <= 0 || n_pairs / nq > 0x7fffffff)
+    return fail(c, GQE_ERR_INVALID, "regular layout needs n_pairs (%lld) to be a positive multiple of n_queries (%lld)",
+                (long long)n_pairs, (long long)nq);
+  *T = (int32_t)(n_pairs / nq);
+  return GQE_OK;
+}
+
+extern "C" int gqe_score_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                                int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets,
+                                float* out_scores) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!plan || !out_scores) return fail(c, GQE_ERR_INVALID, "gqe_score_device: null argument");
+  int32_t T;
+  int rc = regular_T(c, n_queries, n_pairs, target_offsets, &T);
+  if (rc != GQE_OK) return rc;
+  gqe_segment seg{*plan, 0, n_queries};
+  return run_fused(c, &seg, 1, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, T, out_scores, 0.f, nullptr);
+}
+
+extern "C" int gqe_margin_loss_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                                      const int32_t* pair_rows, float margin, float* out_loss, float* out_scores) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!plan || !out_loss) return fail(c, GQE_ERR_INVALID, "gqe_margin_loss_device: null argument");
+  gqe_segment seg{*plan, 0, n_queries};
+  return run_fused(c, &seg, 1, n_queries, anchor_rows, 2 * n_queries, pair_rows, nullptr, 2, out_scores, margin, out_loss);
+}
+
+extern "C" int gqe_score_grouped_device(gqe_ctx* c, const gqe_segment* segments, int32_t n_segments,
+                                        int64_t n_queries_total, const int32_t* anchor_rows, const int32_t* target_rows,
+                                        int32_t targets_per_query, float* out_scores, float margin, float* out_loss) {
+  if (!c) return GQE_ERR_INVALID;
+  return run_fused(c, segments, n_segments, n_queries_total, anchor_rows, n_queries_total * targets_per_query,
+                   target_rows, nullptr, targets_per_query, out_scores, margin, out_loss);
+}
+
+// ---- host-buffer variants ------------------------------------------------------
+static int stage_reserve(gqe_ctx* c, int slot, size_t bytes) {
+  if (bytes <= c->stage_cap[slot]) return GQE_OK;
+  GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->stage[slot]);
+  c->stage[slot] = nullptr;
+  c->stage_cap[slot] = 0;
+  const size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 16);
+  GQE_CUDA(c, cudaMalloc(&c->stage[slot], cap));
+  c->stage_cap[slot] = cap;
+  return GQE_OK;
+}
+enum { ST_ANCHOR = 0, ST_TARGET = 1, ST_OFFSETS = 2, ST_SCORES = 3, ST_LOSS = 4 };
+
+static int max_anchors(const gqe_segment* segs, int n) {
+  int m = 0;
+  for (int i = 0; i < n; ++i) m = std::max(m, n_anchors_of(segs[i].plan.structure));
+  return m;
+}
+
+static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_t nq, const int32_t* anchor_rows,
+                          int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets, int32_t T,
+                          float* out_scores, float margin, float* out_loss) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!segs || n_segs <= 0) return fail(c, GQE_ERR_INVALID, "no segments");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  const int na = max_anchors(segs, n_segs);
+  if (na <= 0) return fail(c, GQE_ERR_INVALID, "unknown query structure");
+  int rc;
+  if ((rc = stage_reserve(c, ST_ANCHOR, sizeof(int32_t) * (size_t)na * nq)) != GQE_OK) return rc;
+  if ((rc = stage_reserve(c, ST_TARGET, sizeof(int32_t) * (size_t)n_pairs)) != GQE_OK) return rc;
+  if (target_offsets && (rc = stage_reserve(c, ST_OFFSETS, sizeof(int64_t) * (size_t)(nq + 1))) != GQE_OK) return rc;
+  if (out_scores && (rc = stage_reserve(c, ST_SCORES, sizeof(float) * (size_t)n_pairs)) != GQE_OK) return rc;
+  if (out_loss && (rc = stage_reserve(c, ST_LOSS, sizeof(float))) != GQE_OK) return rc;
+  if (nq > 0) {
+    if (!anchor_rows || !target_rows) return fail(c, GQE_ERR_INVALID, "index arrays are null");
+    GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_ANCHOR], anchor_rows, sizeof(int32_t) * (size_t)na * nq,
+                                cudaMemcpyHostToDevice, c->stream));
+    GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_TARGET], target_rows, sizeof(int32_t) * (size_t)n_pairs,
+                                cudaMemcpyHostToDevice, c->stream));
+    if (target_offsets)
+      GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_OFFSETS], target_offsets, sizeof(int64_t) * (size_t)(nq + 1),
+                                  cudaMemcpyHostToDevice, c->stream));
+  }
+  rc = run_fused(c, segs, n_segs, nq, (const int32_t*)c->stage[ST_ANCHOR], n_pairs, (const int32_t*)c->stage[ST_TARGET],
+                 target_offsets ? (const int64_t*)c->stage[ST_OFFSETS] : nullptr, T,
+                 out_scores ? (float*)c->stage[ST_SCORES] : nullptr, margin, out_loss ? (float*)c->stage[ST_LOSS] : nullptr);
+  if (rc != GQE_OK) return rc;
+  if (out_scores && n_pairs > 0)
+    GQE_CUDA(c, cudaMemcpyAsync(out_scores, c->stage[ST_SCORES], sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost,
+                                c->stream));
+  if (out_loss)
+    GQE_CUDA(c, cudaMemcpyAsync(out_loss, c->stage[ST_LOSS], sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GQE_OK;
+}
+
+extern "C" int gqe_score_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                              int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets,
+                              float* out_scores) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!plan || !out_scores) return fail(c, GQE_ERR_INVALID, "gqe_score_host: null argument");
+  int32_t T;
+  int rc = regular_T(c, n_queries, n_pairs, target_offsets, &T);
+  if (rc != GQE_OK) return rc;
+  gqe_segment seg{*plan, 0, n_queries};
+  return run_fused_host(c, &seg, 1, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, T, out_scores, 0.f,
+                        nullptr);
+}
+
+extern "C" int gqe_margin_loss_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                                    const int32_t* pair_rows, float margin, float* out_loss, float* out_scores) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!plan || !out_loss) return fail(c, GQE_ERR_INVALID, "gqe_margin_loss_host: null argument");
+  gqe_segment seg{*plan, 0, n_queries};
+  return run_fused_host(c, &seg, 1, n_queries, anchor_rows, 2 * n_queries, pair_rows, nullptr, 2, out_scores, margin,
+                        out_loss);
+}
+
+extern "C" int gqe_score_grouped_host(gqe_ctx* c, const gqe_segment* segments, int32_t n_segments,
+                                      int64_t n_queries_total, const int32_t* anchor_rows, const int32_t* target_rows,
+                                      int32_t targets_per_query, float* out_scores, float margin, float* out_loss) {
+  if (!c) return GQE_ERR_INVALID;
+  // grouped anchors are always laid out with GQE_MAX_ANCHORS slots
+  if (!segments || n_segments <= 0) return fail(c, GQE_ERR_INVALID, "no segments");
+  return run_fused_host(c, segments, n_segments, n_queries_total, anchor_rows, n_queries_total * targets_per_query,
+                        target_rows, nullptr, targets_per_query, out_scores, margin, out_loss);
+}
+
+// ---- operator-level entry points -------------------------------------------------
+template <int D>
+static cudaError_t launch_op_d(const OpParams& op, cudaStream_t st) {
+  static bool configured[64] = {false};
+  auto kern = gqe_op_simt<D>;
+  const int dev = current_device();
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<D>));
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  const int64_t grid = (op.n + kTileRows - 1) / kTileRows;
+  kern<<<(unsigned)grid, kThreads, sizeof(TileSmem<D>), st>>>(op);
+  return cudaGetLastError();
+}
+
+static int launch_op(gqe_ctx* c, int d, const OpParams& op) {
+  if (op.n == 0) return GQE_OK;
+  if (op.n < 0) return fail(c, GQE_ERR_INVALID, "negative column count");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  cudaError_t e;
+  switch (d) {
+    case 32: e = launch_op_d<32>(op, c->stream); break;
+    case 64: e = launch_op_d<64>(op, c->stream); break;
+    case 128: e = launch_op_d<128>(op, c->stream); break;
+    case 256: e = launch_op_d<256>(op, c->stream); break;
+    default: return fail(c, GQE_ERR_UNSUPPORTED, "dimension %d not supported (32/64/128/256)", d);
+  }
+  if (e != cudaSuccess) return fail(c, GQE_ERR_CUDA, "operator launch failed: %s", cudaGetErrorString(e));
+  c->launches += 1;
+  return GQE_OK;
+}
+
+extern "C" int gqe_encode_device(gqe_ctx* c, int32_t mode, int64_t n, const int32_t* rows, float* out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (c->tables.empty()) return fail(c, GQE_ERR_UNBOUND, "embedding tables are not bound");
+  if (mode < 0 || mode >= (int)c->tables.size()) return fail(c, GQE_ERR_INVALID, "mode %d out of range", mode);
+  if (n > 0 && (!rows || !out)) return fail(c, GQE_ERR_INVALID, "gqe_encode_device: null argument");
+  OpParams op;
+  std::memset(&op, 0, sizeof op);
+  op.op = OP_ENCODE;
+  op.n = n;
+  op.table = c->tables[mode];
+  op.rows = rows;
+  op.out = out;
+  return launch_op(c, c->d, op);
+}
+
+extern "C" int gqe_project_device(gqe_ctx* c, int32_t rel, int64_t n, const float* in, float* out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (c->rels.empty()) return fail(c, GQE_ERR_UNBOUND, "relation parameters are not bound");
+  if (rel < 0 || rel >= (int)c->rels.size()) return fail(c, GQE_ERR_INVALID, "relation id %d out of range", rel);
+  if (n > 0 && (!in || !out)) return fail(c, GQE_ERR_INVALID, "gqe_project_device: null argument");
+  OpParams op;
+  std::memset(&op, 0, sizeof op);
+  op.op = OP_PROJECT;
+  op.decoder = c->decoder;
+  op.n = n;
+  op.rel[0] = c->rels[rel];
+  op.in0 = in;
+  op.out = out;
+  return launch_op(c, c->rel_d, op);
+}
+
+extern "C" int gqe_path_score_device(gqe_ctx* c, int32_t n_rels, const int32_t* rels, int64_t n, float* embeds1,
+                                     const float* embeds2, int32_t mutate_embeds1, float* out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (c->rels.empty()) return fail(c, GQE_ERR_UNBOUND, "relation parameters are not bound");
+  if (n_rels < 1 || n_rels > GQE_MAX_RELS || !rels) return fail(c, GQE_ERR_INVALID, "metapath must have 1..3 relations");
+  if (n > 0 && (!embeds1 || !embeds2 || !out)) return fail(c, GQE_ERR_INVALID, "gqe_path_score_device: null argument");
+  OpParams op;
+  std::memset(&op, 0, sizeof op);
+  op.op = OP_PATH_SCORE;
+  op.decoder = c->decoder;
+  op.n_rels = n_rels;
+  op.mutate = mutate_embeds1;
+  op.n = n;
+  for (int k = 0; k < n_rels; ++k) {
+    if (rels[k] < 0 || rels[k] >= (int)c->rels.size()) return fail(c, GQE_ERR_INVALID, "relation id %d out of range", rels[k]);
+    op.rel[k] = c->rels[rels[k]];
+  }
+  op.io0 = embeds1;
+  op.in1 = embeds2;
+  op.out = out;
+  return launch_op(c, c->rel_d, op);
+}
+
+extern "C" int gqe_intersect_device(gqe_ctx* c, int32_t mode, int64_t n, const float* e1, const float* e2,
+                                    const float* e3, float* out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (c->inter < 0) return fail(c, GQE_ERR_UNBOUND, "intersection operator is not bound");
+  if (n > 0 && (!e1 || !e2 || !out)) return fail(c, GQE_ERR_INVALID, "gqe_intersect_device: null argument");
+  OpParams op;
+  std::memset(&op, 0, sizeof op);
+  op.op = OP_INTERSECT;
+  op.inter = c->inter;
+  op.n = n;
+  if (c->inter <= GQE_INTER_DEEPSETS_MIN) {
+    if (mode < 0 || mode >= (int)c->pre.size()) return fail(c, GQE_ERR_INVALID, "intersection mode %d out of range", mode);
+    op.pre = c->pre[mode];
+    op.post = c->post[mode];
+  }
+  op.in0 = e1;
+  op.in1 = e2;
+  op.in2 = e3;
+  op.out = out;
+  return launch_op(c, c->inter_d, op);
+}
+
+extern "C" int gqe_cosine_device(gqe_ctx* c, int32_t d, int64_t n, const float* x, const float* y, float* out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (n > 0 && (!x || !y || !out)) return fail(c, GQE_ERR_INVALID, "gqe_cosine_device: null argument");
+  OpParams op;
+  std::memset(&op, 0, sizeof op);
+  op.op = OP_COSINE;
+  op.n = n;
+  op.in0 = x;
+  op.in1 = y;
+  op.out = out;
+  return launch_op(c, d, op);
+}

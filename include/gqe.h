@@ -1,0 +1,217 @@
+/*
+ * gqe.h -- C ABI of the B200-native conjunctive-query scorer.
+ *
+ * This is the drop-in boundary for ONE path of williamleif/graphqembed
+ * ("netquery"): the batched forward scoring of conjunctive graph queries and
+ * its margin loss.  The reference has no FFI of its own (it is pure Python on
+ * top of torch); what a maintainer would bind are the operator methods below.
+ * Each entry point names the reference interface it replaces (file:line under
+ * the reference tree).  See INTEGRATION.md for the ctypes stubs.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked DEVICE is a CUDA device
+ *     pointer on the context's device, every pointer marked HOST is host
+ *     memory (pinned for true async, pageable works).
+ *   - all work is enqueued on the context's stream; *_device entry points do
+ *     not synchronise, *_host entry points return after their result landed.
+ *   - return value: GQE_OK (0) or a negative gqe_status; the message of the
+ *     last failure on a context is kept in gqe_last_error().
+ *   - "row" always means a row of a mode's embedding table, i.e. the value
+ *     node_maps[mode][node] + 1 of reference netquery/bio/data_utils.py:20-21.
+ *   - "relation id" is the position of the canonical triple
+ *     (from_mode, name, to_mode) in the decoder's registration order,
+ *     reference netquery/decoders.py:135-137.
+ *   - embeddings exchanged by the operator-level calls are FEATURE-MAJOR
+ *     [d, n] fp32 (reference layout: encoders.py:41, decoders.py:150).
+ *   - there is no CPU fallback anywhere behind this header.
+ */
+#ifndef GQE_H_
+#define GQE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GQE_ABI_VERSION 1
+#define GQE_MAX_ANCHORS 3
+#define GQE_MAX_RELS 3
+
+typedef enum gqe_status {
+  GQE_OK = 0,
+  GQE_ERR_INVALID = -1,      /* bad argument (null pointer, negative size, unknown enum) */
+  GQE_ERR_UNBOUND = -2,      /* tables / relations / intersection not bound yet */
+  GQE_ERR_UNSUPPORTED = -3,  /* dimension or combination this build has no kernel for */
+  GQE_ERR_CUDA = -4,         /* a CUDA runtime call failed; see gqe_last_error */
+  GQE_ERR_NOMEM = -5
+} gqe_status;
+
+/* Query structures of reference netquery/model.py:70-109. */
+typedef enum gqe_structure {
+  GQE_CHAIN1 = 0,       /* "1-chain"       model.py:71-76  */
+  GQE_CHAIN2 = 1,       /* "2-chain"                       */
+  GQE_CHAIN3 = 2,       /* "3-chain"                       */
+  GQE_INTER2 = 3,       /* "2-inter"       model.py:77-98  */
+  GQE_INTER3 = 4,       /* "3-inter"                       */
+  GQE_INTER_CHAIN3 = 5, /* "3-inter_chain" model.py:83-86  */
+  GQE_CHAIN_INTER3 = 6  /* "3-chain_inter" model.py:99-109 */
+} gqe_structure;
+
+/* Metapath decoders selectable by reference netquery/utils.py:128-137. */
+typedef enum gqe_decoder {
+  GQE_DEC_BILINEAR = 0, /* BilinearMetapathDecoder      decoders.py:123-150, params [R,d,d] */
+  GQE_DEC_TRANSE = 1,   /* TransEMetapathDecoder        decoders.py:181-208, params [R,d]   */
+  GQE_DEC_DISTMULT = 2  /* BilinearDiagMetapathDecoder  decoders.py:211-236, params [R,d]   */
+} gqe_decoder;
+
+/* Intersection operators selectable by reference netquery/utils.py:139-150. */
+typedef enum gqe_inter {
+  GQE_INTER_DEEPSETS_MEAN = 0, /* SetIntersection(agg=mean)       decoders.py:270-300 */
+  GQE_INTER_DEEPSETS_MIN = 1,  /* SetIntersection(agg=min)                            */
+  GQE_INTER_SIMPLE_MEAN = 2,   /* SimpleSetIntersection(agg=mean) decoders.py:302-319 */
+  GQE_INTER_SIMPLE_MIN = 3     /* SimpleSetIntersection(agg=min)                      */
+} gqe_inter;
+
+/*
+ * A lowered Formula (reference netquery/graph.py:11-36): which table feeds
+ * which operand and which relation parameter is applied in which order.
+ * rel[] is in APPLICATION order, which is exactly the order in which the
+ * reference touches its parameter dict:
+ *   chains          rel[0..n-1] = r1..rn, applied to the TARGET (decoders.py:143-145)
+ *   2/3-inter       rel[k] = reverse(r_k), applied to anchor k (model.py:81,88,92)
+ *   3-inter_chain   rel[0] = reverse(r1) on anchor 0;
+ *                   rel[1] = reverse(r2b) then rel[2] = reverse(r2a) on anchor 1
+ *                   (model.py:84-86 walks rels[1][::-1])
+ *   3-chain_inter   rel[0] = reverse(r2a) on anchor 0, rel[1] = reverse(r2b) on
+ *                   anchor 1, rel[2] = reverse(r1) applied after the
+ *                   intersection (model.py:102-107)
+ * inter_mode is the mode whose pre/post matrices are used: the target mode, or
+ * for 3-chain_inter the intermediate node's mode (model.py:106); -1 for chains.
+ */
+typedef struct gqe_plan {
+  int32_t structure;                    /* gqe_structure */
+  int32_t target_mode;
+  int32_t anchor_mode[GQE_MAX_ANCHORS]; /* unused slots: -1 */
+  int32_t inter_mode;
+  int32_t rel[GQE_MAX_RELS];            /* unused slots: -1 */
+} gqe_plan;
+
+/* One formula's slice of a grouped (multi-formula) batch: queries
+ * [query_begin, query_end) of the concatenated index arrays. */
+typedef struct gqe_segment {
+  gqe_plan plan;
+  int64_t query_begin;
+  int64_t query_end;
+} gqe_segment;
+
+typedef struct gqe_ctx gqe_ctx;
+
+/* ---- context ----------------------------------------------------------- */
+int gqe_abi_version(void);
+/* stream: a cudaStream_t (NULL = the legacy default stream of `device`). */
+int gqe_create(int device, void* stream, gqe_ctx** out);
+void gqe_destroy(gqe_ctx* ctx);
+int gqe_set_stream(gqe_ctx* ctx, void* stream);
+/* Message of the last failure on ctx (ctx == NULL: last gqe_create failure). */
+const char* gqe_last_error(const gqe_ctx* ctx);
+/* Number of kernels this context has launched so far (bench bookkeeping). */
+int64_t gqe_launch_count(const gqe_ctx* ctx);
+
+/* ---- parameter binding (no copies: the pointers alias the owner's storage,
+ *      so in-place optimiser updates are seen by the next call) -------------
+ * Replaces: the `features` closure + nn.Embedding tables of reference
+ * netquery/bio/data_utils.py:16-21 (one [rows, d] fp32 table per mode). */
+int gqe_bind_tables(gqe_ctx* ctx, int32_t n_modes, const float* const* tables /*HOST array of DEVICE ptrs*/,
+                    const int64_t* rows /*HOST [n_modes]*/, int32_t d);
+/* Replaces: the `mats` / `vecs` parameter dicts of reference
+ * netquery/decoders.py:129-140,188-197,217-226.  params[r] is [d,d] row-major
+ * (bilinear) or [d] (transe / distmult). */
+int gqe_bind_relations(gqe_ctx* ctx, int32_t decoder /*gqe_decoder*/, int32_t n_rels,
+                       const float* const* params /*HOST array of DEVICE ptrs*/, int32_t d);
+/* Replaces: `pre_mats` / `post_mats` of reference netquery/decoders.py:275-286
+ * (pre[m]: [d_exp, d], post[m]: [d, d_exp], row-major; d_exp must equal d, as
+ * reference netquery/utils.py:141 constructs it).  For the SIMPLE kinds pass
+ * NULL arrays. */
+int gqe_bind_intersection(gqe_ctx* ctx, int32_t inter /*gqe_inter*/, int32_t n_modes,
+                          const float* const* pre, const float* const* post /*HOST arrays of DEVICE ptrs*/,
+                          int32_t d, int32_t d_expand);
+
+/* ---- the fused hot path --------------------------------------------------
+ * gqe_score_device replaces QueryEncoderDecoder.forward (reference
+ * netquery/model.py:70-109) for one formula.
+ *   anchor_rows   DEVICE int32 [n_anchors][n_queries] (anchor k of query q at k*n_queries+q)
+ *   target_rows   DEVICE int32 [n_pairs]; the targets of query q are
+ *                 target_rows[target_offsets[q] .. target_offsets[q+1]) or, when
+ *                 target_offsets == NULL, the regular layout
+ *                 target_rows[q*T .. (q+1)*T) with T = n_pairs / n_queries
+ *   target_offsets DEVICE int64 [n_queries+1] (offsets[0] == 0,
+ *                 offsets[n_queries] == n_pairs, non-decreasing) or NULL
+ *   out_scores    DEVICE fp32 [n_pairs], same order as target_rows
+ * The query side (anchors, projections, intersection) is evaluated ONCE per
+ * query however many targets it is scored against (the reference re-evaluates
+ * it per pair: model.py:122-123, utils.py:58-60,86-88). */
+int gqe_score_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries,
+                     const int32_t* anchor_rows, int64_t n_pairs, const int32_t* target_rows,
+                     const int64_t* target_offsets, float* out_scores);
+
+/* gqe_margin_loss_device replaces QueryEncoderDecoder.margin_loss (reference
+ * netquery/model.py:112-127) once the negatives are chosen: per query one
+ * positive and one negative target row,
+ *   loss = mean_q max(0, margin - (score(q,pos) - score(q,neg))).
+ *   pair_rows   DEVICE int32 [n_queries][2] (positive, negative)
+ *   out_loss    DEVICE fp32 [1]
+ *   out_scores  DEVICE fp32 [n_queries][2] or NULL
+ * The reduction order is fixed (deterministic result). */
+int gqe_margin_loss_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries,
+                           const int32_t* anchor_rows, const int32_t* pair_rows,
+                           float margin, float* out_loss, float* out_scores);
+
+/* Grouped variant: many formulas in one call (the "full mix" workload).
+ *   segments      HOST array; segment s owns queries [query_begin, query_end)
+ *   anchor_rows   DEVICE int32 [GQE_MAX_ANCHORS][n_queries_total]
+ *   target_rows   DEVICE int32 [n_queries_total][targets_per_query]
+ *   out_scores    DEVICE fp32 [n_queries_total][targets_per_query] or NULL when out_loss given
+ *   out_loss      DEVICE fp32 [1] or NULL; requires targets_per_query == 2; mean over ALL queries */
+int gqe_score_grouped_device(gqe_ctx* ctx, const gqe_segment* segments, int32_t n_segments,
+                             int64_t n_queries_total, const int32_t* anchor_rows,
+                             const int32_t* target_rows, int32_t targets_per_query,
+                             float* out_scores, float margin, float* out_loss);
+
+/* Host-buffer variants: same semantics, HOST index arrays in, HOST results
+ * out; the H2D / D2H copies and a stream synchronise happen inside the call.
+ * This is the call a non-torch host (the reference's own CPU pipeline) makes. */
+int gqe_score_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries,
+                   const int32_t* anchor_rows, int64_t n_pairs, const int32_t* target_rows,
+                   const int64_t* target_offsets, float* out_scores);
+int gqe_margin_loss_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries,
+                         const int32_t* anchor_rows, const int32_t* pair_rows,
+                         float margin, float* out_loss, float* out_scores);
+int gqe_score_grouped_host(gqe_ctx* ctx, const gqe_segment* segments, int32_t n_segments,
+                           int64_t n_queries_total, const int32_t* anchor_rows,
+                           const int32_t* target_rows, int32_t targets_per_query,
+                           float* out_scores, float margin, float* out_loss);
+
+/* ---- operator-level entry points (the un-fused reference surface) -------
+ * All embeddings are DEVICE fp32 feature-major [d, n]. */
+/* DirectEncoder.forward (reference netquery/encoders.py:29-43): gather rows of
+ * `mode`, L2-normalise each column (no epsilon). */
+int gqe_encode_device(gqe_ctx* ctx, int32_t mode, int64_t n, const int32_t* rows /*DEVICE*/, float* out);
+/* *MetapathDecoder.project (decoders.py:149-150,207-208,235-236). out may alias in. */
+int gqe_project_device(gqe_ctx* ctx, int32_t rel, int64_t n, const float* in, float* out);
+/* *MetapathDecoder.forward (decoders.py:142-147,200-205,228-233).  For TransE
+ * the reference translates embeds1 in place (decoders.py:203); set
+ * mutate_embeds1 != 0 to reproduce that side effect. */
+int gqe_path_score_device(gqe_ctx* ctx, int32_t n_rels, const int32_t* rels /*HOST*/, int64_t n,
+                          float* embeds1, const float* embeds2, int32_t mutate_embeds1, float* out /*[n]*/);
+/* SetIntersection.forward / SimpleSetIntersection.forward (decoders.py:288-300,311-319).
+ * embeds3 may be NULL (two operands). */
+int gqe_intersect_device(gqe_ctx* ctx, int32_t mode, int64_t n, const float* embeds1,
+                         const float* embeds2, const float* embeds3, float* out);
+/* nn.CosineSimilarity(dim=0, eps=1e-8) as used at model.py:68,97,108. */
+int gqe_cosine_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* x, const float* y, float* out /*[n]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GQE_H_ */

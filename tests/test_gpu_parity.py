@@ -1,0 +1,359 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the
+frozen reference outputs.  Tolerances: the north star allows 1e-4 on cosine
+scores; the exact-fp32 kernels are held to 2e-5 (observed ~1e-6)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import graphqembed_b200 as gqe
+from graphqembed_b200.synth import STRUCTURES, bio_shaped
+from helpers import GOLDEN_FILES, GOLDEN_IDS, LOSS_SEED, build_package_model, load_golden, query_batch
+from oracle.cases import DECODERS, INTERS, make_case
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5          # exact-fp32 path
+NORTH_STAR_TOL = 1e-4
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=GOLDEN_IDS)
+def test_golden_reference_outputs(path):
+    """forward / eval-shaped forward / margin_loss vs outputs of the real reference."""
+    case, exp = load_golden(path)
+    model = build_package_model(case)
+    for s in case.batches:
+        f = case.formula(s, cls=gqe.Formula)
+        qs = case.queries(s, cls=gqe.Query)
+        b = case.batches[s]
+        pos = _np(model.forward(f, qs, [q.target_node for q in qs]))
+        neg = _np(model.forward(f, qs, [int(x) for x in b["negs"][:, 0]]))
+        np.testing.assert_allclose(pos, exp[s + "/pos"], rtol=0, atol=TOL, err_msg=s)
+        np.testing.assert_allclose(neg, exp[s + "/neg"], rtol=0, atol=TOL, err_msg=s)
+        rep = [q for q in qs for _ in q.neg_samples]
+        ev = _np(model.forward(f, qs + rep, [q.target_node for q in qs] + [n for q in qs for n in q.neg_samples]))
+        np.testing.assert_allclose(ev, exp[s + "/eval"], rtol=0, atol=TOL, err_msg=s)
+        random.seed(LOSS_SEED)
+        loss = model.margin_loss(f, qs).item()
+        assert abs(loss - float(exp[s + "/loss"])) <= TOL, s
+        if "inter" in s:
+            random.seed(LOSS_SEED)
+            hard = model.margin_loss(f, qs, hard_negatives=True).item()
+            assert abs(hard - float(exp[s + "/hard"])) <= TOL, s
+
+
+# ---------------------------------------------------------------------------
+def _oracle_scores(case, orc, s, targets):
+    """Oracle scores for targets [Q, T] -> [Q, T] (one forward per target slot)."""
+    qs = case.queries(s)
+    f = case.formula(s)
+    cols = [orc.forward(f, qs, [int(x) for x in targets[:, j]]).numpy() for j in range(targets.shape[1])]
+    return np.stack(cols, axis=1)
+
+
+@pytest.mark.parametrize("d", [32, 64, 128, 256])
+@pytest.mark.parametrize("decoder", DECODERS)
+@pytest.mark.parametrize("inter", INTERS)
+def test_random_cases_vs_oracle(d, decoder, inter):
+    if d in (32, 64) and inter in ("min", "mean-simple") and decoder != "bilinear":
+        pytest.skip("covered by the other dimensions")
+    nq = 203 if d < 256 else 131          # not a multiple of the 64-row tile
+    case = make_case(seed=d + len(decoder) + len(inter), d=d, decoder=decoder, inter=inter, n_queries=nq, n_neg=3,
+                     nodes_per_mode=500)
+    model = build_package_model(case)
+    orc = case.oracle()
+    for s in case.batches:
+        b = case.batches[s]
+        targets = np.concatenate([b["target"][:, None], b["negs"]], axis=1)      # [Q, 4]
+        want = _oracle_scores(case, orc, s, targets)
+        got = _np(model.score_batch(query_batch(case, s, targets))).reshape(nq, -1)
+        np.testing.assert_allclose(got, want, rtol=0, atol=TOL, err_msg="%s %s %s d=%d" % (s, decoder, inter, d))
+        # fused loss on (positive, first negative)
+        loss, sc = model.margin_loss_batch(query_batch(case, s, targets[:, :2]), margin=1, return_scores=True)
+        want_loss = np.maximum(0.0, 1.0 - (want[:, 0] - want[:, 1])).mean()
+        assert abs(loss.item() - want_loss) <= TOL, s
+        np.testing.assert_allclose(_np(sc), want[:, :2], rtol=0, atol=TOL)
+
+
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def small():
+    case = make_case(seed=77, d=64, decoder="bilinear", inter="mean", n_queries=130, n_neg=4, nodes_per_mode=300)
+    return case, build_package_model(case), case.oracle()
+
+
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 128, 130])
+def test_batch_sizes_around_the_tile(small, n):
+    case, model, orc = small
+    for s in ("1-chain", "3-chain", "2-inter", "3-inter_chain", "3-chain_inter"):
+        b = case.batches[s]
+        f = case.formula(s, cls=gqe.Formula)
+        batch = gqe.QueryBatch(f, b["anchors"][:, :n], np.stack([b["target"][:n], b["negs"][:n, 0]], 1).reshape(-1))
+        scores = _np(model.score_batch(batch)).reshape(n, 2)
+        loss = model.margin_loss_batch(batch).item()
+        if n == 0:
+            assert scores.size == 0 and np.isnan(loss)     # torch: mean of an empty tensor
+            continue
+        qs = case.queries(s)[:n]
+        want = np.stack([orc.forward(case.formula(s), qs, [q.target_node for q in qs]).numpy(),
+                         orc.forward(case.formula(s), qs, [int(x) for x in b["negs"][:n, 0]]).numpy()], 1)
+        np.testing.assert_allclose(scores, want, rtol=0, atol=TOL)
+        assert abs(loss - np.maximum(0, 1 - (want[:, 0] - want[:, 1])).mean()) <= TOL
+
+
+def test_ragged_targets_including_empty_lists(small):
+    case, model, orc = small
+    rng = np.random.RandomState(5)
+    for s in ("2-chain", "3-inter"):
+        b = case.batches[s]
+        nq = 100
+        counts = rng.randint(0, 6, size=nq)
+        counts[::7] = 0
+        offsets = np.concatenate([[0], np.cumsum(counts)])
+        tmode = case.formula(s).target_mode
+        targets = case.kg.sample_nodes(tmode, int(offsets[-1]), rng)
+        batch = gqe.QueryBatch(case.formula(s, cls=gqe.Formula), b["anchors"][:, :nq], targets, offsets)
+        got = _np(model.score_batch(batch))
+        qs = case.queries(s)[:nq]
+        rep = [q for q, c in zip(qs, counts) for _ in range(c)]
+        want = orc.forward(case.formula(s), rep, [int(t) for t in targets]).numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=TOL)
+
+
+def test_zero_row_is_nan_like_reference():
+    case = make_case(seed=78, d=32, decoder="bilinear", inter="min", n_queries=70, n_neg=1, nodes_per_mode=50)
+    s = "3-inter"
+    f = case.formula(s)
+    b = case.batches[s]
+    # zero one anchor row and one target row
+    nm = case.kg.node_maps()
+    case.tables[f.anchor_modes[1]][nm[f.anchor_modes[1]][int(b["anchors"][1, 3])] + 1].zero_()
+    case.tables[f.target_mode][nm[f.target_mode][int(b["target"][10])] + 1].zero_()
+    model = build_package_model(case)
+    qs = case.queries(s)
+    want = case.oracle().forward(f, qs, [q.target_node for q in qs]).numpy()
+    got = _np(model.score_batch(query_batch(case, s, b["target"])))
+    assert np.isnan(want[3]) and np.isnan(want[10])
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=TOL)
+    loss = model.margin_loss_batch(query_batch(case, s, np.stack([b["target"], b["negs"][:, 0]], 1))).item()
+    assert np.isnan(loss)       # torch.clamp / mean propagate NaN (model.py:125-126)
+
+
+def test_error_conventions(small):
+    case, model, _ = small
+    f = case.formula("2-chain", cls=gqe.Formula)
+    qs = case.queries("2-chain", cls=gqe.Query)
+    with pytest.raises(Exception, match="Hard negative examples can only be used with intersection queries"):
+        model.margin_loss(f, qs, hard_negatives=True)
+    weird = gqe.Formula("2-chain", f.rels)
+    weird.query_type = "5-chain"
+    assert model.forward(weird, qs, [q.target_node for q in qs]) is None
+    bad = gqe.Formula("1-chain", (("m0", "nope", "m1"),))
+    with pytest.raises(KeyError):
+        model.forward(bad, qs[:2], [1, 2])
+    cpu_model = build_package_model(case, device=None)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cpu_model.forward(f, qs, [q.target_node for q in qs])
+
+
+def test_unsupported_dimension_is_an_error_not_a_fallback():
+    case = make_case(seed=1, d=48, decoder="bilinear", inter="mean", n_queries=4, n_neg=1)
+    model = build_package_model(case)
+    with pytest.raises(gqe.GqeError, match="not supported"):
+        model.score_batch(query_batch(case, "1-chain", case.batches["1-chain"]["target"]))
+
+
+# ---------------------------------------------------------------------------
+def test_grouped_launch_matches_per_formula_calls():
+    case = make_case(seed=79, d=128, decoder="bilinear", inter="mean", n_queries=150, n_neg=1, nodes_per_mode=400)
+    model = build_package_model(case)
+    batches, per_scores, per_n = [], [], []
+    rng = np.random.RandomState(3)
+    for rep in range(3):                     # 21 segments > 16: exercises the multi-launch split
+        for s in STRUCTURES:
+            b = case.batches[s]
+            n = int(rng.randint(1, 150))
+            f = case.formula(s, cls=gqe.Formula)
+            qb = gqe.QueryBatch(f, b["anchors"][:, :n], np.stack([b["target"][:n], b["negs"][:n, 0]], 1).reshape(-1))
+            batches.append(qb)
+            per_scores.append(_np(model.score_batch(qb)).reshape(n, 2))
+            per_n.append(n)
+    loss, scores = model.margin_loss_grouped(batches, margin=1, return_scores=True)
+    want = np.concatenate(per_scores)
+    np.testing.assert_array_equal(_np(scores), want)           # same kernels, same arithmetic
+    want_loss = np.maximum(0, 1 - (want[:, 0] - want[:, 1])).mean()
+    assert abs(loss.item() - want_loss) <= 1e-6
+    loss_only = model.margin_loss_grouped(batches, margin=1)
+    assert loss_only.item() == loss.item()                     # deterministic reduction
+
+
+def test_host_buffer_entry_points_match_device_ones(small):
+    case, model, _ = small
+    ctx = model.context()
+    for s in ("3-chain", "3-inter"):
+        b = case.batches[s]
+        batch = query_batch(case, s, np.stack([b["target"], b["negs"][:, 0]], 1))
+        plan = model.plan(batch.formula)
+        a, t = model.lower_batch(batch)
+        dev = _np(model.score_batch(batch))
+        out = np.empty(batch.n_pairs, dtype=np.float32)
+        ctx.score_host(plan, a, t, None, out)
+        np.testing.assert_array_equal(out, dev)
+        loss = np.empty(1, dtype=np.float32)
+        sc = np.empty(batch.n_pairs, dtype=np.float32)
+        ctx.margin_loss_host(plan, a, t, 1.0, loss, sc)
+        assert loss[0] == model.margin_loss_batch(batch).item()
+        np.testing.assert_array_equal(sc, dev)
+        segs = gqe.make_segments([(plan, 0, batch.n_queries)])
+        a3 = np.zeros((3, batch.n_queries), dtype=np.int32)
+        a3[:a.shape[0]] = a
+        loss2 = np.empty(1, dtype=np.float32)
+        ctx.score_grouped_host(segs, a3, t, 2, None, 1.0, loss2)
+        assert loss2[0] == loss[0]
+        # ragged through the host entry
+        offsets = np.arange(batch.n_queries + 1, dtype=np.int64) * 2
+        out2 = np.empty(batch.n_pairs, dtype=np.float32)
+        ctx.score_host(plan, a, t, offsets, out2)
+        np.testing.assert_array_equal(out2, dev)
+
+
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("decoder", DECODERS)
+@pytest.mark.parametrize("inter", INTERS)
+def test_operator_surface(decoder, inter):
+    """DirectEncoder.forward / decoder.project / decoder.forward / intersection.forward."""
+    case = make_case(seed=31, d=64, decoder=decoder, inter=inter, n_queries=90, n_neg=1, nodes_per_mode=200)
+    model = build_package_model(case)
+    orc = case.oracle()
+    f = case.formula("3-inter")
+    b = case.batches["3-inter"]
+    nodes = [int(x) for x in b["anchors"][0]]
+    e_ref = orc.encode(nodes, f.anchor_modes[0])
+    e = model.enc.forward(nodes, f.anchor_modes[0])
+    assert tuple(e.shape) == (64, 90)
+    np.testing.assert_allclose(_np(e), e_ref.numpy(), rtol=0, atol=1e-6)
+    rel = gqe.reverse_relation(f.rels[0])
+    p = model.path_dec.project(e, rel)
+    np.testing.assert_allclose(_np(p), orc.project(e_ref, rel).numpy(), rtol=0, atol=TOL)
+    e2_ref = orc.encode([int(x) for x in b["anchors"][1]], f.anchor_modes[1])
+    e3_ref = orc.encode([int(x) for x in b["anchors"][2]], f.anchor_modes[2])
+    e2, e3 = e2_ref.contiguous().cuda(), e3_ref.contiguous().cuda()
+    for parts_ref, parts in (((e_ref, e2_ref), (e, e2)), ((e_ref, e2_ref, e3_ref), (e, e2, e3))):
+        want = orc.intersect(parts_ref[0], parts_ref[1], f.target_mode, parts_ref[2] if len(parts_ref) == 3 else None)
+        got = model.inter_dec.forward(parts[0], parts[1], f.target_mode, *parts[2:])
+        np.testing.assert_allclose(_np(got), want.numpy(), rtol=0, atol=TOL)
+    # metapath score on a 2-chain's relations
+    cf = case.formula("2-chain")
+    cb = case.batches["2-chain"]
+    t_ref = orc.encode([int(x) for x in cb["target"]], cf.target_mode)
+    a_ref = orc.encode([int(x) for x in cb["anchors"][0]], cf.anchor_modes[0])
+    t_dev, a_dev = t_ref.contiguous().cuda(), a_ref.contiguous().cuda()
+    before = t_dev.clone()
+    got = model.path_dec.forward(t_dev, a_dev, cf.rels)
+    want = orc.path_score(t_ref.clone(), a_ref, cf.rels)
+    np.testing.assert_allclose(_np(got), want.numpy(), rtol=0, atol=TOL)
+    if decoder == "transe":     # the reference translates embeds1 in place (decoders.py:203)
+        moved = t_ref.clone()
+        orc.path_score(moved, a_ref, cf.rels)
+        np.testing.assert_allclose(_np(t_dev), moved.numpy(), rtol=0, atol=1e-6)
+    else:
+        assert torch.equal(t_dev, before)
+    with pytest.raises(KeyError):
+        model.path_dec.project(e, ("m0", "missing", "m0"))
+
+
+def test_state_dict_names_match_reference_contract():
+    case = make_case(seed=32, d=32, decoder="bilinear", inter="mean", n_queries=4, n_neg=1)
+    model = build_package_model(case)
+    keys = set(model.state_dict().keys())
+    for m in case.kg.modes:
+        assert "enc.feat-%s.weight" % m in keys                 # encoders.py:25-26
+        assert "inter_dec.%s_premat" % m in keys                # decoders.py:283
+        assert "inter_dec.%s_postmat" % m in keys               # decoders.py:286
+    for rel in case.kg.rel_keys:
+        assert "path_dec." + "_".join(rel) in keys              # decoders.py:140
+    assert len(keys) == 3 * len(case.kg.modes) + len(case.kg.rel_keys)
+
+
+def test_in_place_parameter_updates_are_seen(small):
+    case, model, _ = small
+    s = "2-inter"
+    batch = query_batch(case, s, case.batches[s]["target"])
+    before = _np(model.score_batch(batch)).copy()
+    rel = gqe.reverse_relation(case.formula(s).rels[0])
+    with torch.no_grad():
+        model.path_dec.mats[rel].mul_(-1.0)
+    after = _np(model.score_batch(batch))
+    assert np.abs(after - before).max() > 1e-3
+    with torch.no_grad():
+        model.path_dec.mats[rel].mul_(-1.0)
+    np.testing.assert_array_equal(_np(model.score_batch(batch)), before)
+
+
+# ---------------------------------------------------------------------------
+def test_full_size_mix_properties():
+    """BASELINE config 4 shape (Bio-shaped KG, d=256, 65 536 queries, six structures):
+    size-independent properties + a sub-sample against the oracle."""
+    d, total = 256, 65536
+    kg = bio_shaped(seed=0)
+    structures = STRUCTURES[:6]
+    case = make_case(seed=5, d=d, decoder="bilinear", inter="mean", n_queries=total // 6 + 1, n_neg=1, kg=kg,
+                     structures=structures)
+    model = build_package_model(case)
+    batches = []
+    for s in structures:
+        b = case.batches[s]
+        batches.append(query_batch(case, s, np.stack([b["target"], b["negs"][:, 0]], 1)))
+    loss1, sc1 = model.margin_loss_grouped(batches, return_scores=True)
+    loss2, sc2 = model.margin_loss_grouped(batches, return_scores=True)
+    assert torch.equal(sc1, sc2) and loss1.item() == loss2.item()             # idempotent / deterministic
+    sc = _np(sc1)
+    assert np.isfinite(sc).all() and np.abs(sc).max() <= 1.0 + 1e-5            # cosines
+    hinge = np.maximum(0.0, 1.0 - (sc[:, 0].astype(np.float64) - sc[:, 1])).mean()
+    assert abs(loss1.item() - hinge) <= 1e-6                                   # fused loss == mean hinge of scores
+    # permutation equivariance inside one formula
+    qb = batches[4]
+    perm = np.random.RandomState(0).permutation(qb.n_queries)
+    shuffled = gqe.QueryBatch(qb.formula, qb.anchors[:, perm], qb.targets.reshape(-1, 2)[perm].reshape(-1))
+    a = _np(model.score_batch(qb)).reshape(-1, 2)
+    b2 = _np(model.score_batch(shuffled)).reshape(-1, 2)
+    np.testing.assert_array_equal(a[perm], b2)
+    # sub-sample of every structure against the oracle
+    orc = case.oracle()
+    q0 = 0
+    for s, qb in zip(structures, batches):
+        idx = np.random.RandomState(1).choice(qb.n_queries, 96, replace=False)
+        qs_all = case.batches[s]
+        sub = make_sub(case, s, idx)
+        f = case.formula(s)
+        want = np.stack([orc.forward(f, sub, [int(qs_all["target"][i]) for i in idx]).numpy(),
+                         orc.forward(f, sub, [int(qs_all["negs"][i, 0]) for i in idx]).numpy()], 1)
+        np.testing.assert_allclose(sc[q0 + idx], want, rtol=0, atol=TOL, err_msg=s)
+        q0 += qb.n_queries
+
+
+def make_sub(case, s, idx):
+    from graphqembed_b200.synth import SynthKG
+    from oracle import netquery_oracle as O
+    b = case.batches[s]
+    return [O.Query(SynthKG.query_graph(s, b["rels"], b["target"][i], b["anchors"][:, i]), None, None) for i in idx]
+
+
+def test_identity_relation_self_match_scores_one():
+    """1-chain with an identity relation matrix and anchor == target scores cos = 1."""
+    case = make_case(seed=9, d=128, decoder="bilinear", inter="mean", n_queries=300, n_neg=1, nodes_per_mode=100,
+                     n_modes=1, n_rel_pairs=1)
+    rel = case.batches["1-chain"]["rels"][0]
+    case.rel_params[rel] = torch.eye(128)
+    model = build_package_model(case)
+    b = case.batches["1-chain"]
+    batch = gqe.QueryBatch(case.formula("1-chain", cls=gqe.Formula), b["target"][None, :], b["target"])
+    np.testing.assert_allclose(_np(model.score_batch(batch)), 1.0, rtol=0, atol=1e-6)
