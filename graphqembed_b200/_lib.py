@@ -13,8 +13,18 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_NAME = "libgqe_b200.so"
 LIB_PATH = os.path.join(_PKG, LIB_NAME)
-SOURCES = [os.path.join(_PKG, "csrc", "gqe_capi.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "gqe_simt.cuh"), os.path.join(_ROOT, "include", "gqe.h")]
+CSRC = os.path.join(_PKG, "csrc")
+BUILD_DIR = os.path.join(_PKG, "build")
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    return sorted(hs) + [os.path.join(_ROOT, "include", "gqe.h")]
+
 
 GQE_MAX_ANCHORS = 3
 GQE_MAX_RELS = 3
@@ -73,27 +83,46 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"]
 
 
 def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
+    return any(os.path.getmtime(p) > built for p in _sources() + _headers())
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA sources for sm_100a into the in-tree shared library."""
+def build(force=False, verbose=False, jobs=None):
+    """Compile every csrc/*.cu for sm_100a (one nvcc per translation unit, in
+    parallel) and link them into the in-tree shared library."""
     if not force and not needs_build():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    newest_header = max(os.path.getmtime(h) for h in _headers())
+
+    def compile_one(src):
+        obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_header):
+            return obj, ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed (%d):\n%s\n%s" % (proc.returncode, " ".join(cmd), proc.stdout))
+        return obj, proc.stdout
+
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=jobs or min(len(srcs), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    if verbose:
+        for _, log in results:
+            sys.stderr.write(log)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + [o for o, _ in results]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed (%d):\n%s\n%s" % (proc.returncode, " ".join(cmd), proc.stdout))
-    if verbose:
-        sys.stderr.write(proc.stdout)
+        raise RuntimeError("link failed (%d):\n%s\n%s" % (proc.returncode, " ".join(cmd), proc.stdout))
     return LIB_PATH
 
 

@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/gqe.h"
-#include "gqe_simt.cuh"
+#include "gqe_launch.h"
 
 using namespace gqe;
 
@@ -223,51 +223,6 @@ static int resolve(gqe_ctx* c, const gqe_plan& pl, SegDev* s) {
   return GQE_OK;
 }
 
-// cudaFuncSetAttribute is per device: remember which devices were configured.
-static int current_device() {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  return dev & 63;
-}
-
-template <int D, int STRUCT>
-static cudaError_t launch_one(const LaunchParams& lp, int64_t grid, cudaStream_t st) {
-  static bool configured[64] = {false};
-  auto kern = gqe_fused_simt<D, STRUCT>;
-  const int dev = current_device();
-  if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<D>));
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
-  }
-  kern<<<(unsigned)grid, kThreads, sizeof(TileSmem<D>), st>>>(lp);
-  return cudaGetLastError();
-}
-
-template <int D>
-static cudaError_t launch_struct(int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {
-  switch (structure) {
-    case GQE_CHAIN1: return launch_one<D, GQE_CHAIN1>(lp, grid, st);
-    case GQE_CHAIN2: return launch_one<D, GQE_CHAIN2>(lp, grid, st);
-    case GQE_CHAIN3: return launch_one<D, GQE_CHAIN3>(lp, grid, st);
-    case GQE_INTER2: return launch_one<D, GQE_INTER2>(lp, grid, st);
-    case GQE_INTER3: return launch_one<D, GQE_INTER3>(lp, grid, st);
-    case GQE_INTER_CHAIN3: return launch_one<D, GQE_INTER_CHAIN3>(lp, grid, st);
-    case GQE_CHAIN_INTER3: return launch_one<D, GQE_CHAIN_INTER3>(lp, grid, st);
-    default: return launch_one<D, -1>(lp, grid, st);
-  }
-}
-
-static cudaError_t launch_dim(int d, int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {
-  switch (d) {
-    case 32: return launch_struct<32>(structure, lp, grid, st);
-    case 64: return launch_struct<64>(structure, lp, grid, st);
-    case 128: return launch_struct<128>(structure, lp, grid, st);
-    case 256: return launch_struct<256>(structure, lp, grid, st);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
 static int ensure_partials(gqe_ctx* c, int64_t n) {
   if (n <= c->partials_cap) return GQE_OK;
   // the old buffer may still be read by a kernel in flight on the stream
@@ -288,7 +243,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
   if (!c) return GQE_ERR_INVALID;
   if (!segs || n_segs <= 0) return fail(c, GQE_ERR_INVALID, "no segments");
   if (nq_total < 0 || n_pairs < 0) return fail(c, GQE_ERR_INVALID, "negative size");
-  if (!out_scores && !out_loss) return fail(c, GQE_ERR_INVALID, "no output requested");
+  if (!out_scores && !out_loss && n_pairs > 0) return fail(c, GQE_ERR_INVALID, "no output requested");
   if (target_offsets && n_segs != 1) return fail(c, GQE_ERR_INVALID, "ragged targets need a single formula");
   if (target_offsets && out_loss) return fail(c, GQE_ERR_INVALID, "margin loss needs the regular (pos,neg) layout");
   if (out_loss && T != 2) return fail(c, GQE_ERR_INVALID, "margin loss needs exactly 2 targets per query");
@@ -355,7 +310,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     }
     // single formula -> that structure's own kernel; otherwise the grouped kernel
     const int structure = (n == 1 && uniform) ? first_structure : -1;
-    GQE_CUDA(c, launch_dim(c->d, structure, lp, tiles, c->stream));
+    GQE_CUDA(c, launch_fused_simt(c->d, structure, lp, tiles, c->stream));
     c->launches += 1;
   }
   return GQE_OK;
@@ -376,7 +331,7 @@ extern "C" int gqe_score_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_quer
                                 int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets,
                                 float* out_scores) {
   if (!c) return GQE_ERR_INVALID;
-  if (!plan || !out_scores) return fail(c, GQE_ERR_INVALID, "gqe_score_device: null argument");
+  if (!plan || (!out_scores && n_pairs > 0)) return fail(c, GQE_ERR_INVALID, "gqe_score_device: null argument");
   int32_t T;
   int rc = regular_T(c, n_queries, n_pairs, target_offsets, &T);
   if (rc != GQE_OK) return rc;
@@ -461,7 +416,7 @@ extern "C" int gqe_score_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_querie
                               int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets,
                               float* out_scores) {
   if (!c) return GQE_ERR_INVALID;
-  if (!plan || !out_scores) return fail(c, GQE_ERR_INVALID, "gqe_score_host: null argument");
+  if (!plan || (!out_scores && n_pairs > 0)) return fail(c, GQE_ERR_INVALID, "gqe_score_host: null argument");
   int32_t T;
   int rc = regular_T(c, n_queries, n_pairs, target_offsets, &T);
   if (rc != GQE_OK) return rc;
@@ -490,33 +445,12 @@ extern "C" int gqe_score_grouped_host(gqe_ctx* c, const gqe_segment* segments, i
 }
 
 // ---- operator-level entry points -------------------------------------------------
-template <int D>
-static cudaError_t launch_op_d(const OpParams& op, cudaStream_t st) {
-  static bool configured[64] = {false};
-  auto kern = gqe_op_simt<D>;
-  const int dev = current_device();
-  if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<D>));
-    if (e != cudaSuccess) return e;
-    configured[dev] = true;
-  }
-  const int64_t grid = (op.n + kTileRows - 1) / kTileRows;
-  kern<<<(unsigned)grid, kThreads, sizeof(TileSmem<D>), st>>>(op);
-  return cudaGetLastError();
-}
-
 static int launch_op(gqe_ctx* c, int d, const OpParams& op) {
   if (op.n == 0) return GQE_OK;
   if (op.n < 0) return fail(c, GQE_ERR_INVALID, "negative column count");
   GQE_CUDA(c, cudaSetDevice(c->device));
-  cudaError_t e;
-  switch (d) {
-    case 32: e = launch_op_d<32>(op, c->stream); break;
-    case 64: e = launch_op_d<64>(op, c->stream); break;
-    case 128: e = launch_op_d<128>(op, c->stream); break;
-    case 256: e = launch_op_d<256>(op, c->stream); break;
-    default: return fail(c, GQE_ERR_UNSUPPORTED, "dimension %d not supported (32/64/128/256)", d);
-  }
+  if (!dim_supported(d)) return fail(c, GQE_ERR_UNSUPPORTED, "dimension %d not supported (32/64/128/256)", d);
+  cudaError_t e = launch_op_simt(d, op, c->stream);
   if (e != cudaSuccess) return fail(c, GQE_ERR_CUDA, "operator launch failed: %s", cudaGetErrorString(e));
   c->launches += 1;
   return GQE_OK;

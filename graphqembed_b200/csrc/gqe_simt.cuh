@@ -18,52 +18,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/gqe.h"
+#include "gqe_params.h"
 
 namespace gqe {
-
-constexpr int kTileRows = 64;
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kRowsPerWarp = kTileRows / kWarps;  // 8
-constexpr int kPanelK = 16;
-constexpr int kRowStride = kTileRows + 4;  // 68 floats: 16B-aligned rows, 4-bank skew
-constexpr int kMaxSegs = 16;
-constexpr float kCosEps = 1e-8f;  // nn.CosineSimilarity default eps (model.py:68)
-
-// One formula's slice of a launch, fully resolved to device pointers.
-struct SegDev {
-  int32_t structure;
-  int32_t n_anchor;
-  const float* tgt_table;
-  const float* anc_table[GQE_MAX_ANCHORS];
-  const float* rel[GQE_MAX_RELS];  // relation parameters in application order
-  const float* pre;                // DeepSets pre/post of the intersection mode
-  const float* post;
-  int64_t q_begin, q_end;          // query range in the concatenated arrays
-  int64_t tile_begin;              // first tile of this segment inside the launch
-};
-
-struct LaunchParams {
-  SegDev seg[kMaxSegs];
-  int32_t n_segs;
-  int32_t decoder;  // gqe_decoder
-  int32_t inter;    // gqe_inter
-  const int32_t* anchor_rows;
-  int64_t anchor_stride;  // total queries (distance between anchor slots)
-  const int32_t* target_rows;
-  const int64_t* target_offsets;  // ragged layout (single segment only) or null
-  int64_t n_pairs;
-  int32_t T;  // regular layout: targets per query
-  float* out_scores;
-  // fused margin loss (T == 2): deterministic two-level reduction
-  float* out_loss;
-  float margin;
-  double inv_q;
-  double* partials;   // [gridDim.x]
-  double* loss_acc;   // running sum across the launches of one call
-  unsigned int* ticket;
-};
 
 template <int D>
 struct __align__(16) TileSmem {
@@ -458,26 +415,6 @@ __device__ __forceinline__ void store_fm(float* __restrict__ dst, float (*X)[kRo
     if (r < n_valid) dst[(size_t)k * n + c0 + r] = X[k][r];
   }
 }
-
-struct OpParams {
-  int32_t op;       // see OP_* below
-  int32_t decoder;
-  int32_t inter;
-  int32_t n_rels;
-  int32_t mutate;   // TransE path score: write the translated embeds1 back
-  int64_t n;
-  const float* table;
-  const int32_t* rows;
-  const float* rel[GQE_MAX_RELS];
-  const float* pre;
-  const float* post;
-  const float* in0;
-  const float* in1;
-  const float* in2;
-  float* io0;       // embeds1 when mutated in place
-  float* out;
-};
-enum { OP_ENCODE = 0, OP_PROJECT = 1, OP_PATH_SCORE = 2, OP_INTERSECT = 3, OP_COSINE = 4 };
 
 // cosine_similarity(dim=0, eps) of two smem tiles, one column per warp pass
 template <int D>
