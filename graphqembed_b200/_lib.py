@@ -33,6 +33,8 @@ STRUCTURE_ID = {"1-chain": 0, "2-chain": 1, "3-chain": 2, "2-inter": 3, "3-inter
                 "3-inter_chain": 5, "3-chain_inter": 6}
 DECODER_ID = {"bilinear": 0, "transe": 1, "bilinear-diag": 2}
 INTER_ID = {"mean": 0, "min": 1, "mean-simple": 2, "min-simple": 3}
+PRECISION_ID = {"bf16x3": 0, "fp32": 1}
+ABI_VERSION = 2
 
 
 class GqeError(RuntimeError):
@@ -61,6 +63,8 @@ _SIGNATURES = {
     "gqe_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "gqe_destroy": (None, [_P]),
     "gqe_set_stream": (C.c_int, [_P, _P]),
+    "gqe_set_precision": (C.c_int, [_P, C.c_int32]),
+    "gqe_get_precision": (C.c_int, [_P]),
     "gqe_last_error": (C.c_char_p, [_P]),
     "gqe_launch_count": (C.c_int64, [_P]),
     "gqe_bind_tables": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64), C.c_int32]),
@@ -143,7 +147,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.gqe_abi_version() != 1:
+    if lib.gqe_abi_version() != ABI_VERSION:
         raise RuntimeError("libgqe_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -185,6 +189,14 @@ class Context(object):
 
     def set_stream(self, stream):
         self._check(self._lib.gqe_set_stream(self._h, _P(stream or 0)))
+
+    def set_precision(self, precision):
+        """"bf16x3" (tensor cores, default) or "fp32" (exact CUDA-core FMA)."""
+        self._check(self._lib.gqe_set_precision(self._h, PRECISION_ID[precision]))
+
+    def get_precision(self):
+        code = int(self._lib.gqe_get_precision(self._h))
+        return [k for k, v in PRECISION_ID.items() if v == code][0]
 
     def launch_count(self):
         return int(self._lib.gqe_launch_count(self._h))

@@ -35,6 +35,13 @@ struct gqe_ctx {
   int inter_d = 0;
   std::vector<const float*> pre, post;
 
+  // arithmetic of the d x d contractions (gqe_precision)
+  int precision = GQE_PREC_BF16X3;
+  // tensor-core path: packed (bf16 hi/lo, pre-swizzled) copies of the matrices one
+  // launch uses, rebuilt on every call because the parameters are live
+  uint8_t* packed = nullptr;
+  size_t packed_cap = 0;
+
   // margin-loss reduction scratch
   double* partials = nullptr;
   int64_t partials_cap = 0;
@@ -119,6 +126,7 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->partials);
+  cudaFree(c->packed);
   cudaFree(c->loss_acc);
   cudaFree(c->ticket);
   for (void* p : c->stage) cudaFree(p);
@@ -130,6 +138,15 @@ extern "C" int gqe_set_stream(gqe_ctx* c, void* stream) {
   c->stream = (cudaStream_t)stream;
   return GQE_OK;
 }
+
+extern "C" int gqe_set_precision(gqe_ctx* c, int32_t precision) {
+  if (!c) return GQE_ERR_INVALID;
+  if (precision != GQE_PREC_BF16X3 && precision != GQE_PREC_FP32)
+    return fail(c, GQE_ERR_INVALID, "gqe_set_precision: unknown precision %d", precision);
+  c->precision = precision;
+  return GQE_OK;
+}
+extern "C" int gqe_get_precision(const gqe_ctx* c) { return c ? c->precision : GQE_ERR_INVALID; }
 
 extern "C" const char* gqe_last_error(const gqe_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 extern "C" int64_t gqe_launch_count(const gqe_ctx* c) { return c ? c->launches : 0; }
@@ -275,10 +292,42 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
   lp.loss_acc = c->loss_acc;
   lp.ticket = c->ticket;
 
+  // Bilinear d x d contractions go to the tensor cores (tcgen05, bf16x3 split) unless the
+  // context asks for exact fp32; the ragged target layout stays on the fp32 kernels.
+  const bool use_tc = c->precision == GQE_PREC_BF16X3 && c->decoder == GQE_DEC_BILINEAR && tc_dim_supported(c->d) &&
+                      target_offsets == nullptr;
+  const int64_t tile_rows = use_tc ? kTcTileRows : kTileRows;
+  if (use_tc) {
+    const size_t need = (size_t)kMaxPack * tc_packed_bytes(c->d);
+    if (c->packed_cap < need) {
+      GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->packed);
+      c->packed = nullptr;
+      c->packed_cap = 0;
+      GQE_CUDA(c, cudaMalloc(&c->packed, need));
+      c->packed_cap = need;
+    }
+  }
+
   int32_t i = 0;
   while (i < n_segs) {
     int n = 0;
     int64_t tiles = 0;
+    PackParams pp;
+    int n_pack = 0;
+    // packed copy of one matrix in the orientation its use needs (deduplicated per launch)
+    auto packed_of = [&](const float* src, int chain_form) -> const float* {
+      int k = 0;
+      for (; k < n_pack; ++k)
+        if (pp.e[k].src == src && pp.e[k].chain_form == chain_form) break;
+      if (k == n_pack) {
+        pp.e[k].src = src;
+        pp.e[k].chain_form = chain_form;
+        pp.e[k].pad_ = 0;
+        ++n_pack;
+      }
+      return reinterpret_cast<const float*>(c->packed + (size_t)k * tc_packed_bytes(c->d));
+    };
     int first_structure = -1;
     bool uniform = true;
     while (i < n_segs && n < kMaxSegs) {
@@ -295,7 +344,13 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       s->tile_begin = tiles;
       const int64_t nq = g.query_end - g.query_begin;
       const int64_t rows = g.plan.structure <= GQE_CHAIN3 ? (target_offsets ? n_pairs : nq * T) : nq;
-      tiles += (rows + kTileRows - 1) / kTileRows;
+      tiles += (rows + tile_rows - 1) / tile_rows;
+      if (use_tc) {
+        const int chain_form = g.plan.structure <= GQE_CHAIN3 ? 1 : 0;
+        for (int k = 0; k < n_rels_of(g.plan.structure); ++k) s->rel[k] = packed_of(s->rel[k], chain_form);
+        if (s->pre) s->pre = packed_of(s->pre, 0);
+        if (s->post) s->post = packed_of(s->post, 0);
+      }
       if (first_structure < 0) first_structure = g.plan.structure;
       else if (first_structure != g.plan.structure) uniform = false;
       ++n;
@@ -310,8 +365,15 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     }
     // single formula -> that structure's own kernel; otherwise the grouped kernel
     const int structure = (n == 1 && uniform) ? first_structure : -1;
-    GQE_CUDA(c, launch_fused_simt(c->d, structure, lp, tiles, c->stream));
-    c->launches += 1;
+    if (use_tc) {
+      pp.dst = c->packed;
+      GQE_CUDA(c, launch_pack(c->d, pp, n_pack, c->stream));
+      GQE_CUDA(c, launch_fused_tc(c->d, structure, lp, tiles, c->stream));
+      c->launches += 2;
+    } else {
+      GQE_CUDA(c, launch_fused_simt(c->d, structure, lp, tiles, c->stream));
+      c->launches += 1;
+    }
   }
   return GQE_OK;
 }

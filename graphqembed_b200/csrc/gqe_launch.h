@@ -14,6 +14,31 @@ GQE_DECLARE_DIM(128)
 GQE_DECLARE_DIM(256)
 #undef GQE_DECLARE_DIM
 
+// tensor-core (tcgen05) kernels: Bilinear decoder, d = 128 / 256
+#define GQE_DECLARE_TC_DIM(D)                                                                                \
+  cudaError_t launch_fused_tc_d##D(int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st);    \
+  cudaError_t launch_pack_d##D(const PackParams& pp, int n_entries, cudaStream_t st);
+GQE_DECLARE_TC_DIM(128)
+GQE_DECLARE_TC_DIM(256)
+#undef GQE_DECLARE_TC_DIM
+
+inline bool tc_dim_supported(int d) { return d == 128 || d == 256; }
+inline size_t tc_packed_bytes(int d) { return (size_t)4 * d * d; }
+inline cudaError_t launch_fused_tc(int d, int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {
+  switch (d) {
+    case 128: return launch_fused_tc_d128(structure, lp, grid, st);
+    case 256: return launch_fused_tc_d256(structure, lp, grid, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+inline cudaError_t launch_pack(int d, const PackParams& pp, int n_entries, cudaStream_t st) {
+  switch (d) {
+    case 128: return launch_pack_d128(pp, n_entries, st);
+    case 256: return launch_pack_d256(pp, n_entries, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // structure < 0 selects the grouped kernel
 inline cudaError_t launch_fused_simt(int d, int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {
   switch (d) {

@@ -69,6 +69,19 @@ struct OpParams {
   float* io0;       // embeds1 when mutated in place
   float* out;
 };
+// Tensor-core path: rows per tile and the weight-packing request (gqe_pack).
+constexpr int kTcTileRows = 128;
+struct PackEntry {
+  const float* src;
+  int32_t chain_form;  // 1: B[n][k] = M[k][n] (act.mm(M)); 0: B[n][k] = M[n][k] (M.mm(embeds))
+  int32_t pad_;
+};
+constexpr int kMaxPack = 5 * kMaxSegs;
+struct PackParams {
+  PackEntry e[kMaxPack];
+  uint8_t* dst;
+};
+
 enum { OP_ENCODE = 0, OP_PROJECT = 1, OP_PATH_SCORE = 2, OP_INTERSECT = 3, OP_COSINE = 4 };
 
 }  // namespace gqe

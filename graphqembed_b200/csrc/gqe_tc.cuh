@@ -1,0 +1,630 @@
+// gqe_tc.cuh -- tensor-core (tcgen05 / TMEM / TMA) kernels of the
+// conjunctive-query scorer for the Bilinear decoder at d = 128 / 256.
+//
+// One CTA owns a tile of 128 rows (queries, or (query,target) pairs for chain
+// structures) = one UMMA M.  Every d x d contraction of the path -- the chained
+// relation projections (reference netquery/decoders.py:142-150) and the DeepSets
+// pre / post matrices (decoders.py:288-300) -- is a [128 x d] x [d x d] product on
+// the 5th-generation tensor cores:
+//
+//   * the activations live in shared memory as two bf16 planes (hi, lo with
+//     x ~= hi + lo) in the UMMA canonical K-major SWIZZLE_128B layout;
+//   * the relation matrix is pre-split and pre-swizzled by gqe_pack (same layout,
+//     hi and lo planes per 64-wide K block) and streamed L2 -> smem by TMA bulk
+//     copies through a 3-stage mbarrier ring;
+//   * one elected thread issues tcgen05.mma (kind::f16, M=128, N=d, K=16) three
+//     times per K step -- hi*hi, lo*hi, hi*lo -- accumulating in fp32 in TMEM.
+//     Dropping lo*lo leaves a relative error of ~2^-17 per product, two orders
+//     below the 1e-4 parity bound on the cosine score (tests/test_gpu_parity.py);
+//   * the worker warps read the accumulator back with tcgen05.ld (thread == row),
+//     apply the epilogue (re-split for the next hop, ReLU + mean/min aggregation
+//     kept in a second TMEM region, or the cosine / margin loss against the gathered
+//     target rows) and never write an intermediate to global memory.
+//
+// Warp roles: warps [0, W) workers (W = d/32), warp W = TMA producer, warp W+1 =
+// MMA issuer + TMEM owner.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gqe_params.h"
+#include "gqe_ptx.cuh"
+
+namespace gqe {
+namespace tc {
+
+constexpr int kRows = 128;     // rows per tile = UMMA M
+constexpr int kKBlock = 64;    // bf16 per 128-byte swizzle row
+constexpr int kStages = 3;     // weight ring depth
+constexpr int kMaxSteps = 8;
+
+template <int D>
+struct Cfg {
+  static constexpr int kWorkerWarps = D / 32;  // each worker thread owns 128 columns of one row
+  static constexpr int kWorkerThreads = kWorkerWarps * 32;
+  static constexpr int kThreads = kWorkerThreads + 64;
+  static constexpr int kKB = D / kKBlock;
+  static constexpr int kABlockBytes = kRows * 128;     // one 64-wide K block of the A tile
+  static constexpr int kAPlaneBytes = kKB * kABlockBytes;
+  static constexpr int kStageBytes = D * 128;          // one plane of one K block of the weights
+  static constexpr int kOffAhi = 0;
+  static constexpr int kOffAlo = kAPlaneBytes;
+  static constexpr int kOffB = 2 * kAPlaneBytes;
+  static constexpr int kOffCtl = kOffB + kStages * kStageBytes;
+  static constexpr int kCtlBytes = 256;
+  static constexpr int kSmemBytes = kOffCtl + kCtlBytes;
+  static constexpr int kTmemCols = 2 * D;              // accumulator + aggregation region
+  static constexpr int kPackedBytes = 4 * D * D;       // one packed matrix (2 planes x bf16)
+  static constexpr int kCtasPerSm = (D <= 128) ? 2 : 1;
+};
+
+struct Ctl {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t a_ready;
+  uint64_t acc_full;
+  double red[8];
+  uint32_t tmem_base;
+  int last;
+};
+static_assert(sizeof(Ctl) <= 256, "control block");
+
+// ---- the per-structure program --------------------------------------------------
+enum { G_NONE = 7, G_TARGET = 3 };                       // gather source: anchor 0..2, target, none
+enum { M_REL0 = 0, M_REL1 = 1, M_REL2 = 2, M_PRE = 3, M_POST = 4 };
+enum { E_TO_A = 0, E_AGG = 1, E_SCORE = 2, E_KIND = 3, F_RELU = 4, F_FIRST = 8, F_LAST = 16, F_DEST_ACC = 32 };
+
+struct Prog {
+  int n;
+  uint8_t mat[kMaxSteps];
+  uint8_t gather[kMaxSteps];
+  uint8_t epi[kMaxSteps];
+};
+
+// Operator order of reference netquery/model.py:70-109 (see include/gqe.h gqe_plan).
+__device__ __forceinline__ void build_program(Prog& pg, int structure, bool deepsets) {
+  int n = 0;
+  auto push = [&](int mat, int gather, int epi) {
+    pg.mat[n] = (uint8_t)mat;
+    pg.gather[n] = (uint8_t)gather;
+    pg.epi[n] = (uint8_t)epi;
+    ++n;
+  };
+  if (structure <= GQE_CHAIN3) {
+    const int hops = structure + 1;
+    for (int h = 0; h < hops; ++h) push(h, h == 0 ? G_TARGET : G_NONE, h == hops - 1 ? E_SCORE : E_TO_A);
+  } else {
+    const int nb = structure == GQE_INTER3 ? 3 : 2;
+    for (int b = 0; b < nb; ++b) {
+      const int pos = (b == 0 ? F_FIRST : 0) | (b == nb - 1 ? F_LAST : 0);
+      const int agg_simple = E_AGG | pos | ((b == nb - 1 && structure != GQE_CHAIN_INTER3) ? F_DEST_ACC : 0);
+      if (structure == GQE_INTER_CHAIN3 && b == 1) {
+        push(M_REL1, b, E_TO_A);                               // reverse(r2b) first (model.py:85)
+        push(M_REL2, G_NONE, deepsets ? E_TO_A : agg_simple);  // then reverse(r2a)
+      } else {
+        push(b, b, deepsets ? E_TO_A : agg_simple);
+      }
+      if (deepsets) push(M_PRE, G_NONE, E_AGG | F_RELU | pos);  // relu(pre.mm(e)) decoders.py:289-292
+    }
+    if (deepsets) push(M_POST, G_NONE, structure == GQE_CHAIN_INTER3 ? E_TO_A : E_SCORE);  // decoders.py:299
+    if (structure == GQE_CHAIN_INTER3) push(M_REL2, G_NONE, E_SCORE);                      // model.py:107
+  }
+  pg.n = n;
+}
+
+__device__ __forceinline__ const uint8_t* step_matrix(const SegDev& s, int mat) {
+  const float* p = mat <= M_REL2 ? s.rel[mat] : (mat == M_PRE ? s.pre : s.post);
+  return reinterpret_cast<const uint8_t*>(p);  // packed bf16 planes on this path
+}
+
+// ---- small math helpers -----------------------------------------------------------
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float relu_nan_(float x) { return x < 0.f ? 0.f : x; }
+__device__ __forceinline__ float min_nan_(float a, float b) { return (a < b || a != a) ? a : b; }
+
+// x0,x1 -> packed bf16 hi pair and packed bf16 lo pair with x ~= hi + lo
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __low2float(h), x1 - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// byte offset of (row r, 16-byte chunk c of K block kb) inside an A plane
+__device__ __forceinline__ uint32_t a_chunk_off(int r, int kb, int c) {
+  return (uint32_t)(kb * (kRows * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+// ---- DirectEncoder: gather, L2-normalise, split, park as the A operand ---------------
+// (reference netquery/encoders.py:41-43; true division, no epsilon.)  A warp reads
+// one table row per instruction group with 128-bit loads, fully coalesced.
+template <int D>
+__device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restrict__ table,
+                                            const int32_t* __restrict__ rows, int n_valid, int wid, int lane) {
+  using C = Cfg<D>;
+  constexpr int RPW = kRows / C::kWorkerWarps;
+  constexpr int NV = D / 128;
+#pragma unroll 1
+  for (int r0 = 0; r0 < RPW; r0 += 4) {
+    float4 v[4][NV];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = wid * RPW + r0 + u;
+      const bool ok = r < n_valid;
+      const size_t row = ok ? (size_t)__ldg(rows + r) : 0;
+      const float4* src = reinterpret_cast<const float4*>(table + row * D);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[u][j] = ok ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = wid * RPW + r0 + u;
+      const bool ok = r < n_valid;
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        ss = fmaf(v[u][j].x, v[u][j].x, ss);
+        ss = fmaf(v[u][j].y, v[u][j].y, ss);
+        ss = fmaf(v[u][j].z, v[u][j].z, ss);
+        ss = fmaf(v[u][j].w, v[u][j].w, ss);
+      }
+      ss = warp_sum_f(ss);
+      const float nrm = sqrtf(ss);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        if (ok) {
+          x0 = __fdiv_rn(v[u][j].x, nrm);
+          x1 = __fdiv_rn(v[u][j].y, nrm);
+          x2 = __fdiv_rn(v[u][j].z, nrm);
+          x3 = __fdiv_rn(v[u][j].w, nrm);
+        }
+        uint2 hi, lo;
+        split2(x0, x1, hi.x, lo.x);
+        split2(x2, x3, hi.y, lo.y);
+        // element k = 128 j + 4 lane: K block 2j + lane/16, chunk (lane%16)/2, half (lane&1)
+        const uint32_t off = a_chunk_off(r, 2 * j + (lane >> 4), (lane & 15) >> 1) + ((lane & 1) << 3);
+        *reinterpret_cast<uint2*>(smem + C::kOffAhi + off) = hi;
+        *reinterpret_cast<uint2*>(smem + C::kOffAlo + off) = lo;
+      }
+    }
+  }
+}
+
+// 32 fp32 values of (row r, columns col0..col0+31) -> the A operand planes
+template <int D>
+__device__ __forceinline__ void store_a32(uint8_t* smem, int r, int col0, const float (&x)[32]) {
+  using C = Cfg<D>;
+  const int kb = col0 >> 6, c0 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 hi, lo;
+    split2(x[8 * j + 0], x[8 * j + 1], hi.x, lo.x);
+    split2(x[8 * j + 2], x[8 * j + 3], hi.y, lo.y);
+    split2(x[8 * j + 4], x[8 * j + 5], hi.z, lo.z);
+    split2(x[8 * j + 6], x[8 * j + 7], hi.w, lo.w);
+    const uint32_t off = a_chunk_off(r, kb, c0 + j);
+    *reinterpret_cast<uint4*>(smem + C::kOffAhi + off) = hi;
+    *reinterpret_cast<uint4*>(smem + C::kOffAlo + off) = lo;
+  }
+}
+
+__device__ __forceinline__ float hinge_(float margin, float pos, float neg) {
+  const float h = margin - (pos - neg);
+  return h < 0.f ? 0.f : h;
+}
+
+// Deterministic two-level reduction of the per-CTA hinge sums (model.py:126 mean);
+// executed by the worker threads only.
+template <int D>
+__device__ __forceinline__ void loss_reduce(const LaunchParams& p, Ctl* ctl, double local, int wid, int lane) {
+  using C = Cfg<D>;
+  local = warp_sum_d(local);
+  if (lane == 0) ctl->red[wid] = local;
+  ptx::named_bar_sync(1, C::kWorkerThreads);
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < C::kWorkerWarps; ++w) s += ctl->red[w];
+    p.partials[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int t = atomicAdd(p.ticket, 1u);
+    ctl->last = (t == gridDim.x - 1);
+  }
+  ptx::named_bar_sync(1, C::kWorkerThreads);
+  if (ctl->last && wid == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned int i = lane; i < gridDim.x; i += 32) s += __ldcg(p.partials + i);
+    s = warp_sum_d(s);
+    if (lane == 0) {
+      const double acc = *p.loss_acc + s;
+      *p.loss_acc = acc;
+      *p.out_loss = (float)(acc * p.inv_q);
+      *p.ticket = 0u;
+    }
+  }
+}
+
+// ---- worker warps ---------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, int structure, int64_t tile_in_seg,
+                                       uint8_t* smem, Ctl* ctl) {
+  using C = Cfg<D>;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = 32 * (wid & 3) + lane;      // TMEM lane == tile row
+  const int col_base = (wid >> 2) * 128;      // this thread's 128 columns
+  const bool chain = structure <= GQE_CHAIN3;
+  const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
+  const bool use_min = p.inter == GQE_INTER_DEEPSETS_MIN || p.inter == GQE_INTER_SIMPLE_MIN;
+  const int n_branch = s.n_anchor;
+  const int T = p.T;
+
+  // rows of this tile
+  const int64_t row_begin = (chain ? s.q_begin * T : s.q_begin) + tile_in_seg * kRows;
+  const int64_t row_end = chain ? s.q_end * T : s.q_end;
+  const int n_valid = (int)min((int64_t)kRows, row_end - row_begin);
+  const bool valid = row < n_valid;
+
+  Prog pg;
+  build_program(pg, structure, deepsets);
+
+  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t t_acc = tmem_base + ((uint32_t)(32 * (wid & 3)) << 16) + col_base;
+  const uint32_t t_agg = t_acc + D;
+  const uint32_t bar_a_ready = ptx::smem_u32(&ctl->a_ready);
+  const uint32_t bar_acc_full = ptx::smem_u32(&ctl->acc_full);
+
+  for (int st = 0; st < pg.n; ++st) {
+    const int g = pg.gather[st];
+    if (g != G_NONE) {
+      if (g == G_TARGET) gather_to_a<D>(smem, s.tgt_table, p.target_rows + row_begin, n_valid, wid, lane);
+      else gather_to_a<D>(smem, s.anc_table[g], p.anchor_rows + (int64_t)g * p.anchor_stride + row_begin, n_valid, wid, lane);
+    }
+    // A operand complete (generic-proxy stores -> async proxy) and this thread's
+    // TMEM reads of the previous accumulator retired: hand over to the MMA issuer
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before_sync();
+    ptx::mbar_arrive(bar_a_ready);
+
+    ptx::mbar_wait(bar_acc_full, (uint32_t)(st & 1));
+    ptx::tc_fence_after_sync();
+
+    const int epi = pg.epi[st];
+    const int kind = epi & E_KIND;
+    if (kind == E_SCORE) break;  // scored below, straight from the accumulator
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t raw[32];
+      float x[32];
+      ptx::tmem_ld32(t_acc + 32 * ch, raw);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]);
+      if (kind == E_AGG) {
+        if (epi & F_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = relu_nan_(x[i]);
+        }
+        if (!(epi & F_FIRST)) {
+          uint32_t araw[32];
+          ptx::tmem_ld32(t_agg + 32 * ch, araw);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = __uint_as_float(araw[i]);
+            x[i] = use_min ? min_nan_(a, x[i]) : a + x[i];
+          }
+        }
+        if (!(epi & F_LAST)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(x[i]);
+          ptx::tmem_st32(t_agg + 32 * ch, raw);
+          continue;
+        }
+        if (!use_min) {  // torch.mean over the stacked operands
+          const float nb = (float)n_branch;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __fdiv_rn(x[i], nb);
+        }
+        if (epi & F_DEST_ACC) {  // combined embedding is the query embedding itself
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(x[i]);
+          ptx::tmem_st32(t_acc + 32 * ch, raw);
+          continue;
+        }
+      }
+      store_a32<D>(smem, row, col_base + 32 * ch, x);
+    }
+    ptx::tmem_wait_st();
+    if (kind == E_AGG && (epi & F_DEST_ACC)) break;
+  }
+
+  // ---- score: the accumulator row is the projected target (chains) or the query
+  // embedding (intersections); thread == row, no intermediate leaves the SM -------
+  float* scratch = reinterpret_cast<float*>(smem);  // A planes are dead now
+  if (chain) {
+    const int64_t pair = row_begin + row;
+    const float* a_src = s.anc_table[0];
+    if (valid) a_src += (size_t)__ldg(p.anchor_rows + pair / T) * D + col_base;
+    float dot = 0.f, yy = 0.f, aa = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t raw[32];
+      ptx::tmem_ld32(t_acc + 32 * ch, raw);
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        a[i] = valid ? __ldg(reinterpret_cast<const float4*>(a_src + 32 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y0 = __uint_as_float(raw[4 * i]), y1 = __uint_as_float(raw[4 * i + 1]);
+        const float y2 = __uint_as_float(raw[4 * i + 2]), y3 = __uint_as_float(raw[4 * i + 3]);
+        dot = fmaf(y0, a[i].x, dot); dot = fmaf(y1, a[i].y, dot); dot = fmaf(y2, a[i].z, dot); dot = fmaf(y3, a[i].w, dot);
+        yy = fmaf(y0, y0, yy); yy = fmaf(y1, y1, yy); yy = fmaf(y2, y2, yy); yy = fmaf(y3, y3, yy);
+        aa = fmaf(a[i].x, a[i].x, aa); aa = fmaf(a[i].y, a[i].y, aa); aa = fmaf(a[i].z, a[i].z, aa); aa = fmaf(a[i].w, a[i].w, aa);
+      }
+    }
+    if (D == 256) {  // the two column halves of a row meet in shared memory
+      if (col_base != 0) {
+        scratch[row * 4 + 0] = dot; scratch[row * 4 + 1] = yy; scratch[row * 4 + 2] = aa;
+      }
+      ptx::named_bar_sync(1, C::kWorkerThreads);
+      if (col_base == 0) {
+        dot += scratch[row * 4 + 0]; yy += scratch[row * 4 + 1]; aa += scratch[row * 4 + 2];
+      }
+      ptx::named_bar_sync(1, C::kWorkerThreads);
+    }
+    // cos(y, a_hat) with a_hat = a/|a| (unit norm): (y.a/|a|) / max(|y|, eps); a zero
+    // anchor row gives 0/0 = NaN as in the reference
+    float score = 0.f;
+    if (col_base == 0) {
+      score = __fdiv_rn(dot, sqrtf(aa)) / fmaxf(sqrtf(yy), kCosEps);
+      if (valid && p.out_scores) p.out_scores[pair] = score;
+      scratch[512 + row] = score;
+    }
+    if (p.out_loss) {
+      ptx::named_bar_sync(1, C::kWorkerThreads);
+      double local = 0.0;
+      if (threadIdx.x < kRows / 2 && 2 * (int)threadIdx.x + 1 < n_valid)
+        local = (double)hinge_(p.margin, scratch[512 + 2 * threadIdx.x], scratch[512 + 2 * threadIdx.x + 1]);
+      loss_reduce<D>(p, ctl, local, wid, lane);
+    }
+  } else {
+    const int64_t q = row_begin + row;
+    double local = 0.0;
+    float qq = 0.f;
+#pragma unroll 1
+    for (int t0 = 0; t0 < T; t0 += 2) {
+      const bool has1 = t0 + 1 < T;
+      const float* src0 = s.tgt_table;
+      const float* src1 = s.tgt_table;
+      if (valid) {
+        src0 += (size_t)__ldg(p.target_rows + q * T + t0) * D + col_base;
+        if (has1) src1 += (size_t)__ldg(p.target_rows + q * T + t0 + 1) * D + col_base;
+      }
+      float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f, qs = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t raw[32];
+        ptx::tmem_ld32(t_acc + 32 * ch, raw);
+        float4 a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[i] = valid ? __ldg(reinterpret_cast<const float4*>(src0 + 32 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[i] = (valid && has1) ? __ldg(reinterpret_cast<const float4*>(src1 + 32 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y0 = __uint_as_float(raw[4 * i]), y1 = __uint_as_float(raw[4 * i + 1]);
+          const float y2 = __uint_as_float(raw[4 * i + 2]), y3 = __uint_as_float(raw[4 * i + 3]);
+          qs = fmaf(y0, y0, qs); qs = fmaf(y1, y1, qs); qs = fmaf(y2, y2, qs); qs = fmaf(y3, y3, qs);
+          d0 = fmaf(y0, a[i].x, d0); d0 = fmaf(y1, a[i].y, d0); d0 = fmaf(y2, a[i].z, d0); d0 = fmaf(y3, a[i].w, d0);
+          n0 = fmaf(a[i].x, a[i].x, n0); n0 = fmaf(a[i].y, a[i].y, n0); n0 = fmaf(a[i].z, a[i].z, n0); n0 = fmaf(a[i].w, a[i].w, n0);
+          d1 = fmaf(y0, b[i].x, d1); d1 = fmaf(y1, b[i].y, d1); d1 = fmaf(y2, b[i].z, d1); d1 = fmaf(y3, b[i].w, d1);
+          n1 = fmaf(b[i].x, b[i].x, n1); n1 = fmaf(b[i].y, b[i].y, n1); n1 = fmaf(b[i].z, b[i].z, n1); n1 = fmaf(b[i].w, b[i].w, n1);
+        }
+      }
+      if (D == 256) {
+        if (col_base != 0) {
+          float* sp = scratch + row * 8;
+          sp[0] = d0; sp[1] = d1; sp[2] = n0; sp[3] = n1; sp[4] = qs;
+        }
+        ptx::named_bar_sync(1, C::kWorkerThreads);
+        if (col_base == 0) {
+          const float* sp = scratch + row * 8;
+          d0 += sp[0]; d1 += sp[1]; n0 += sp[2]; n1 += sp[3]; qs += sp[4];
+        }
+        ptx::named_bar_sync(1, C::kWorkerThreads);
+      }
+      if (t0 == 0) qq = qs;
+      if (col_base == 0 && valid) {
+        // t_hat = t/|t| has unit norm: cos(t_hat, q) = (t.q/|t|) / max(|q|, eps); a zero
+        // target row gives 0/0 = NaN as in the reference
+        const float nq = fmaxf(sqrtf(qq), kCosEps);
+        const float s0 = __fdiv_rn(d0, sqrtf(n0)) / nq;
+        const float s1 = has1 ? __fdiv_rn(d1, sqrtf(n1)) / nq : 0.f;
+        if (p.out_scores) {
+          p.out_scores[q * T + t0] = s0;
+          if (has1) p.out_scores[q * T + t0 + 1] = s1;
+        }
+        if (p.out_loss && t0 == 0) local = (double)hinge_(p.margin, s0, s1);
+      }
+    }
+    if (p.out_loss) loss_reduce<D>(p, ctl, local, wid, lane);
+  }
+}
+
+// ---- TMA producer: streams the packed planes of every step's matrix -------------------
+template <int D>
+__device__ __forceinline__ void producer(const LaunchParams& p, const SegDev& s, int structure, uint8_t* smem, Ctl* ctl) {
+  using C = Cfg<D>;
+  const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
+  Prog pg;
+  build_program(pg, structure, deepsets);
+  uint32_t slot = 0, phase = 0;
+  for (int st = 0; st < pg.n; ++st) {
+    const uint8_t* src = step_matrix(s, pg.mat[st]);
+#pragma unroll 1
+    for (int i = 0; i < 2 * C::kKB; ++i) {
+      const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
+      ptx::mbar_wait(empty, phase ^ 1);
+      ptx::mbar_arrive_expect_tx(full, C::kStageBytes);
+      ptx::tma_bulk_g2s(ptx::smem_u32(smem + C::kOffB + slot * C::kStageBytes), src + (size_t)i * C::kStageBytes,
+                        C::kStageBytes, full);
+      if (++slot == kStages) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+// ---- MMA issuer ------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void mma_issuer(const LaunchParams& p, int structure, uint8_t* smem, Ctl* ctl) {
+  using C = Cfg<D>;
+  const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
+  Prog pg;
+  build_program(pg, structure, deepsets);
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, D);
+  const uint32_t tmem_acc = ctl->tmem_base;
+  const uint32_t a_hi = ptx::smem_u32(smem + C::kOffAhi), a_lo = ptx::smem_u32(smem + C::kOffAlo);
+  const uint32_t b0 = ptx::smem_u32(smem + C::kOffB);
+  const uint32_t bar_a_ready = ptx::smem_u32(&ctl->a_ready), bar_acc_full = ptx::smem_u32(&ctl->acc_full);
+  uint32_t slot = 0, phase = 0;
+  for (int st = 0; st < pg.n; ++st) {
+    ptx::mbar_wait(bar_a_ready, (uint32_t)(st & 1));
+    ptx::tc_fence_after_sync();
+#pragma unroll 1
+    for (int kb = 0; kb < C::kKB; ++kb) {
+      // plane 0 of this K block: B_hi, used by A_hi and A_lo
+      {
+        const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
+        ptx::mbar_wait(full, phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t b = b0 + slot * C::kStageBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
+                            ptx::umma_desc_sw128(b + 32 * k), idesc, (kb | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_lo + kb * C::kABlockBytes + 32 * k),
+                            ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
+        ptx::umma_commit(empty);
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      }
+      // plane 1: B_lo, used by A_hi
+      {
+        const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
+        ptx::mbar_wait(full, phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t b = b0 + slot * C::kStageBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
+                            ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
+        ptx::umma_commit(empty);
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      }
+    }
+    ptx::umma_commit(bar_acc_full);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// STRUCT >= 0: the single-formula kernel of that query structure; STRUCT < 0: the grouped
+// kernel, which looks its segment's structure up at run time (CTA-uniform).
+template <int D, int STRUCT>
+__global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fused_tc(const __grid_constant__ LaunchParams p) {
+  using C = Cfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + C::kOffCtl);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int si = 0;
+  if (STRUCT < 0) {
+    for (int i = 1; i < p.n_segs; ++i)
+      if ((int64_t)blockIdx.x >= p.seg[i].tile_begin) si = i;
+  }
+  const SegDev& s = p.seg[si];
+  const int structure = STRUCT >= 0 ? STRUCT : s.structure;
+  const int64_t tile_in_seg = (int64_t)blockIdx.x - s.tile_begin;
+
+  if (wid == C::kWorkerWarps && lane == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&ctl->full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ctl->empty[i]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(&ctl->a_ready), C::kWorkerThreads);
+    ptx::mbar_init(ptx::smem_u32(&ctl->acc_full), 1);
+    ptx::fence_mbar_init();
+  } else if (wid == C::kWorkerWarps + 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&ctl->tmem_base), C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+
+  if (wid < C::kWorkerWarps) {
+    worker<D>(p, s, structure, tile_in_seg, smem, ctl);
+  } else if (wid == C::kWorkerWarps) {
+    if (lane == 0) producer<D>(p, s, structure, smem, ctl);
+    __syncwarp();
+  } else {
+    if (lane == 0) mma_issuer<D>(p, structure, smem, ctl);
+    __syncwarp();
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (wid == C::kWorkerWarps + 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(ctl->tmem_base, C::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// gqe_pack: fp32 [d,d] parameter -> two bf16 planes per 64-wide K block in the smem image
+// the tensor-core kernel streams.  B[n][k] = chain_form ? M[k][n] : M[n][k]
+//   chain_form  : act.mm(M)       (decoders.py:145)
+//   !chain_form : M.mm(embeds)    (decoders.py:150,289,299)
+template <int D>
+__global__ void __launch_bounds__(256) gqe_pack(const __grid_constant__ PackParams p) {
+  const PackEntry& e = p.e[blockIdx.y];
+  uint8_t* out = p.dst + (size_t)blockIdx.y * Cfg<D>::kPackedBytes;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 k) of one n
+  if (item >= D * D / 8) return;
+  int n, kc;
+  if (!e.chain_form) { n = item / (D / 8); kc = item % (D / 8); }
+  else { kc = item / D; n = item % D; }
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = kc * 8 + i;
+    x[i] = e.chain_form ? __ldg(e.src + (size_t)k * D + n) : __ldg(e.src + (size_t)n * D + k);
+  }
+  uint4 hi, lo;
+  split2(x[0], x[1], hi.x, lo.x);
+  split2(x[2], x[3], hi.y, lo.y);
+  split2(x[4], x[5], hi.z, lo.z);
+  split2(x[6], x[7], hi.w, lo.w);
+  const int kb = kc >> 3, c = kc & 7;
+  const uint32_t off = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4));
+  *reinterpret_cast<uint4*>(out + (size_t)(2 * kb) * Cfg<D>::kStageBytes + off) = hi;
+  *reinterpret_cast<uint4*>(out + (size_t)(2 * kb + 1) * Cfg<D>::kStageBytes + off) = lo;
+}
+
+}  // namespace tc
+}  // namespace gqe

@@ -1,0 +1,55 @@
+// gqe_tc_inst.cuh -- instantiates the tensor-core kernels for ONE embedding
+// dimension (GQE_DIM = 128 or 256).
+#pragma once
+#include "gqe_launch.h"
+#include "gqe_tc.cuh"
+
+namespace gqe {
+
+static int tc_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 63;
+}
+
+template <int D, int STRUCT>
+static cudaError_t tc_launch_one(const LaunchParams& lp, int64_t grid, cudaStream_t st) {
+  static bool configured[64] = {false};
+  auto kern = tc::gqe_fused_tc<D, STRUCT>;
+  const int dev = tc_current_device();
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<D>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  kern<<<(unsigned)grid, tc::Cfg<D>::kThreads, tc::Cfg<D>::kSmemBytes, st>>>(lp);
+  return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t tc_launch_struct(int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {
+  switch (structure) {
+    case GQE_CHAIN1: return tc_launch_one<D, GQE_CHAIN1>(lp, grid, st);
+    case GQE_CHAIN2: return tc_launch_one<D, GQE_CHAIN2>(lp, grid, st);
+    case GQE_CHAIN3: return tc_launch_one<D, GQE_CHAIN3>(lp, grid, st);
+    case GQE_INTER2: return tc_launch_one<D, GQE_INTER2>(lp, grid, st);
+    case GQE_INTER3: return tc_launch_one<D, GQE_INTER3>(lp, grid, st);
+    case GQE_INTER_CHAIN3: return tc_launch_one<D, GQE_INTER_CHAIN3>(lp, grid, st);
+    case GQE_CHAIN_INTER3: return tc_launch_one<D, GQE_CHAIN_INTER3>(lp, grid, st);
+    default: return tc_launch_one<D, -1>(lp, grid, st);
+  }
+}
+
+#define GQE_CAT2(a, b) a##b
+#define GQE_CAT(a, b) GQE_CAT2(a, b)
+cudaError_t GQE_CAT(launch_fused_tc_d, GQE_DIM)(int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {
+  return tc_launch_struct<GQE_DIM>(structure, lp, grid, st);
+}
+cudaError_t GQE_CAT(launch_pack_d, GQE_DIM)(const PackParams& pp, int n_entries, cudaStream_t st) {
+  if (n_entries <= 0) return cudaSuccess;
+  const dim3 grid((GQE_DIM * GQE_DIM / 8 + 255) / 256, (unsigned)n_entries);
+  tc::gqe_pack<GQE_DIM><<<grid, 256, 0, st>>>(pp);
+  return cudaGetLastError();
+}
+
+}  // namespace gqe

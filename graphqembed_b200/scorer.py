@@ -43,6 +43,9 @@ class QueryEncoderDecoder(nn.Module):
             raise ValueError("encoder, decoder and intersection dimensions differ")
         self._plans = {}
         self._state = None   # [Context, device index, pointer signature]
+        # arithmetic of the d x d contractions: "bf16x3" = tcgen05 tensor cores with
+        # split-bf16 operands (default), "fp32" = exact CUDA-core FMA (include/gqe.h)
+        self.precision = "bf16x3"
 
     # ---- context / binding ---------------------------------------------------
     def _signature(self):
@@ -69,6 +72,7 @@ class QueryEncoderDecoder(nn.Module):
                 st[0].bind_intersection(_lib.INTER_ID[self.inter_dec.kind], None, None, self.enc.dim)
             st[2] = sig
         st[0].set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        st[0].set_precision(self.precision)
         return st[0]
 
     @property

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GQE_ABI_VERSION 1
+#define GQE_ABI_VERSION 2
 #define GQE_MAX_ANCHORS 3
 #define GQE_MAX_RELS 3
 
@@ -72,6 +72,17 @@ typedef enum gqe_inter {
   GQE_INTER_SIMPLE_MEAN = 2,   /* SimpleSetIntersection(agg=mean) decoders.py:302-319 */
   GQE_INTER_SIMPLE_MIN = 3     /* SimpleSetIntersection(agg=min)                      */
 } gqe_inter;
+
+/* Arithmetic of the d x d contractions (Bilinear projections, DeepSets pre/post).
+ * Everything else (gather, normalisation, cosine, loss) is fp32 in both modes. */
+typedef enum gqe_precision {
+  GQE_PREC_BF16X3 = 0, /* default: tcgen05 tensor cores, operands split x = hi + lo in bf16, three
+                          products hi*hi + lo*hi + hi*lo accumulated in fp32 (relative error ~2^-17
+                          per product; scores within 1e-4 of the fp32 reference).  Used for the
+                          Bilinear decoder at d = 128 / 256 with the regular target layout; every
+                          other combination runs the fp32 kernels. */
+  GQE_PREC_FP32 = 1    /* exact fp32 FMA on the CUDA cores everywhere */
+} gqe_precision;
 
 /*
  * A lowered Formula (reference netquery/graph.py:11-36): which table feeds
@@ -113,6 +124,9 @@ int gqe_abi_version(void);
 int gqe_create(int device, void* stream, gqe_ctx** out);
 void gqe_destroy(gqe_ctx* ctx);
 int gqe_set_stream(gqe_ctx* ctx, void* stream);
+/* Select / query the arithmetic of the contractions (gqe_precision). */
+int gqe_set_precision(gqe_ctx* ctx, int32_t precision);
+int gqe_get_precision(const gqe_ctx* ctx);
 /* Message of the last failure on ctx (ctx == NULL: last gqe_create failure). */
 const char* gqe_last_error(const gqe_ctx* ctx);
 /* Number of kernels this context has launched so far (bench bookkeeping). */
