@@ -240,12 +240,17 @@ def run_native(args):
         pk = peaks()
         ms_per_step = dev_ms / args.steps
         value = world * nq / (ms_per_step * 1e-3)
-        kern_s = ms_per_step * 1e-3 / max(1, launches // args.steps)
+        kern_s = ms_per_step * 1e-3     # gqe_pack + the fused kernel; gqe_pack's share is in profiles/
         bytes_alg, flops_alg = wl.algorithmic_bytes(), wl.algorithmic_flops()
         gbs = bytes_alg / (ms_per_step * 1e-3) / 1e9
         tfl = flops_alg / (ms_per_step * 1e-3) / 1e12
+        # the contractions run as three bf16 tensor-core products per algorithmic one
+        # (hi*hi + lo*hi + hi*lo, fp32 accumulate): the tensor pipe executes 3x the
+        # algorithmic flops, so the usable ceiling is the measured bf16 peak / 3
+        passes = 3
+        tfl_exec = passes * tfl
         t_hbm = bytes_alg / (pk["hbm_gbs"] * 1e9)
-        t_tc = flops_alg / (pk["bf16_tflops"] * 1e12)
+        t_tc = passes * flops_alg / (pk["bf16_tflops"] * 1e12)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -253,25 +258,26 @@ def run_native(args):
                 traffic = json.load(fh).get(name)
         bound = "hbm" if t_hbm >= t_tc else "tensor"
         roof = {"bound": bound,
-                "achieved": round(gbs if bound == "hbm" else tfl, 3),
+                "achieved": round(gbs if bound == "hbm" else tfl_exec, 3),
                 "peak": pk["hbm_gbs"] if bound == "hbm" else pk["bf16_tflops"],
                 "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-                "frac": round((gbs / pk["hbm_gbs"]) if bound == "hbm" else (tfl / pk["bf16_tflops"]), 4),
+                "frac": round((gbs / pk["hbm_gbs"]) if bound == "hbm" else (tfl_exec / pk["bf16_tflops"]), 4),
                 "traffic": traffic, "peak_source": pk["source"],
-                "kernel": "gqe_fused (grouped, one launch per step)",
+                "kernel": "gqe_fused_tc<256,-1> (grouped tcgen05 kernel, one launch per step, preceded by gqe_pack)",
                 "kernel_ms": round(kern_s * 1e3, 4),
                 "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_flops_per_launch": flops_alg,
                 "hbm": {"achieved_gbs": round(gbs, 2), "frac": round(gbs / pk["hbm_gbs"], 4)},
-                "tensor": {"achieved_tflops": round(tfl, 3), "peak_tflops": pk["bf16_tflops"],
-                           "frac": round(tfl / pk["bf16_tflops"], 4),
-                           "note": "d x d contractions; peak = measured bf16 dense"}}
+                "tensor": {"executed_tflops": round(tfl_exec, 3), "algorithmic_tflops": round(tfl, 3),
+                           "peak_tflops": pk["bf16_tflops"], "frac": round(tfl_exec / pk["bf16_tflops"], 4),
+                           "note": "d x d contractions as bf16x3 split products on tcgen05 (3 MMAs per algorithmic "
+                                   "product); executed = 3 x algorithmic; peak = measured sustained bf16 dense"}}
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[name][0], "name": name, "queries_per_step_per_gpu": nq,
                        "targets_per_query": 2, "decoder": wl.decoder, "intersection": wl.inter, "d": wl.d,
-                       "formulas": len(wl.batches), "tables": "replicated per GPU (Bio-size)",
+                       "formulas": len(wl.batches), "contractions": "bf16x3 split on tcgen05, fp32 accumulate (scores within 1e-4 of fp32)", "tables": "replicated per GPU (Bio-size)",
                        "l2": "flushed before every step (256 MiB write)"},
             "e2e": {"value": round(world * nq / (e2e_ms * 1e-3 / args.steps), 1), "unit": UNIT,
                     "h2d_bytes_per_step": int(anchor_rows.nbytes + pair_rows.nbytes), "d2h_bytes_per_step": 4,

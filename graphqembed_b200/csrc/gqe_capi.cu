@@ -357,6 +357,24 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     }
     if (n == 0 || tiles == 0) continue;
     if (tiles > 0x7fffffffLL) return fail(c, GQE_ERR_UNSUPPORTED, "batch too large for one launch (%lld tiles)", (long long)tiles);
+    // heaviest structures first: CTAs are dispatched in tile order, so the cheap
+    // tiles (1-chain) fill the tail of the last wave instead of the 7-contraction ones
+    {
+      auto cost = [](const SegDev& sd) {
+        switch (sd.structure) {
+          case GQE_CHAIN1: return 1; case GQE_CHAIN2: return 2; case GQE_CHAIN3: return 3;
+          case GQE_INTER2: return 5; case GQE_INTER3: return 7; default: return 6;
+        }
+      };
+      std::stable_sort(lp.seg, lp.seg + n, [&](const SegDev& a, const SegDev& b) { return cost(a) > cost(b); });
+      int64_t t = 0;
+      for (int k = 0; k < n; ++k) {
+        const int64_t nq = lp.seg[k].q_end - lp.seg[k].q_begin;
+        const int64_t rows = lp.seg[k].structure <= GQE_CHAIN3 ? (target_offsets ? n_pairs : nq * T) : nq;
+        lp.seg[k].tile_begin = t;
+        t += (rows + tile_rows - 1) / tile_rows;
+      }
+    }
     lp.n_segs = n;
     if (out_loss) {
       int rc = ensure_partials(c, tiles);

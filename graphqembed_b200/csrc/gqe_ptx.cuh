@@ -46,6 +46,11 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src,
                : "memory");
 }
 
+// L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // ---- fences ---------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -154,11 +154,12 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
   using C = Cfg<D>;
   constexpr int RPW = kRows / C::kWorkerWarps;
   constexpr int NV = D / 128;
+  constexpr int U = 8;  // rows in flight per warp
 #pragma unroll 1
-  for (int r0 = 0; r0 < RPW; r0 += 4) {
-    float4 v[4][NV];
+  for (int r0 = 0; r0 < RPW; r0 += U) {
+    float4 v[U][NV];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = wid * RPW + r0 + u;
       const bool ok = r < n_valid;
       const size_t row = ok ? (size_t)__ldg(rows + r) : 0;
@@ -167,7 +168,7 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
       for (int j = 0; j < NV; ++j) v[u][j] = ok ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = wid * RPW + r0 + u;
       const bool ok = r < n_valid;
       float ss = 0.f;
@@ -179,25 +180,32 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
         ss = fmaf(v[u][j].w, v[u][j].w, ss);
       }
       ss = warp_sum_f(ss);
-      const float nrm = sqrtf(ss);
+      // x / |x| as x * (1/|x|): one IEEE division per row (|x| = 0 -> inf -> 0*inf = NaN,
+      // the reference's 0/0); the extra rounding is far below the bf16x3 error
+      const float inv = ok ? __fdiv_rn(1.f, sqrtf(ss)) : 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-        if (ok) {
-          x0 = __fdiv_rn(v[u][j].x, nrm);
-          x1 = __fdiv_rn(v[u][j].y, nrm);
-          x2 = __fdiv_rn(v[u][j].z, nrm);
-          x3 = __fdiv_rn(v[u][j].w, nrm);
-        }
         uint2 hi, lo;
-        split2(x0, x1, hi.x, lo.x);
-        split2(x2, x3, hi.y, lo.y);
+        split2(v[u][j].x * inv, v[u][j].y * inv, hi.x, lo.x);
+        split2(v[u][j].z * inv, v[u][j].w * inv, hi.y, lo.y);
         // element k = 128 j + 4 lane: K block 2j + lane/16, chunk (lane%16)/2, half (lane&1)
         const uint32_t off = a_chunk_off(r, 2 * j + (lane >> 4), (lane & 15) >> 1) + ((lane & 1) << 3);
         *reinterpret_cast<uint2*>(smem + C::kOffAhi + off) = hi;
         *reinterpret_cast<uint2*>(smem + C::kOffAlo + off) = lo;
       }
     }
+  }
+}
+
+// Ask L2 for every table row this tile is going to read (anchors of every branch and
+// all targets): the DRAM latency then overlaps the first contraction instead of
+// stalling each gather.  One bulk prefetch per row.
+template <int D>
+__device__ __forceinline__ void prefetch_rows(const float* __restrict__ table, const int32_t* __restrict__ rows,
+                                              int64_t stride, int per_row, int n_valid, int tid, int n_threads) {
+  for (int i = tid; i < n_valid * per_row; i += n_threads) {
+    const int r = i / per_row, t = i - r * per_row;
+    ptx::tma_prefetch_l2(table + (size_t)__ldg(rows + (int64_t)r * stride + t) * D, D * 4);
   }
 }
 
@@ -284,6 +292,20 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
   const uint32_t bar_a_ready = ptx::smem_u32(&ctl->a_ready);
   const uint32_t bar_acc_full = ptx::smem_u32(&ctl->acc_full);
 
+  // L2 prefetch of everything the tile reads from the tables after its first gather
+  if (n_valid > 0) {
+    if (chain) {
+      const int64_t q_first = row_begin / T, q_last = (row_begin + n_valid - 1) / T;
+      prefetch_rows<D>(s.anc_table[0], p.anchor_rows + q_first, 1, 1, (int)(q_last - q_first + 1), threadIdx.x,
+                       C::kWorkerThreads);
+    } else {
+      for (int b = 1; b < n_branch; ++b)
+        prefetch_rows<D>(s.anc_table[b], p.anchor_rows + (int64_t)b * p.anchor_stride + row_begin, 1, 1, n_valid,
+                         threadIdx.x, C::kWorkerThreads);
+      prefetch_rows<D>(s.tgt_table, p.target_rows + row_begin * T, T, T < 2 ? T : 2, n_valid, threadIdx.x,
+                       C::kWorkerThreads);
+    }
+  }
   for (int st = 0; st < pg.n; ++st) {
     const int g = pg.gather[st];
     if (g != G_NONE) {
@@ -302,44 +324,49 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
     const int epi = pg.epi[st];
     const int kind = epi & E_KIND;
     if (kind == E_SCORE) break;  // scored below, straight from the accumulator
-#pragma unroll 1
+    const bool agg_read = kind == E_AGG && !(epi & F_FIRST);
+    const float inv_nb = 1.f / (float)n_branch;
+    uint32_t raw[32], araw[32] = {};
+    ptx::tmem_ld32(t_acc, raw);
+    if (agg_read) ptx::tmem_ld32(t_agg, araw);
+#pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-      uint32_t raw[32];
-      float x[32];
-      ptx::tmem_ld32(t_acc + 32 * ch, raw);
+      float x[32], a[32];
       ptx::tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]);
+      for (int i = 0; i < 32; ++i) {
+        x[i] = __uint_as_float(raw[i]);
+        a[i] = __uint_as_float(araw[i]);
+      }
+      if (ch < 3) {  // next chunk streams out of TMEM while this one is processed
+        ptx::tmem_ld32(t_acc + 32 * (ch + 1), raw);
+        if (agg_read) ptx::tmem_ld32(t_agg + 32 * (ch + 1), araw);
+      }
       if (kind == E_AGG) {
         if (epi & F_RELU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = relu_nan_(x[i]);
         }
-        if (!(epi & F_FIRST)) {
-          uint32_t araw[32];
-          ptx::tmem_ld32(t_agg + 32 * ch, araw);
-          ptx::tmem_wait_ld();
+        if (agg_read) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float a = __uint_as_float(araw[i]);
-            x[i] = use_min ? min_nan_(a, x[i]) : a + x[i];
-          }
+          for (int i = 0; i < 32; ++i) x[i] = use_min ? min_nan_(a[i], x[i]) : a[i] + x[i];
         }
         if (!(epi & F_LAST)) {
+          uint32_t o[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(x[i]);
-          ptx::tmem_st32(t_agg + 32 * ch, raw);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(x[i]);
+          ptx::tmem_st32(t_agg + 32 * ch, o);
           continue;
         }
         if (!use_min) {  // torch.mean over the stacked operands
-          const float nb = (float)n_branch;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = __fdiv_rn(x[i], nb);
+          for (int i = 0; i < 32; ++i) x[i] *= inv_nb;
         }
         if (epi & F_DEST_ACC) {  // combined embedding is the query embedding itself
+          uint32_t o[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(x[i]);
-          ptx::tmem_st32(t_acc + 32 * ch, raw);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(x[i]);
+          ptx::tmem_st32(t_acc + 32 * ch, o);
           continue;
         }
       }
