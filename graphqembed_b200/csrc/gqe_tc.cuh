@@ -21,8 +21,9 @@
 //     kept in a second TMEM region, or the cosine / margin loss against the gathered
 //     target rows) and never write an intermediate to global memory.
 //
-// Warp roles: warps [0, W) workers (W = d/32), warp W = TMA producer, warp W+1 =
-// MMA issuer + TMEM owner.
+// Warp roles: warps [0, W) workers (W = d/16: four TMEM lane quarters x d/64 column
+// groups, thread == one row x 64 columns), warp W = TMA producer, warp W+1 = MMA
+// issuer + TMEM owner.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -41,7 +42,9 @@ constexpr int kMaxSteps = 8;
 
 template <int D>
 struct Cfg {
-  static constexpr int kWorkerWarps = D / 32;  // each worker thread owns 128 columns of one row
+  static constexpr int kColsPerThread = 64;    // each worker thread owns 64 columns of one row
+  static constexpr int kColGroups = D / kColsPerThread;
+  static constexpr int kWorkerWarps = 4 * kColGroups;  // 4 TMEM lane quarters x column groups
   static constexpr int kWorkerThreads = kWorkerWarps * 32;
   static constexpr int kThreads = kWorkerThreads + 64;
   static constexpr int kKB = D / kKBlock;
@@ -64,7 +67,7 @@ struct Ctl {
   uint64_t empty[kStages];
   uint64_t a_ready;
   uint64_t acc_full;
-  double red[8];
+  double red[16];
   uint32_t tmem_base;
   int last;
 };
@@ -154,7 +157,7 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
   using C = Cfg<D>;
   constexpr int RPW = kRows / C::kWorkerWarps;
   constexpr int NV = D / 128;
-  constexpr int U = 8;  // rows in flight per warp
+  constexpr int U = D >= 256 ? 4 : 8;  // rows in flight per warp (register budget)
 #pragma unroll 1
   for (int r0 = 0; r0 < RPW; r0 += U) {
     float4 v[U][NV];
@@ -209,13 +212,13 @@ __device__ __forceinline__ void prefetch_rows(const float* __restrict__ table, c
   }
 }
 
-// 32 fp32 values of (row r, columns col0..col0+31) -> the A operand planes
+// 16 fp32 values of (row r, columns col0..col0+15) -> the A operand planes
 template <int D>
-__device__ __forceinline__ void store_a32(uint8_t* smem, int r, int col0, const float (&x)[32]) {
+__device__ __forceinline__ void store_a16(uint8_t* smem, int r, int col0, const float (&x)[16]) {
   using C = Cfg<D>;
   const int kb = col0 >> 6, c0 = (col0 & 63) >> 3;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 2; ++j) {
     uint4 hi, lo;
     split2(x[8 * j + 0], x[8 * j + 1], hi.x, lo.x);
     split2(x[8 * j + 2], x[8 * j + 3], hi.y, lo.y);
@@ -264,13 +267,32 @@ __device__ __forceinline__ void loss_reduce(const LaunchParams& p, Ctl* ctl, dou
 }
 
 // ---- worker warps ---------------------------------------------------------------------
+// dot / squared norms of 16 accumulator columns against 16 floats of a table row
+__device__ __forceinline__ void dot16(const uint32_t (&raw)[16], const float4 (&a)[4], float& dot, float& aa) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float y0 = __uint_as_float(raw[4 * i]), y1 = __uint_as_float(raw[4 * i + 1]);
+    const float y2 = __uint_as_float(raw[4 * i + 2]), y3 = __uint_as_float(raw[4 * i + 3]);
+    dot = fmaf(y0, a[i].x, dot); dot = fmaf(y1, a[i].y, dot); dot = fmaf(y2, a[i].z, dot); dot = fmaf(y3, a[i].w, dot);
+    aa = fmaf(a[i].x, a[i].x, aa); aa = fmaf(a[i].y, a[i].y, aa); aa = fmaf(a[i].z, a[i].z, aa); aa = fmaf(a[i].w, a[i].w, aa);
+  }
+}
+__device__ __forceinline__ float sumsq16(const uint32_t (&raw)[16]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s = fmaf(__uint_as_float(raw[i]), __uint_as_float(raw[i]), s);
+  return s;
+}
+
 template <int D>
 __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, int structure, int64_t tile_in_seg,
                                        uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
+  constexpr int NCH = C::kColsPerThread / 16;  // 16-column TMEM chunks per thread
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = 32 * (wid & 3) + lane;      // TMEM lane == tile row
-  const int col_base = (wid >> 2) * 128;      // this thread's 128 columns
+  const int row = 32 * (wid & 3) + lane;                 // TMEM lane == tile row
+  const int grp = wid >> 2;                              // column group of this thread
+  const int col_base = grp * C::kColsPerThread;
   const bool chain = structure <= GQE_CHAIN3;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
   const bool use_min = p.inter == GQE_INTER_DEEPSETS_MIN || p.inter == GQE_INTER_SIMPLE_MIN;
@@ -306,6 +328,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
                        C::kWorkerThreads);
     }
   }
+
   for (int st = 0; st < pg.n; ++st) {
     const int g = pg.gather[st];
     if (g != G_NONE) {
@@ -326,105 +349,102 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
     if (kind == E_SCORE) break;  // scored below, straight from the accumulator
     const bool agg_read = kind == E_AGG && !(epi & F_FIRST);
     const float inv_nb = 1.f / (float)n_branch;
-    uint32_t raw[32], araw[32] = {};
-    ptx::tmem_ld32(t_acc, raw);
-    if (agg_read) ptx::tmem_ld32(t_agg, araw);
+    uint32_t raw[16], araw[16] = {};
+    ptx::tmem_ld16(t_acc, raw);
+    if (agg_read) ptx::tmem_ld16(t_agg, araw);
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      float x[32], a[32];
+    for (int ch = 0; ch < NCH; ++ch) {
+      float x[16], a[16];
       ptx::tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 16; ++i) {
         x[i] = __uint_as_float(raw[i]);
         a[i] = __uint_as_float(araw[i]);
       }
-      if (ch < 3) {  // next chunk streams out of TMEM while this one is processed
-        ptx::tmem_ld32(t_acc + 32 * (ch + 1), raw);
-        if (agg_read) ptx::tmem_ld32(t_agg + 32 * (ch + 1), araw);
+      if (ch + 1 < NCH) {  // next chunk streams out of TMEM while this one is processed
+        ptx::tmem_ld16(t_acc + 16 * (ch + 1), raw);
+        if (agg_read) ptx::tmem_ld16(t_agg + 16 * (ch + 1), araw);
       }
       if (kind == E_AGG) {
         if (epi & F_RELU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = relu_nan_(x[i]);
+          for (int i = 0; i < 16; ++i) x[i] = relu_nan_(x[i]);
         }
         if (agg_read) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = use_min ? min_nan_(a[i], x[i]) : a[i] + x[i];
+          for (int i = 0; i < 16; ++i) x[i] = use_min ? min_nan_(a[i], x[i]) : a[i] + x[i];
         }
         if (!(epi & F_LAST)) {
-          uint32_t o[32];
+          uint32_t o[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(x[i]);
-          ptx::tmem_st32(t_agg + 32 * ch, o);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(x[i]);
+          ptx::tmem_st16(t_agg + 16 * ch, o);
           continue;
         }
         if (!use_min) {  // torch.mean over the stacked operands
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] *= inv_nb;
+          for (int i = 0; i < 16; ++i) x[i] *= inv_nb;
         }
         if (epi & F_DEST_ACC) {  // combined embedding is the query embedding itself
-          uint32_t o[32];
+          uint32_t o[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(x[i]);
-          ptx::tmem_st32(t_acc + 32 * ch, o);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(x[i]);
+          ptx::tmem_st16(t_acc + 16 * ch, o);
           continue;
         }
       }
-      store_a32<D>(smem, row, col_base + 32 * ch, x);
+      store_a16<D>(smem, row, col_base + 16 * ch, x);
     }
     ptx::tmem_wait_st();
     if (kind == E_AGG && (epi & F_DEST_ACC)) break;
   }
 
   // ---- score: the accumulator row is the projected target (chains) or the query
-  // embedding (intersections); thread == row, no intermediate leaves the SM -------
-  float* scratch = reinterpret_cast<float*>(smem);  // A planes are dead now
+  // embedding (intersections); thread == row x 64 columns, the column groups of a
+  // row meet in shared memory (the A planes are dead by now) ------------------------
+  float* scratch = reinterpret_cast<float*>(smem);
+  float* score_sm = scratch + kRows * 8 * (C::kColGroups - 1);
   if (chain) {
     const int64_t pair = row_begin + row;
     const float* a_src = s.anc_table[0];
     if (valid) a_src += (size_t)__ldg(p.anchor_rows + pair / T) * D + col_base;
     float dot = 0.f, yy = 0.f, aa = 0.f;
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      uint32_t raw[32];
-      ptx::tmem_ld32(t_acc + 32 * ch, raw);
-      float4 a[8];
+    float4 a[NCH][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        a[i] = valid ? __ldg(reinterpret_cast<const float4*>(a_src + 32 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        a[ch][i] = valid ? __ldg(reinterpret_cast<const float4*>(a_src + 16 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      uint32_t raw[16];
+      ptx::tmem_ld16(t_acc + 16 * ch, raw);
       ptx::tmem_wait_ld();
+      dot16(raw, a[ch], dot, aa);
+      yy += sumsq16(raw);
+    }
+    if (grp != 0) {
+      float* sp = scratch + ((grp - 1) * kRows + row) * 8;
+      sp[0] = dot; sp[1] = yy; sp[2] = aa;
+    }
+    ptx::named_bar_sync(1, C::kWorkerThreads);
+    if (grp == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float y0 = __uint_as_float(raw[4 * i]), y1 = __uint_as_float(raw[4 * i + 1]);
-        const float y2 = __uint_as_float(raw[4 * i + 2]), y3 = __uint_as_float(raw[4 * i + 3]);
-        dot = fmaf(y0, a[i].x, dot); dot = fmaf(y1, a[i].y, dot); dot = fmaf(y2, a[i].z, dot); dot = fmaf(y3, a[i].w, dot);
-        yy = fmaf(y0, y0, yy); yy = fmaf(y1, y1, yy); yy = fmaf(y2, y2, yy); yy = fmaf(y3, y3, yy);
-        aa = fmaf(a[i].x, a[i].x, aa); aa = fmaf(a[i].y, a[i].y, aa); aa = fmaf(a[i].z, a[i].z, aa); aa = fmaf(a[i].w, a[i].w, aa);
+      for (int g2 = 1; g2 < C::kColGroups; ++g2) {
+        const float* sp = scratch + ((g2 - 1) * kRows + row) * 8;
+        dot += sp[0]; yy += sp[1]; aa += sp[2];
       }
-    }
-    if (D == 256) {  // the two column halves of a row meet in shared memory
-      if (col_base != 0) {
-        scratch[row * 4 + 0] = dot; scratch[row * 4 + 1] = yy; scratch[row * 4 + 2] = aa;
-      }
-      ptx::named_bar_sync(1, C::kWorkerThreads);
-      if (col_base == 0) {
-        dot += scratch[row * 4 + 0]; yy += scratch[row * 4 + 1]; aa += scratch[row * 4 + 2];
-      }
-      ptx::named_bar_sync(1, C::kWorkerThreads);
-    }
-    // cos(y, a_hat) with a_hat = a/|a| (unit norm): (y.a/|a|) / max(|y|, eps); a zero
-    // anchor row gives 0/0 = NaN as in the reference
-    float score = 0.f;
-    if (col_base == 0) {
-      score = __fdiv_rn(dot, sqrtf(aa)) / fmaxf(sqrtf(yy), kCosEps);
+      // cos(y, a_hat) with a_hat = a/|a| (unit norm): (y.a/|a|) / max(|y|, eps); a zero
+      // anchor row gives 0/0 = NaN as in the reference
+      const float score = __fdiv_rn(dot, sqrtf(aa)) / fmaxf(sqrtf(yy), kCosEps);
       if (valid && p.out_scores) p.out_scores[pair] = score;
-      scratch[512 + row] = score;
+      score_sm[row] = score;
     }
     if (p.out_loss) {
       ptx::named_bar_sync(1, C::kWorkerThreads);
       double local = 0.0;
       if (threadIdx.x < kRows / 2 && 2 * (int)threadIdx.x + 1 < n_valid)
-        local = (double)hinge_(p.margin, scratch[512 + 2 * threadIdx.x], scratch[512 + 2 * threadIdx.x + 1]);
+        local = (double)hinge_(p.margin, score_sm[2 * threadIdx.x], score_sm[2 * threadIdx.x + 1]);
       loss_reduce<D>(p, ctl, local, wid, lane);
     }
   } else {
@@ -441,42 +461,36 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
         if (has1) src1 += (size_t)__ldg(p.target_rows + q * T + t0 + 1) * D + col_base;
       }
       float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f, qs = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t raw[32];
-        ptx::tmem_ld32(t_acc + 32 * ch, raw);
-        float4 a[8], b[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          a[i] = valid ? __ldg(reinterpret_cast<const float4*>(src0 + 32 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          b[i] = (valid && has1) ? __ldg(reinterpret_cast<const float4*>(src1 + 32 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ch = 0; ch < NCH; ++ch) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i] = valid ? __ldg(reinterpret_cast<const float4*>(src0 + 16 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[i] = (valid && has1) ? __ldg(reinterpret_cast<const float4*>(src1 + 16 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        uint32_t raw[16];
+        ptx::tmem_ld16(t_acc + 16 * ch, raw);
         ptx::tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float y0 = __uint_as_float(raw[4 * i]), y1 = __uint_as_float(raw[4 * i + 1]);
-          const float y2 = __uint_as_float(raw[4 * i + 2]), y3 = __uint_as_float(raw[4 * i + 3]);
-          qs = fmaf(y0, y0, qs); qs = fmaf(y1, y1, qs); qs = fmaf(y2, y2, qs); qs = fmaf(y3, y3, qs);
-          d0 = fmaf(y0, a[i].x, d0); d0 = fmaf(y1, a[i].y, d0); d0 = fmaf(y2, a[i].z, d0); d0 = fmaf(y3, a[i].w, d0);
-          n0 = fmaf(a[i].x, a[i].x, n0); n0 = fmaf(a[i].y, a[i].y, n0); n0 = fmaf(a[i].z, a[i].z, n0); n0 = fmaf(a[i].w, a[i].w, n0);
-          d1 = fmaf(y0, b[i].x, d1); d1 = fmaf(y1, b[i].y, d1); d1 = fmaf(y2, b[i].z, d1); d1 = fmaf(y3, b[i].w, d1);
-          n1 = fmaf(b[i].x, b[i].x, n1); n1 = fmaf(b[i].y, b[i].y, n1); n1 = fmaf(b[i].z, b[i].z, n1); n1 = fmaf(b[i].w, b[i].w, n1);
-        }
+        dot16(raw, a, d0, n0);
+        dot16(raw, b, d1, n1);
+        qs += sumsq16(raw);
       }
-      if (D == 256) {
-        if (col_base != 0) {
-          float* sp = scratch + row * 8;
-          sp[0] = d0; sp[1] = d1; sp[2] = n0; sp[3] = n1; sp[4] = qs;
-        }
-        ptx::named_bar_sync(1, C::kWorkerThreads);
-        if (col_base == 0) {
-          const float* sp = scratch + row * 8;
+      if (grp != 0) {
+        float* sp = scratch + ((grp - 1) * kRows + row) * 8;
+        sp[0] = d0; sp[1] = d1; sp[2] = n0; sp[3] = n1; sp[4] = qs;
+      }
+      ptx::named_bar_sync(1, C::kWorkerThreads);
+      if (grp == 0) {
+#pragma unroll
+        for (int g2 = 1; g2 < C::kColGroups; ++g2) {
+          const float* sp = scratch + ((g2 - 1) * kRows + row) * 8;
           d0 += sp[0]; d1 += sp[1]; n0 += sp[2]; n1 += sp[3]; qs += sp[4];
         }
-        ptx::named_bar_sync(1, C::kWorkerThreads);
       }
+      ptx::named_bar_sync(1, C::kWorkerThreads);
       if (t0 == 0) qq = qs;
-      if (col_base == 0 && valid) {
+      if (grp == 0 && valid) {
         // t_hat = t/|t| has unit norm: cos(t_hat, q) = (t.q/|t|) / max(|q|, eps); a zero
         // target row gives 0/0 = NaN as in the reference
         const float nq = fmaxf(sqrtf(qq), kCosEps);
