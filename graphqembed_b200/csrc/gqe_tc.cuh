@@ -151,9 +151,11 @@ __device__ __forceinline__ uint32_t a_chunk_off(int r, int kb, int c) {
 // ---- DirectEncoder: gather, L2-normalise, split, park as the A operand ---------------
 // (reference netquery/encoders.py:41-43; true division, no epsilon.)  A warp reads
 // one table row per instruction group with 128-bit loads, fully coalesced.
+// `my_row` holds, in lane i, the table row of tile row wid*RPW + i (-1: past the end);
+// the index loads were issued at tile start so only the row loads are exposed here.
 template <int D>
-__device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restrict__ table,
-                                            const int32_t* __restrict__ rows, int n_valid, int wid, int lane) {
+__device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restrict__ table, int32_t my_row, int wid,
+                                            int lane) {
   using C = Cfg<D>;
   constexpr int RPW = kRows / C::kWorkerWarps;
   constexpr int NV = D / 128;
@@ -161,19 +163,18 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
 #pragma unroll 1
   for (int r0 = 0; r0 < RPW; r0 += U) {
     float4 v[U][NV];
+    bool okv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int r = wid * RPW + r0 + u;
-      const bool ok = r < n_valid;
-      const size_t row = ok ? (size_t)__ldg(rows + r) : 0;
-      const float4* src = reinterpret_cast<const float4*>(table + row * D);
+      const int32_t row = __shfl_sync(0xffffffffu, my_row, r0 + u);
+      okv[u] = row >= 0;
+      const float4* src = reinterpret_cast<const float4*>(table + (size_t)(okv[u] ? row : 0) * D);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[u][j] = ok ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NV; ++j) v[u][j] = okv[u] ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int r = wid * RPW + r0 + u;
-      const bool ok = r < n_valid;
       float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
@@ -185,7 +186,7 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
       ss = warp_sum_f(ss);
       // x / |x| as x * (1/|x|): one IEEE division per row (|x| = 0 -> inf -> 0*inf = NaN,
       // the reference's 0/0); the extra rounding is far below the bf16x3 error
-      const float inv = ok ? __fdiv_rn(1.f, sqrtf(ss)) : 0.f;
+      const float inv = okv[u] ? __fdiv_rn(1.f, sqrtf(ss)) : 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         uint2 hi, lo;
@@ -197,18 +198,6 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
         *reinterpret_cast<uint2*>(smem + C::kOffAlo + off) = lo;
       }
     }
-  }
-}
-
-// Ask L2 for every table row this tile is going to read (anchors of every branch and
-// all targets): the DRAM latency then overlaps the first contraction instead of
-// stalling each gather.  One bulk prefetch per row.
-template <int D>
-__device__ __forceinline__ void prefetch_rows(const float* __restrict__ table, const int32_t* __restrict__ rows,
-                                              int64_t stride, int per_row, int n_valid, int tid, int n_threads) {
-  for (int i = tid; i < n_valid * per_row; i += n_threads) {
-    const int r = i / per_row, t = i - r * per_row;
-    ptx::tma_prefetch_l2(table + (size_t)__ldg(rows + (int64_t)r * stride + t) * D, D * 4);
   }
 }
 
@@ -267,32 +256,17 @@ __device__ __forceinline__ void loss_reduce(const LaunchParams& p, Ctl* ctl, dou
 }
 
 // ---- worker warps ---------------------------------------------------------------------
-// dot / squared norms of 16 accumulator columns against 16 floats of a table row
-__device__ __forceinline__ void dot16(const uint32_t (&raw)[16], const float4 (&a)[4], float& dot, float& aa) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float y0 = __uint_as_float(raw[4 * i]), y1 = __uint_as_float(raw[4 * i + 1]);
-    const float y2 = __uint_as_float(raw[4 * i + 2]), y3 = __uint_as_float(raw[4 * i + 3]);
-    dot = fmaf(y0, a[i].x, dot); dot = fmaf(y1, a[i].y, dot); dot = fmaf(y2, a[i].z, dot); dot = fmaf(y3, a[i].w, dot);
-    aa = fmaf(a[i].x, a[i].x, aa); aa = fmaf(a[i].y, a[i].y, aa); aa = fmaf(a[i].z, a[i].z, aa); aa = fmaf(a[i].w, a[i].w, aa);
-  }
-}
-__device__ __forceinline__ float sumsq16(const uint32_t (&raw)[16]) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) s = fmaf(__uint_as_float(raw[i]), __uint_as_float(raw[i]), s);
-  return s;
-}
-
 template <int D>
 __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, int structure, int64_t tile_in_seg,
                                        uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
-  constexpr int NCH = C::kColsPerThread / 16;  // 16-column TMEM chunks per thread
+  constexpr int NCH = C::kColsPerThread / 16;      // 16-column TMEM chunks per thread
+  constexpr int RPW = kRows / C::kWorkerWarps;     // tile rows per warp in the warp-per-row phases
+  constexpr int NV = D / 128;                      // float4 per lane per table row
+  constexpr int QS = D + 4;                        // fp32 row stride of the transposed query tile
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = 32 * (wid & 3) + lane;                 // TMEM lane == tile row
-  const int grp = wid >> 2;                              // column group of this thread
-  const int col_base = grp * C::kColsPerThread;
+  const int row = 32 * (wid & 3) + lane;           // TMEM lane == tile row (thread-per-row phases)
+  const int col_base = (wid >> 2) * C::kColsPerThread;
   const bool chain = structure <= GQE_CHAIN3;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
   const bool use_min = p.inter == GQE_INTER_DEEPSETS_MIN || p.inter == GQE_INTER_SIMPLE_MIN;
@@ -303,7 +277,6 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
   const int64_t row_begin = (chain ? s.q_begin * T : s.q_begin) + tile_in_seg * kRows;
   const int64_t row_end = chain ? s.q_end * T : s.q_end;
   const int n_valid = (int)min((int64_t)kRows, row_end - row_begin);
-  const bool valid = row < n_valid;
 
   Prog pg;
   build_program(pg, structure, deepsets);
@@ -314,26 +287,36 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
   const uint32_t bar_a_ready = ptx::smem_u32(&ctl->a_ready);
   const uint32_t bar_acc_full = ptx::smem_u32(&ctl->acc_full);
 
-  // L2 prefetch of everything the tile reads from the tables after its first gather
-  if (n_valid > 0) {
-    if (chain) {
-      const int64_t q_first = row_begin / T, q_last = (row_begin + n_valid - 1) / T;
-      prefetch_rows<D>(s.anc_table[0], p.anchor_rows + q_first, 1, 1, (int)(q_last - q_first + 1), threadIdx.x,
-                       C::kWorkerThreads);
-    } else {
-      for (int b = 1; b < n_branch; ++b)
-        prefetch_rows<D>(s.anc_table[b], p.anchor_rows + (int64_t)b * p.anchor_stride + row_begin, 1, 1, n_valid,
-                         threadIdx.x, C::kWorkerThreads);
-      prefetch_rows<D>(s.tgt_table, p.target_rows + row_begin * T, T, T < 2 ? T : 2, n_valid, threadIdx.x,
-                       C::kWorkerThreads);
+  // ---- every index this warp will need, loaded once, up front (lane i <-> tile row
+  // wid*RPW + i), and an L2 prefetch of the table rows behind them: the DRAM latency of
+  // the later gathers and of the scoring rows overlaps the first contraction ------------
+  const int my_r = wid * RPW + lane;               // meaningful for lane < RPW
+  const bool mine = lane < RPW && my_r < n_valid;
+  int32_t gsrc0 = -1, gsrc1 = -1, gsrc2 = -1;      // gather sources: anchors 0..2 or (chains) the targets
+  int32_t ssrc0 = -1, ssrc1 = -1;                  // scoring rows: the anchor (chains) or targets 0, 1
+  if (chain) {
+    if (mine) {
+      gsrc0 = __ldg(p.target_rows + row_begin + my_r);
+      ssrc0 = __ldg(p.anchor_rows + (row_begin + my_r) / T);
+      ptx::tma_prefetch_l2(s.anc_table[0] + (size_t)ssrc0 * D, D * 4);
     }
+  } else if (mine) {
+    gsrc0 = __ldg(p.anchor_rows + row_begin + my_r);
+    gsrc1 = __ldg(p.anchor_rows + p.anchor_stride + row_begin + my_r);
+    if (n_branch > 2) gsrc2 = __ldg(p.anchor_rows + 2 * p.anchor_stride + row_begin + my_r);
+    ssrc0 = __ldg(p.target_rows + (row_begin + my_r) * T);
+    if (T > 1) ssrc1 = __ldg(p.target_rows + (row_begin + my_r) * T + 1);
+    ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
+    if (n_branch > 2) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
+    ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
+    if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
   }
 
   for (int st = 0; st < pg.n; ++st) {
     const int g = pg.gather[st];
     if (g != G_NONE) {
-      if (g == G_TARGET) gather_to_a<D>(smem, s.tgt_table, p.target_rows + row_begin, n_valid, wid, lane);
-      else gather_to_a<D>(smem, s.anc_table[g], p.anchor_rows + (int64_t)g * p.anchor_stride + row_begin, n_valid, wid, lane);
+      if (g == G_TARGET) gather_to_a<D>(smem, s.tgt_table, gsrc0, wid, lane);
+      else gather_to_a<D>(smem, s.anc_table[g], g == 0 ? gsrc0 : (g == 1 ? gsrc1 : gsrc2), wid, lane);
     }
     // A operand complete (generic-proxy stores -> async proxy) and this thread's
     // TMEM reads of the previous accumulator retired: hand over to the MMA issuer
@@ -399,112 +382,104 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
     if (kind == E_AGG && (epi & F_DEST_ACC)) break;
   }
 
-  // ---- score: the accumulator row is the projected target (chains) or the query
-  // embedding (intersections); thread == row x 64 columns, the column groups of a
-  // row meet in shared memory (the A planes are dead by now) ------------------------
-  float* scratch = reinterpret_cast<float*>(smem);
-  float* score_sm = scratch + kRows * 8 * (C::kColGroups - 1);
+  // ---- score ------------------------------------------------------------------------
+  // The accumulator row is the projected target (chains) or the query embedding
+  // (intersections).  It is transposed through shared memory (the A planes and the weight
+  // ring are dead by now) so that the table rows it is scored against are read warp-per-row
+  // with coalesced 128-bit loads, like the gathers.
+  float* qsm = reinterpret_cast<float*>(smem);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t raw[16];
+    ptx::tmem_ld16(t_acc + 16 * ch, raw);
+    ptx::tmem_wait_ld();
+    float4* dst = reinterpret_cast<float4*>(qsm + (size_t)row * QS + col_base + 16 * ch);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      dst[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
+                           __uint_as_float(raw[4 * i + 3]));
+  }
+  ptx::named_bar_sync(1, C::kWorkerThreads);
+
+  double local = 0.0;
   if (chain) {
-    const int64_t pair = row_begin + row;
-    const float* a_src = s.anc_table[0];
-    if (valid) a_src += (size_t)__ldg(p.anchor_rows + pair / T) * D + col_base;
-    float dot = 0.f, yy = 0.f, aa = 0.f;
-    float4 a[NCH][4];
+    float s_even = 0.f;
+#pragma unroll 2
+    for (int u = 0; u < RPW; ++u) {
+      const int r = wid * RPW + u;
+      const int32_t arow = __shfl_sync(0xffffffffu, ssrc0, u);
+      if (arow < 0) continue;  // warp-uniform: row past the end of the tile
+      const float4* a_src = reinterpret_cast<const float4*>(s.anc_table[0] + (size_t)arow * D);
+      const float4* q_src = reinterpret_cast<const float4*>(qsm + (size_t)r * QS);
+      float dot = 0.f, yy = 0.f, aa = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        a[ch][i] = valid ? __ldg(reinterpret_cast<const float4*>(a_src + 16 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      uint32_t raw[16];
-      ptx::tmem_ld16(t_acc + 16 * ch, raw);
-      ptx::tmem_wait_ld();
-      dot16(raw, a[ch], dot, aa);
-      yy += sumsq16(raw);
-    }
-    if (grp != 0) {
-      float* sp = scratch + ((grp - 1) * kRows + row) * 8;
-      sp[0] = dot; sp[1] = yy; sp[2] = aa;
-    }
-    ptx::named_bar_sync(1, C::kWorkerThreads);
-    if (grp == 0) {
-#pragma unroll
-      for (int g2 = 1; g2 < C::kColGroups; ++g2) {
-        const float* sp = scratch + ((g2 - 1) * kRows + row) * 8;
-        dot += sp[0]; yy += sp[1]; aa += sp[2];
+      for (int j = 0; j < NV; ++j) {
+        const float4 a = __ldg(a_src + lane + 32 * j);
+        const float4 y = q_src[lane + 32 * j];
+        dot = fmaf(y.x, a.x, dot); dot = fmaf(y.y, a.y, dot); dot = fmaf(y.z, a.z, dot); dot = fmaf(y.w, a.w, dot);
+        yy = fmaf(y.x, y.x, yy); yy = fmaf(y.y, y.y, yy); yy = fmaf(y.z, y.z, yy); yy = fmaf(y.w, y.w, yy);
+        aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
       }
+      dot = warp_sum_f(dot); yy = warp_sum_f(yy); aa = warp_sum_f(aa);
       // cos(y, a_hat) with a_hat = a/|a| (unit norm): (y.a/|a|) / max(|y|, eps); a zero
       // anchor row gives 0/0 = NaN as in the reference
       const float score = __fdiv_rn(dot, sqrtf(aa)) / fmaxf(sqrtf(yy), kCosEps);
-      if (valid && p.out_scores) p.out_scores[pair] = score;
-      score_sm[row] = score;
-    }
-    if (p.out_loss) {
-      ptx::named_bar_sync(1, C::kWorkerThreads);
-      double local = 0.0;
-      if (threadIdx.x < kRows / 2 && 2 * (int)threadIdx.x + 1 < n_valid)
-        local = (double)hinge_(p.margin, score_sm[2 * threadIdx.x], score_sm[2 * threadIdx.x + 1]);
-      loss_reduce<D>(p, ctl, local, wid, lane);
+      if (lane == 0 && p.out_scores) p.out_scores[row_begin + r] = score;
+      if (u & 1) { if (lane == 0) local += (double)hinge_(p.margin, s_even, score); }   // rows (2i, 2i+1) = (pos, neg)
+      else s_even = score;
     }
   } else {
-    const int64_t q = row_begin + row;
-    double local = 0.0;
-    float qq = 0.f;
 #pragma unroll 1
-    for (int t0 = 0; t0 < T; t0 += 2) {
-      const bool has1 = t0 + 1 < T;
-      const float* src0 = s.tgt_table;
-      const float* src1 = s.tgt_table;
-      if (valid) {
-        src0 += (size_t)__ldg(p.target_rows + q * T + t0) * D + col_base;
-        if (has1) src1 += (size_t)__ldg(p.target_rows + q * T + t0 + 1) * D + col_base;
+    for (int u = 0; u < RPW; ++u) {
+      const int r = wid * RPW + u;
+      int32_t t_a = __shfl_sync(0xffffffffu, ssrc0, u);
+      int32_t t_b = __shfl_sync(0xffffffffu, ssrc1, u);
+      if (t_a < 0) continue;  // warp-uniform: row past the end of the tile
+      const int64_t q = row_begin + r;
+      const float4* q_src = reinterpret_cast<const float4*>(qsm + (size_t)r * QS);
+      float4 y[NV];
+      float qq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        y[j] = q_src[lane + 32 * j];
+        qq = fmaf(y[j].x, y[j].x, qq); qq = fmaf(y[j].y, y[j].y, qq); qq = fmaf(y[j].z, y[j].z, qq); qq = fmaf(y[j].w, y[j].w, qq);
       }
-      float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f, qs = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        float4 a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          a[i] = valid ? __ldg(reinterpret_cast<const float4*>(src0 + 16 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          b[i] = (valid && has1) ? __ldg(reinterpret_cast<const float4*>(src1 + 16 * ch) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qq = warp_sum_f(qq);
+      const float nq = fmaxf(sqrtf(qq), kCosEps);
+      float s_first = 0.f;
+      for (int t0 = 0; t0 < T; t0 += 2) {
+        const bool has1 = t0 + 1 < T;
+        if (t0 > 0) {  // more than one (pos, neg) pair per query: the eval shape
+          t_a = __ldg(p.target_rows + q * T + t0);
+          t_b = has1 ? __ldg(p.target_rows + q * T + t0 + 1) : t_a;
         }
-        uint32_t raw[16];
-        ptx::tmem_ld16(t_acc + 16 * ch, raw);
-        ptx::tmem_wait_ld();
-        dot16(raw, a, d0, n0);
-        dot16(raw, b, d1, n1);
-        qs += sumsq16(raw);
-      }
-      if (grp != 0) {
-        float* sp = scratch + ((grp - 1) * kRows + row) * 8;
-        sp[0] = d0; sp[1] = d1; sp[2] = n0; sp[3] = n1; sp[4] = qs;
-      }
-      ptx::named_bar_sync(1, C::kWorkerThreads);
-      if (grp == 0) {
+        const float4* a_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)t_a * D);
+        const float4* b_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)(has1 ? t_b : t_a) * D);
+        float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
 #pragma unroll
-        for (int g2 = 1; g2 < C::kColGroups; ++g2) {
-          const float* sp = scratch + ((g2 - 1) * kRows + row) * 8;
-          d0 += sp[0]; d1 += sp[1]; n0 += sp[2]; n1 += sp[3]; qs += sp[4];
+        for (int j = 0; j < NV; ++j) {
+          const float4 a = __ldg(a_src + lane + 32 * j);
+          const float4 b = __ldg(b_src + lane + 32 * j);
+          d0 = fmaf(y[j].x, a.x, d0); d0 = fmaf(y[j].y, a.y, d0); d0 = fmaf(y[j].z, a.z, d0); d0 = fmaf(y[j].w, a.w, d0);
+          n0 = fmaf(a.x, a.x, n0); n0 = fmaf(a.y, a.y, n0); n0 = fmaf(a.z, a.z, n0); n0 = fmaf(a.w, a.w, n0);
+          d1 = fmaf(y[j].x, b.x, d1); d1 = fmaf(y[j].y, b.y, d1); d1 = fmaf(y[j].z, b.z, d1); d1 = fmaf(y[j].w, b.w, d1);
+          n1 = fmaf(b.x, b.x, n1); n1 = fmaf(b.y, b.y, n1); n1 = fmaf(b.z, b.z, n1); n1 = fmaf(b.w, b.w, n1);
         }
-      }
-      ptx::named_bar_sync(1, C::kWorkerThreads);
-      if (t0 == 0) qq = qs;
-      if (grp == 0 && valid) {
+        d0 = warp_sum_f(d0); n0 = warp_sum_f(n0); d1 = warp_sum_f(d1); n1 = warp_sum_f(n1);
         // t_hat = t/|t| has unit norm: cos(t_hat, q) = (t.q/|t|) / max(|q|, eps); a zero
         // target row gives 0/0 = NaN as in the reference
-        const float nq = fmaxf(sqrtf(qq), kCosEps);
         const float s0 = __fdiv_rn(d0, sqrtf(n0)) / nq;
-        const float s1 = has1 ? __fdiv_rn(d1, sqrtf(n1)) / nq : 0.f;
-        if (p.out_scores) {
+        const float s1 = __fdiv_rn(d1, sqrtf(n1)) / nq;
+        if (lane == 0 && p.out_scores) {
           p.out_scores[q * T + t0] = s0;
           if (has1) p.out_scores[q * T + t0 + 1] = s1;
         }
-        if (p.out_loss && t0 == 0) local = (double)hinge_(p.margin, s0, s1);
+        if (t0 == 0) s_first = hinge_(p.margin, s0, s1);
       }
+      if (lane == 0) local += (double)s_first;
     }
-    if (p.out_loss) loss_reduce<D>(p, ctl, local, wid, lane);
   }
+  if (p.out_loss) loss_reduce<D>(p, ctl, local, wid, lane);
 }
 
 // ---- TMA producer: streams the packed planes of every step's matrix -------------------
