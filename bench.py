@@ -40,7 +40,7 @@ BF16_FALLBACK_TFLOPS = 1590.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("native", "reference"), default="native")
     ap.add_argument("--workload", default=None)
@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((self.active, mhz, mask))
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def stop(self):
         self._stop_evt.set()
@@ -256,6 +256,8 @@ def run_native(args):
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = json.load(fh).get(name)
+            if isinstance(traffic, dict):
+                traffic = traffic.get("bytes")
         bound = "hbm" if t_hbm >= t_tc else "tensor"
         roof = {"bound": bound,
                 "achieved": round(gbs if bound == "hbm" else tfl_exec, 3),

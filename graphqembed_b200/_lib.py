@@ -34,7 +34,7 @@ STRUCTURE_ID = {"1-chain": 0, "2-chain": 1, "3-chain": 2, "2-inter": 3, "3-inter
 DECODER_ID = {"bilinear": 0, "transe": 1, "bilinear-diag": 2}
 INTER_ID = {"mean": 0, "min": 1, "mean-simple": 2, "min-simple": 3}
 PRECISION_ID = {"bf16x3": 0, "fp32": 1}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class GqeError(RuntimeError):
@@ -83,7 +83,12 @@ _SIGNATURES = {
     "gqe_path_score_device": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int64, _P, _P, C.c_int32, _P]),
     "gqe_intersect_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "gqe_cosine_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+    "gqe_ipc_export": (C.c_int, [_P, _P, C.c_char_p, C.POINTER(C.c_int64)]),
+    "gqe_ipc_open": (C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(_P)]),
+    "gqe_ipc_close": (C.c_int, [_P, _P]),
+    "gqe_gather_rows_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
 }
+IPC_HANDLE_BYTES = 64
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -269,6 +274,26 @@ class Context(object):
 
     def cosine_device(self, d, n, x, y, out):
         self._check(self._lib.gqe_cosine_device(self._h, d, n, x, y, out))
+
+    # -- node-type-sharded tables ---------------------------------------------------------
+    def ipc_export(self, dev_ptr):
+        """-> (handle bytes[64], byte offset) of a device pointer of this process."""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        off = C.c_int64()
+        self._check(self._lib.gqe_ipc_export(self._h, _P(dev_ptr), buf, C.byref(off)))
+        return buf.raw, int(off.value)
+
+    def ipc_open(self, handle, offset):
+        """Map a peer rank's shard; returns the peer device pointer (int)."""
+        out = _P()
+        self._check(self._lib.gqe_ipc_open(self._h, bytes(handle), int(offset), C.byref(out)))
+        return int(out.value)
+
+    def ipc_close(self, peer_ptr):
+        self._check(self._lib.gqe_ipc_close(self._h, _P(peer_ptr)))
+
+    def gather_rows_device(self, mode, n, rows, out):
+        self._check(self._lib.gqe_gather_rows_device(self._h, int(mode), int(n), rows, out))
 
 
 def make_segments(items):

@@ -158,8 +158,11 @@ extern "C" int gqe_bind_tables(gqe_ctx* c, int32_t n_modes, const float* const* 
   if (n_modes <= 0 || !tables || !rows) return fail(c, GQE_ERR_INVALID, "gqe_bind_tables: bad arguments");
   if (!dim_supported(d))
     return fail(c, GQE_ERR_UNSUPPORTED, "gqe_bind_tables: embedding dimension %d not supported (32/64/128/256)", d);
-  for (int m = 0; m < n_modes; ++m)
+  for (int m = 0; m < n_modes; ++m) {
+    // (NULL, 0 rows) = a mode that is absent on this rank (sharded tables)
+    if (!tables[m] && rows[m] == 0) continue;
     if (!tables[m] || rows[m] <= 0) return fail(c, GQE_ERR_INVALID, "gqe_bind_tables: mode %d has no table", m);
+  }
   c->tables.assign(tables, tables + n_modes);
   c->table_rows.assign(rows, rows + n_modes);
   c->d = d;
@@ -217,10 +220,13 @@ static int resolve(gqe_ctx* c, const gqe_plan& pl, SegDev* s) {
   s->structure = pl.structure;
   s->n_anchor = na;
   s->tgt_table = c->tables[pl.target_mode];
+  if (!s->tgt_table) return fail(c, GQE_ERR_UNBOUND, "target mode %d has no table on this rank", pl.target_mode);
   for (int k = 0; k < na; ++k) {
     if (pl.anchor_mode[k] < 0 || pl.anchor_mode[k] >= nm)
       return fail(c, GQE_ERR_INVALID, "anchor %d mode %d out of range", k, pl.anchor_mode[k]);
     s->anc_table[k] = c->tables[pl.anchor_mode[k]];
+    if (!s->anc_table[k])
+      return fail(c, GQE_ERR_UNBOUND, "anchor %d mode %d has no table on this rank", k, pl.anchor_mode[k]);
   }
   for (int k = 0; k < nr; ++k) {
     if (pl.rel[k] < 0 || pl.rel[k] >= (int)c->rels.size())
@@ -540,6 +546,7 @@ extern "C" int gqe_encode_device(gqe_ctx* c, int32_t mode, int64_t n, const int3
   if (!c) return GQE_ERR_INVALID;
   if (c->tables.empty()) return fail(c, GQE_ERR_UNBOUND, "embedding tables are not bound");
   if (mode < 0 || mode >= (int)c->tables.size()) return fail(c, GQE_ERR_INVALID, "mode %d out of range", mode);
+  if (!c->tables[mode]) return fail(c, GQE_ERR_UNBOUND, "mode %d has no table on this rank", mode);
   if (n > 0 && (!rows || !out)) return fail(c, GQE_ERR_INVALID, "gqe_encode_device: null argument");
   OpParams op;
   std::memset(&op, 0, sizeof op);
@@ -623,4 +630,122 @@ extern "C" int gqe_cosine_device(gqe_ctx* c, int32_t d, int64_t n, const float* 
   op.in1 = y;
   op.out = out;
   return launch_op(c, d, op);
+}
+
+// ---- node-type-sharded tables: CUDA IPC mapping of peer shards ----------------------
+#include <map>
+#include <mutex>
+
+namespace {
+struct IpcKey {
+  unsigned char b[GQE_IPC_HANDLE_BYTES];
+  bool operator<(const IpcKey& o) const { return std::memcmp(b, o.b, sizeof b) < 0; }
+};
+struct IpcMapping {
+  void* base;
+  int refs;
+  int device;
+};
+std::mutex g_ipc_mu;
+std::map<IpcKey, IpcMapping> g_ipc_open;       // handle -> mapping (a handle can be opened once per process)
+std::map<void*, IpcKey> g_ipc_by_ptr;          // returned peer pointer -> handle
+
+// cuMemGetAddressRange through the runtime's driver entry point (no -lcuda at link time)
+typedef int (*cuMemGetAddressRange_t)(unsigned long long* pbase, size_t* psize, unsigned long long dptr);
+cuMemGetAddressRange_t address_range_fn() {
+  static cuMemGetAddressRange_t fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<cuMemGetAddressRange_t>(p);
+  }
+  return fn;
+}
+}  // namespace
+
+static_assert(sizeof(cudaIpcMemHandle_t) == GQE_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int gqe_ipc_export(gqe_ctx* c, const void* dev_ptr, uint8_t* handle_out, int64_t* offset_out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!dev_ptr || !handle_out || !offset_out) return fail(c, GQE_ERR_INVALID, "gqe_ipc_export: null argument");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  cuMemGetAddressRange_t range = address_range_fn();
+  if (!range) return fail(c, GQE_ERR_CUDA, "gqe_ipc_export: cuMemGetAddressRange is not available");
+  unsigned long long base = 0;
+  size_t size = 0;
+  const int rc = range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr);
+  if (rc != 0) return fail(c, GQE_ERR_CUDA, "gqe_ipc_export: cuMemGetAddressRange failed (CUresult %d)", rc);
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base));
+  if (e != cudaSuccess)
+    return fail(c, GQE_ERR_CUDA,
+                "gqe_ipc_export: cudaIpcGetMemHandle failed: %s (the table must live in a cudaMalloc allocation, "
+                "not an expandable-segments / VMM mapping)", cudaGetErrorString(e));
+  std::memcpy(handle_out, &h, GQE_IPC_HANDLE_BYTES);
+  *offset_out = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+  return GQE_OK;
+}
+
+extern "C" int gqe_ipc_open(gqe_ctx* c, const uint8_t* handle, int64_t offset, void** peer_ptr_out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!handle || !peer_ptr_out || offset < 0) return fail(c, GQE_ERR_INVALID, "gqe_ipc_open: bad argument");
+  *peer_ptr_out = nullptr;
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  IpcKey key;
+  std::memcpy(key.b, handle, sizeof key.b);
+  std::lock_guard<std::mutex> lock(g_ipc_mu);
+  auto it = g_ipc_open.find(key);
+  if (it == g_ipc_open.end()) {
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return fail(c, GQE_ERR_CUDA, "gqe_ipc_open: cudaIpcOpenMemHandle failed: %s (peer shard not reachable)",
+                  cudaGetErrorString(e));
+    it = g_ipc_open.insert({key, IpcMapping{base, 0, c->device}}).first;
+  } else if (it->second.device != c->device) {
+    return fail(c, GQE_ERR_UNSUPPORTED, "gqe_ipc_open: handle already mapped on device %d", it->second.device);
+  }
+  it->second.refs += 1;
+  void* p = static_cast<char*>(it->second.base) + offset;
+  g_ipc_by_ptr[p] = key;
+  *peer_ptr_out = p;
+  return GQE_OK;
+}
+
+extern "C" int gqe_ipc_close(gqe_ctx* c, void* peer_ptr) {
+  if (!c) return GQE_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(g_ipc_mu);
+  auto pit = g_ipc_by_ptr.find(peer_ptr);
+  if (pit == g_ipc_by_ptr.end()) return fail(c, GQE_ERR_INVALID, "gqe_ipc_close: not a pointer from gqe_ipc_open");
+  auto it = g_ipc_open.find(pit->second);
+  if (it != g_ipc_open.end() && --it->second.refs <= 0) {
+    cudaSetDevice(it->second.device);
+    cudaDeviceSynchronize();  // no kernel may still be reading the peer shard
+    cudaIpcCloseMemHandle(it->second.base);
+    g_ipc_open.erase(it);
+    for (auto q = g_ipc_by_ptr.begin(); q != g_ipc_by_ptr.end();)
+      q = (std::memcmp(q->second.b, pit->second.b, sizeof pit->second.b) == 0 && q != pit) ? g_ipc_by_ptr.erase(q) : std::next(q);
+  }
+  g_ipc_by_ptr.erase(pit);
+  return GQE_OK;
+}
+
+extern "C" int gqe_gather_rows_device(gqe_ctx* c, int32_t mode, int64_t n, const int32_t* rows, float* out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (c->tables.empty()) return fail(c, GQE_ERR_UNBOUND, "embedding tables are not bound");
+  if (mode < 0 || mode >= (int)c->tables.size()) return fail(c, GQE_ERR_INVALID, "mode %d out of range", mode);
+  if (!c->tables[mode]) return fail(c, GQE_ERR_UNBOUND, "mode %d has no table on this rank", mode);
+  if (n < 0) return fail(c, GQE_ERR_INVALID, "negative row count");
+  if (n == 0) return GQE_OK;
+  if (!rows || !out) return fail(c, GQE_ERR_INVALID, "gqe_gather_rows_device: null argument");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  GQE_CUDA(c, launch_gather_rows(c->tables[mode], rows, n, c->d, out, c->stream));
+  c->launches += 1;
+  return GQE_OK;
 }

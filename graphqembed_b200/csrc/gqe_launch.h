@@ -22,6 +22,9 @@ GQE_DECLARE_TC_DIM(128)
 GQE_DECLARE_TC_DIM(256)
 #undef GQE_DECLARE_TC_DIM
 
+// raw row gather (gqe_rows.cu): out[i] = table[rows[i]], any d % 4 == 0
+cudaError_t launch_gather_rows(const float* table, const int32_t* rows, int64_t n, int d, float* out, cudaStream_t st);
+
 inline bool tc_dim_supported(int d) { return d == 128 || d == 256; }
 inline size_t tc_packed_bytes(int d) { return (size_t)4 * d * d; }
 inline cudaError_t launch_fused_tc(int d, int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {

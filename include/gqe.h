@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GQE_ABI_VERSION 2
+#define GQE_ABI_VERSION 3
 #define GQE_MAX_ANCHORS 3
 #define GQE_MAX_RELS 3
 
@@ -138,6 +138,11 @@ int64_t gqe_launch_count(const gqe_ctx* ctx);
  * netquery/bio/data_utils.py:16-21 (one [rows, d] fp32 table per mode). */
 int gqe_bind_tables(gqe_ctx* ctx, int32_t n_modes, const float* const* tables /*HOST array of DEVICE ptrs*/,
                     const int64_t* rows /*HOST [n_modes]*/, int32_t d);
+/* A table pointer may be a PEER pointer obtained from gqe_ipc_open (another
+ * GPU's shard of the node-type-sharded table): the fused kernels then read
+ * those rows in place over NVLink.  tables[m] == NULL with rows[m] == 0 marks
+ * a mode that is absent on this rank; a plan that references it fails with
+ * GQE_ERR_UNBOUND. */
 /* Replaces: the `mats` / `vecs` parameter dicts of reference
  * netquery/decoders.py:129-140,188-197,217-226.  params[r] is [d,d] row-major
  * (bilinear) or [d] (transe / distmult). */
@@ -224,6 +229,27 @@ int gqe_intersect_device(gqe_ctx* ctx, int32_t mode, int64_t n, const float* emb
                          const float* embeds2, const float* embeds3, float* out);
 /* nn.CosineSimilarity(dim=0, eps=1e-8) as used at model.py:68,97,108. */
 int gqe_cosine_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* x, const float* y, float* out /*[n]*/);
+
+/* ---- node-type-sharded tables across the GPUs of one box -------------------
+ * (no counterpart in the reference, which is single-process: this is the
+ * multi-GPU form of the `features` lookup of netquery/bio/data_utils.py:20-21.)
+ * One process per GPU.  The owner of a shard exports its table with
+ * gqe_ipc_export; the 64-byte handle and the offset travel to the other ranks
+ * by whatever the host uses (torch.distributed here); each of them maps the
+ * shard with gqe_ipc_open and binds the returned peer pointer in
+ * gqe_bind_tables.  Peer access over NVLink is enabled by the open. */
+#define GQE_IPC_HANDLE_BYTES 64
+/* dev_ptr: any pointer inside a cudaMalloc'ed allocation of this process (not
+ * a VMM / expandable-segments mapping).  handle_out: HOST [64]; offset_out:
+ * byte offset of dev_ptr inside the exported allocation. */
+int gqe_ipc_export(gqe_ctx* ctx, const void* dev_ptr, uint8_t* handle_out, int64_t* offset_out);
+/* handle: HOST [64] from a DIFFERENT process on the same box.  The mapping is
+ * reference counted per process (several tables may live in one allocation). */
+int gqe_ipc_open(gqe_ctx* ctx, const uint8_t* handle, int64_t offset, void** peer_ptr_out);
+int gqe_ipc_close(gqe_ctx* ctx, void* peer_ptr);
+/* Staged alternative (owner side of an NCCL exchange): out[i, :] =
+ * table[mode][rows[i], :], raw rows, DEVICE int32 rows [n] -> DEVICE fp32 [n, d]. */
+int gqe_gather_rows_device(gqe_ctx* ctx, int32_t mode, int64_t n, const int32_t* rows, float* out);
 
 #ifdef __cplusplus
 }
