@@ -48,6 +48,11 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=12288, help="queries in the CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tables", choices=("replicated", "p2p", "staged"), default=None,
+                    help="table placement (default: replicated; p2p for the 10M-node workload at N>1)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded 10M-node leg at N>1")
+    ap.add_argument("--with-sharded", action="store_true", help="also run the 10M-node workload at N=1")
+    ap.add_argument("--sharded-formulas", type=int, default=4, help="formulas per structure of the 10M-node leg")
     return ap.parse_args()
 
 
@@ -119,29 +124,251 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------
-def device_parameters(wl, torch, device, seed):
+def device_parameters(wl, torch, device, seed, owner=None, rank=0):
     """Random-init parameters of the reference's architecture, on the device:
     tables N(0, 1/d) (bio/data_utils.py:17-19), xavier-uniform relation / pre /
-    post matrices (decoders.py:139,282,285)."""
+    post matrices (decoders.py:139,282,285).  Every tensor has its own seed, so
+    a rank that holds only its shard (``owner[m] == rank``) holds exactly the
+    values the single-GPU run holds for that mode."""
     import math
-    g = torch.Generator(device=device).manual_seed(seed)
     d, kg = wl.d, wl.kg
-    tables = [torch.randn(kg.sizes[m] + 2, d, generator=g, device=device) * (1.0 / d) for m in kg.modes]
+
+    def gen(k):
+        return torch.Generator(device=device).manual_seed(seed * 1000003 + k)
+
+    tables = []
+    for i, m in enumerate(kg.modes):
+        if owner is not None and owner[i] != rank:
+            tables.append(None)
+        else:
+            tables.append(torch.randn(kg.sizes[m] + 2, d, generator=gen(i), device=device) * (1.0 / d))
     bound = math.sqrt(6.0 / (2 * d))
-    uni = lambda *shape: (torch.rand(*shape, generator=g, device=device) * 2 - 1) * bound
-    rels = [uni(d, d) for _ in kg.rel_keys]
-    pre = [uni(d, d) for _ in kg.modes]
-    post = [uni(d, d) for _ in kg.modes]
+    uni = lambda k: (torch.rand(d, d, generator=gen(k), device=device) * 2 - 1) * bound
+    rels = [uni(1000 + i) for i in range(len(kg.rel_keys))]
+    pre = [uni(2000 + i) for i in range(len(kg.modes))]
+    post = [uni(3000 + i) for i in range(len(kg.modes))]
     return tables, rels, pre, post
 
 
-def run_native(args):
+class Timed(object):
+    """K timed steps after W warm-ups: CUDA events on the launching stream, L2
+    flushed before every step, barrier + synchronize on both sides, max over ranks."""
+
+    def __init__(self, torch, dist, device, stream, flush):
+        self.torch, self.dist, self.device, self.stream, self.flush = torch, dist, device, stream, flush
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.device)
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.device)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def device_ms(self, step, steps, warmup, sampler=None):
+        torch = self.torch
+        for _ in range(warmup):
+            self.flush.zero_()
+            step()
+        self.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        if sampler is not None:
+            sampler.active = True
+        for e0, e1 in evs:
+            self.flush.zero_()
+            e0.record(self.stream)
+            step()
+            e1.record(self.stream)
+        self.barrier()
+        if sampler is not None:
+            sampler.active = False
+        return self.max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs))[0] / steps
+
+    def host_ms(self, step, steps, warmup=3):
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        tot = 0.0
+        for _ in range(steps):
+            self.flush.zero_()
+            self.torch.cuda.synchronize(self.device)
+            t0 = time.perf_counter()
+            step()
+            tot += time.perf_counter() - t0
+        self.barrier()
+        return self.max_over_ranks(tot * 1e3)[0] / steps
+
+
+def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, formulas_per_structure=1):
+    """One workload on this process group.  tables_mode:
+         replicated  every rank holds every table (Bio-size); pure data parallel
+         p2p         tables sharded by node type, peers mapped with CUDA IPC, the fused kernel
+                     gathers remote rows in place over NVLink
+         staged      tables sharded by node type, rows fetched by an NCCL all-to-all exchange
+                     into staging tables before the same fused kernel runs
+    """
     import numpy as np
     import torch
 
     import graphqembed_b200 as gqe
-    from graphqembed_b200 import _lib
-    from graphqembed_b200.workloads import DEFAULT_WORKLOAD, WORKLOADS, make_workload
+    from graphqembed_b200 import _lib, sharded
+    from graphqembed_b200.workloads import make_workload
+
+    device, stream, dist = tm.device, tm.stream, tm.dist
+    wl = make_workload(name, seed=rank, formulas_per_structure=formulas_per_structure)
+    n_modes = len(wl.kg.modes)
+    owner = None if tables_mode == "replicated" else sharded.owner_by_node_type(n_modes, world)
+    tables, rels, pre, post = device_parameters(wl, torch, device, seed=1234, owner=owner, rank=rank)
+    lookup = gqe.RowLookup(wl.kg.node_ids)
+    mode_ids = {m: i for i, m in enumerate(wl.kg.modes)}
+    rel_ids = {r: i for i, r in enumerate(wl.kg.rel_keys)}
+    segs, anchor_rows, pair_rows = wl.lower(lookup, mode_ids, rel_ids)
+    nq = wl.n_queries
+    rows = [wl.kg.sizes[m] + 2 for m in wl.kg.modes]
+
+    ctx = gqe.Context(local_rank, stream.cuda_stream)
+    ctx.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
+    ctx.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
+    own_ptrs = [0 if t is None else t.data_ptr() for t in tables]
+    own_rows = [0 if t is None else r for t, r in zip(tables, rows)]
+
+    h_anchor = torch.from_numpy(anchor_rows).pin_memory()
+    h_pairs = torch.from_numpy(pair_rows).pin_memory()
+    h_loss = torch.zeros(1).pin_memory()
+    d_loss = torch.zeros(1, device=device)
+    remote_rows = 0
+    peers = None
+
+    if tables_mode in ("replicated", "p2p"):
+        if tables_mode == "p2p" and world > 1:
+            peers = sharded.PeerTables(ctx, owner, rows, {m: t for m, t in enumerate(tables) if t is not None})
+            ctx.bind_tables(peers.pointers(), rows, wl.d)
+            for c_mode, c_n, _, _, _ in sharded.chunks_of_segments(segs, nq, 2):
+                if owner[c_mode] != rank:
+                    remote_rows += c_n
+        else:
+            ctx.bind_tables(own_ptrs, own_rows, wl.d)
+        d_anchor, d_pairs = h_anchor.to(device), h_pairs.to(device)
+
+        def step_device():
+            ctx.score_grouped_device(segs, nq, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, None, 1.0, d_loss.data_ptr())
+
+        def step_host():
+            ctx._check(ctx._lib.gqe_score_grouped_host(ctx._h, segs, len(segs), nq, h_anchor.data_ptr(),
+                                                       h_pairs.data_ptr(), 2, None, 1.0, h_loss.data_ptr()))
+        h2d = int(anchor_rows.nbytes + pair_rows.nbytes)
+        call = "gqe_score_grouped_host (pinned int32 row indices in, fp32 loss out)"
+    else:
+        info = sharded.chunks_of_segments(segs, nq, 2)
+        plan = sharded.ExchangePlan(owner, world, rank, [(m, n) for m, n, _, _, _ in info])
+        ctx.bind_tables(own_ptrs, own_rows, wl.d)          # the owner-side gather reads these
+        ex = sharded.RowExchange(plan, wl.d, sharded.device_gather(ctx), device=device)
+        req, s_anchor, s_pairs = sharded.stage_grouped(plan, info, segs, anchor_rows, pair_rows, 2)
+        h_req = torch.from_numpy(req).pin_memory()
+        h_sanchor = torch.from_numpy(s_anchor).pin_memory()
+        h_spairs = torch.from_numpy(s_pairs).pin_memory()
+        d_req, d_sanchor, d_spairs = h_req.to(device), h_sanchor.to(device), h_spairs.to(device)
+        e_req, e_sanchor, e_spairs = torch.empty_like(d_req), torch.empty_like(d_sanchor), torch.empty_like(d_spairs)
+        for c_mode, c_n, _, _, _ in info:
+            if owner[c_mode] != rank:
+                remote_rows += c_n
+        # a second context scores against the staging tables (the first keeps the shards bound)
+        sctx = gqe.Context(local_rank, stream.cuda_stream)
+        sctx.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
+        sctx.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
+        st_ptrs, st_rows = ex.staging_tables()
+        sctx.bind_tables(st_ptrs, st_rows, wl.d)
+
+        def step_device():
+            ex.run(d_req)
+            sctx.score_grouped_device(segs, nq, d_sanchor.data_ptr(), d_spairs.data_ptr(), 2, None, 1.0,
+                                      d_loss.data_ptr())
+
+        def step_host():
+            e_req.copy_(h_req, non_blocking=True)
+            e_sanchor.copy_(h_sanchor, non_blocking=True)
+            e_spairs.copy_(h_spairs, non_blocking=True)
+            ex.run(e_req)
+            sctx.score_grouped_device(segs, nq, e_sanchor.data_ptr(), e_spairs.data_ptr(), 2, None, 1.0,
+                                      d_loss.data_ptr())
+            h_loss.copy_(d_loss, non_blocking=True)
+            stream.synchronize()
+        h2d = int(req.nbytes + s_anchor.nbytes + s_pairs.nbytes)
+        call = "request H2D + NCCL all-to-all exchange + gqe_score_grouped_device + loss D2H"
+        launch_ctxs = (ctx, sctx)
+    if tables_mode != "staged":
+        launch_ctxs = (ctx,)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        tm.flush.zero_()
+        step_device()
+    tm.barrier()
+    loss_ref = float(d_loss.item())
+    launches0 = sum(c.launch_count() for c in launch_ctxs)
+    dev_ms = tm.device_ms(step_device, args.steps, 0, sampler)
+    launches = sum(c.launch_count() for c in launch_ctxs) - launches0
+    assert float(d_loss.item()) == loss_ref, "non-deterministic loss"
+    e2e_ms = tm.host_ms(step_host, args.steps)
+    assert float(h_loss[0]) == loss_ref, "host entry point disagrees with the device one"
+    tm.barrier()
+    if peers is not None:
+        peers.close()
+    res = {"wl": wl, "nq": nq, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "loss": loss_ref, "launches": int(launches),
+           "h2d": h2d, "call": call, "remote_rows": int(remote_rows), "formulas": len(wl.batches),
+           "params": (tables, rels, pre, post)}
+    return res
+
+
+def roofline_of(wl, name, ms_per_step, pk, world=1):
+    """Roofline of the fused kernel for one step of `wl` on one GPU."""
+    bytes_alg, flops_alg = wl.algorithmic_bytes(), wl.algorithmic_flops()
+    sec = ms_per_step * 1e-3
+    gbs = bytes_alg / sec / 1e9
+    tfl = flops_alg / sec / 1e12
+    # the contractions run as three bf16 tensor-core products per algorithmic one
+    # (hi*hi + lo*hi + hi*lo, fp32 accumulate): the tensor pipe executes 3x the
+    # algorithmic flops, so the usable ceiling is the measured bf16 peak / 3
+    passes = 3
+    tfl_exec = passes * tfl
+    t_hbm = bytes_alg / (pk["hbm_gbs"] * 1e9)
+    t_tc = passes * flops_alg / (pk["bf16_tflops"] * 1e12)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(name)
+        if isinstance(traffic, dict):
+            traffic = traffic.get("bytes")
+    bound = "hbm" if t_hbm >= t_tc else "tensor"
+    return {"bound": bound,
+            "achieved": round(gbs if bound == "hbm" else tfl_exec, 3),
+            "peak": pk["hbm_gbs"] if bound == "hbm" else pk["bf16_tflops"],
+            "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+            "frac": round((gbs / pk["hbm_gbs"]) if bound == "hbm" else (tfl_exec / pk["bf16_tflops"]), 4),
+            "traffic": traffic, "peak_source": pk["source"],
+            "kernel": "gqe_fused_tc<%d,-1> (grouped tcgen05 kernel, one launch per <=32 formulas, preceded by "
+                      "gqe_pack)" % wl.d,
+            "kernel_ms": round(ms_per_step, 4),
+            "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_flops_per_launch": flops_alg,
+            "hbm": {"achieved_gbs": round(gbs, 2), "frac": round(gbs / pk["hbm_gbs"], 4)},
+            "tensor": {"executed_tflops": round(tfl_exec, 3), "algorithmic_tflops": round(tfl, 3),
+                       "peak_tflops": pk["bf16_tflops"], "frac": round(tfl_exec / pk["bf16_tflops"], 4),
+                       "note": "d x d contractions as bf16x3 split products on tcgen05 (3 MMAs per algorithmic "
+                               "product); executed = 3 x algorithmic; peak = measured sustained bf16 dense"}}
+
+
+NVLINK_PEER_GBS = 770.0     # /opt/skills/guides/B200_PROFILING.md: measured peer copy, per direction per GPU
+
+
+def run_native(args):
+    import torch
+
+    from graphqembed_b200.workloads import DEFAULT_WORKLOAD, LARGE_WORKLOAD, WORKLOADS
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -154,143 +381,67 @@ def run_native(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
+    stream = torch.cuda.current_stream(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+    tm = Timed(torch, dist, device, stream, flush)
 
     name = args.workload or DEFAULT_WORKLOAD
-    wl = make_workload(name, seed=rank, formulas_per_structure=args.formulas_per_structure)
-    tables, rels, pre, post = device_parameters(wl, torch, device, seed=1234)
-    lookup = gqe.RowLookup(wl.kg.node_ids)
-    mode_ids = {m: i for i, m in enumerate(wl.kg.modes)}
-    rel_ids = {r: i for i, r in enumerate(wl.kg.rel_keys)}
-    segs, anchor_rows, pair_rows = wl.lower(lookup, mode_ids, rel_ids)
-
-    stream = torch.cuda.current_stream(device)
-    ctx = gqe.Context(local_rank, stream.cuda_stream)
-    ctx.bind_tables([t.data_ptr() for t in tables], [t.size(0) for t in tables], wl.d)
-    ctx.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
-    ctx.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
-
-    # host buffers are pinned; the device copies are what `value` is timed on
-    h_anchor = torch.from_numpy(anchor_rows).pin_memory()
-    h_pairs = torch.from_numpy(pair_rows).pin_memory()
-    h_loss = torch.zeros(1).pin_memory()
-    d_anchor = h_anchor.to(device)
-    d_pairs = h_pairs.to(device)
-    d_loss = torch.zeros(1, device=device)
-    nq = wl.n_queries
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
-
-    def step_device():
-        ctx.score_grouped_device(segs, nq, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, None, 1.0, d_loss.data_ptr())
-
-    def step_host():
-        ctx._check(ctx._lib.gqe_score_grouped_host(ctx._h, segs, len(segs), nq, h_anchor.data_ptr(), h_pairs.data_ptr(),
-                                                   2, None, 1.0, h_loss.data_ptr()))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
+    tables_mode = args.tables or ("p2p" if name == LARGE_WORKLOAD and world > 1 else "replicated")
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step_device()
-    barrier()
-    loss_ref = float(d_loss.item())
-
-    # ---- device-resident timing: K steps, L2 flushed before each, CUDA events ----
-    launches0 = ctx.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    sampler.active = True
-    for e0, e1 in evs:
-        flush.zero_()
-        e0.record(stream)
-        step_device()
-        e1.record(stream)
-    barrier()
-    sampler.active = False
-    launches = ctx.launch_count() - launches0
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    assert float(d_loss.item()) == loss_ref, "non-deterministic loss"
-
-    # ---- end to end through the host-buffer C-ABI call ----------------------------
-    for _ in range(3):
-        step_host()
-    barrier()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize(device)
-        t0 = time.perf_counter()
-        step_host()
-        e2e_s += time.perf_counter() - t0
-    barrier()
-    assert abs(float(h_loss[0]) - loss_ref) == 0.0, "host entry point disagrees with the device one"
+    res = measure(args, name, tables_mode, tm, rank, world, local_rank, sampler, args.formulas_per_structure)
     sampler.stop()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    # BASELINE.json configs[4]: the node-type-sharded 10 M-node table, measured beside the
+    # headline whenever the job has more than one GPU (and on request at N=1)
+    extra = {}
+    if (world > 1 and args.workload is None and not args.no_sharded) or args.with_sharded:
+        for mode in (("p2p", "staged") if world > 1 else ("replicated",)):
+            r = measure(args, LARGE_WORKLOAD, mode, tm, rank, world, local_rank, None, args.sharded_formulas)
+            r.pop("params")
+            extra[mode] = r
+            torch.cuda.empty_cache()
 
     line = None
     if rank == 0:
         pk = peaks()
-        ms_per_step = dev_ms / args.steps
-        value = world * nq / (ms_per_step * 1e-3)
-        kern_s = ms_per_step * 1e-3     # gqe_pack + the fused kernel; gqe_pack's share is in profiles/
-        bytes_alg, flops_alg = wl.algorithmic_bytes(), wl.algorithmic_flops()
-        gbs = bytes_alg / (ms_per_step * 1e-3) / 1e9
-        tfl = flops_alg / (ms_per_step * 1e-3) / 1e12
-        # the contractions run as three bf16 tensor-core products per algorithmic one
-        # (hi*hi + lo*hi + hi*lo, fp32 accumulate): the tensor pipe executes 3x the
-        # algorithmic flops, so the usable ceiling is the measured bf16 peak / 3
-        passes = 3
-        tfl_exec = passes * tfl
-        t_hbm = bytes_alg / (pk["hbm_gbs"] * 1e9)
-        t_tc = passes * flops_alg / (pk["bf16_tflops"] * 1e12)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get(name)
-            if isinstance(traffic, dict):
-                traffic = traffic.get("bytes")
-        bound = "hbm" if t_hbm >= t_tc else "tensor"
-        roof = {"bound": bound,
-                "achieved": round(gbs if bound == "hbm" else tfl_exec, 3),
-                "peak": pk["hbm_gbs"] if bound == "hbm" else pk["bf16_tflops"],
-                "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-                "frac": round((gbs / pk["hbm_gbs"]) if bound == "hbm" else (tfl_exec / pk["bf16_tflops"]), 4),
-                "traffic": traffic, "peak_source": pk["source"],
-                "kernel": "gqe_fused_tc<256,-1> (grouped tcgen05 kernel, one launch per step, preceded by gqe_pack)",
-                "kernel_ms": round(kern_s * 1e3, 4),
-                "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_flops_per_launch": flops_alg,
-                "hbm": {"achieved_gbs": round(gbs, 2), "frac": round(gbs / pk["hbm_gbs"], 4)},
-                "tensor": {"executed_tflops": round(tfl_exec, 3), "algorithmic_tflops": round(tfl, 3),
-                           "peak_tflops": pk["bf16_tflops"], "frac": round(tfl_exec / pk["bf16_tflops"], 4),
-                           "note": "d x d contractions as bf16x3 split products on tcgen05 (3 MMAs per algorithmic "
-                                   "product); executed = 3 x algorithmic; peak = measured sustained bf16 dense"}}
+        wl, nq = res["wl"], res["nq"]
+        ms_per_step = res["dev_ms"]
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "metric": METRIC, "value": round(world * nq / (ms_per_step * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[name][0], "name": name, "queries_per_step_per_gpu": nq,
                        "targets_per_query": 2, "decoder": wl.decoder, "intersection": wl.inter, "d": wl.d,
-                       "formulas": len(wl.batches), "contractions": "bf16x3 split on tcgen05, fp32 accumulate (scores within 1e-4 of fp32)", "tables": "replicated per GPU (Bio-size)",
+                       "formulas": res["formulas"],
+                       "contractions": "bf16x3 split on tcgen05, fp32 accumulate (scores within 1e-4 of fp32)",
+                       "tables": {"replicated": "replicated per GPU (Bio-size); queries sharded, no collective",
+                                  "p2p": "sharded by node type; remote rows gathered in place over NVLink (CUDA IPC)",
+                                  "staged": "sharded by node type; NCCL all-to-all row exchange"}[tables_mode],
                        "l2": "flushed before every step (256 MiB write)"},
-            "e2e": {"value": round(world * nq / (e2e_ms * 1e-3 / args.steps), 1), "unit": UNIT,
-                    "h2d_bytes_per_step": int(anchor_rows.nbytes + pair_rows.nbytes), "d2h_bytes_per_step": 4,
-                    "ms_per_step": round(e2e_ms / args.steps, 5),
-                    "call": "gqe_score_grouped_host (pinned int32 row indices in, fp32 loss out)"},
-            "gpu_launches": int(launches),
+            "e2e": {"value": round(world * nq / (res["e2e_ms"] * 1e-3), 1), "unit": UNIT,
+                    "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(res["e2e_ms"], 5), "call": res["call"]},
+            "gpu_launches": res["launches"],
             "clocks": sampler.summary(),
-            "roofline": roof,
-            "loss": loss_ref,
+            "roofline": roofline_of(wl, name, ms_per_step, pk),
+            "loss": res["loss"],
         }
+        for mode, r in extra.items():
+            sec = r["dev_ms"] * 1e-3
+            nv_bytes = r["remote_rows"] * r["wl"].d * 4
+            line.setdefault("sharded", {})[mode] = {
+                "workload": WORKLOADS[LARGE_WORKLOAD][0], "value": round(world * r["nq"] / sec, 1), "unit": UNIT,
+                "ms_per_step": round(r["dev_ms"], 5), "e2e_value": round(world * r["nq"] / (r["e2e_ms"] * 1e-3), 1),
+                "gpu_launches": r["launches"], "formulas": r["formulas"], "loss_rank0": r["loss"],
+                "hbm": {"achieved_gbs": round(r["wl"].algorithmic_bytes() / sec / 1e9, 2),
+                        "frac": round(r["wl"].algorithmic_bytes() / sec / 1e9 / pk["hbm_gbs"], 4)},
+                "nvlink": {"remote_rows_per_step_rank0": r["remote_rows"], "bytes_per_step_rank0": nv_bytes,
+                           "achieved_gbs_in": round(nv_bytes / sec / 1e9, 2), "peak_gbs": NVLINK_PEER_GBS,
+                           "frac": round(nv_bytes / sec / 1e9 / NVLINK_PEER_GBS, 4),
+                           "note": "inbound row bytes of rank 0 / step time vs the measured peer-copy bandwidth"}}
         if world == 1 and not args.no_cpu_baseline:
+            tables, rels, pre, post = res["params"]
             line["cpu_baseline"] = cpu_reference(args, name, tables=[t.cpu() for t in tables],
                                                  rels=[r.cpu() for r in rels], pre=[p.cpu() for p in pre],
                                                  post=[p.cpu() for p in post], steps=None)

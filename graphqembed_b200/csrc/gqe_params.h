@@ -14,7 +14,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kRowsPerWarp = kTileRows / kWarps;  // 8
 constexpr int kPanelK = 16;
 constexpr int kRowStride = kTileRows + 4;  // 68 floats: 16B-aligned rows, 4-bank skew
-constexpr int kMaxSegs = 16;
+constexpr int kMaxSegs = 32;
 constexpr float kCosEps = 1e-8f;  // nn.CosineSimilarity default eps (model.py:68)
 
 // One formula's slice of a launch, fully resolved to device pointers.

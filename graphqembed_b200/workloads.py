@@ -27,8 +27,13 @@ WORKLOADS = {
     # BASELINE.json configs[0] (the reference's own CPU-runnable case)
     "bio-edge-d128-b512": ("Bio KG 1-chain (edge) queries, Bilinear decoder, d=128, batch=512", 128, 512,
                            ("1-chain",), "bilinear", "mean"),
+    # BASELINE.json configs[4]: 8 node types x 1.25 M nodes, 100 directed relations; the table (10.24 GB)
+    # is sharded by node type over the GPUs of one box (1.28 GB per GPU at 8 GPUs)
+    "synth-10m-d256-b65536": ("Synthetic KG 10M nodes / 100 relations, full query mix, d=256, batch=65536 per GPU",
+                              256, 65536, STRUCTURES[:6], "bilinear", "mean"),
 }
 DEFAULT_WORKLOAD = "bio-mix-d256-b65536"
+LARGE_WORKLOAD = "synth-10m-d256-b65536"
 
 
 class Workload(object):
@@ -77,7 +82,7 @@ def make_workload(name=DEFAULT_WORKLOAD, seed=0, kg=None, formulas_per_structure
     if total is not None:
         n_total = int(total)
     if kg is None:
-        kg = bio_shaped(seed=0)
+        kg = synthetic_large(seed=0) if name.startswith("synth-10m") else bio_shaped(seed=0)
     rng = np.random.RandomState(1000 + seed)
     n_slices = len(structures) * formulas_per_structure
     sizes = [n_total // n_slices + (1 if i < n_total % n_slices else 0) for i in range(n_slices)]
