@@ -26,6 +26,7 @@ struct gqe_ctx {
   int d = 0;
   std::vector<const float*> tables;
   std::vector<int64_t> table_rows;
+  std::vector<char> table_remote;  // the table lives in a peer GPU's HBM (mapped with gqe_ipc_open)
 
   int decoder = -1;
   int rel_d = 0;
@@ -71,6 +72,8 @@ static int fail(gqe_ctx* c, int code, const char* fmt, ...) {
     if (e_ != cudaSuccess)                                                                       \
       return fail((c), GQE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+static bool is_ipc_pointer(const void* p);  // defined with the IPC entry points below
 
 static bool dim_supported(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 
@@ -163,8 +166,23 @@ extern "C" int gqe_bind_tables(gqe_ctx* c, int32_t n_modes, const float* const* 
     if (!tables[m] && rows[m] == 0) continue;
     if (!tables[m] || rows[m] <= 0) return fail(c, GQE_ERR_INVALID, "gqe_bind_tables: mode %d has no table", m);
   }
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  std::vector<char> remote(n_modes, 0);
+  for (int m = 0; m < n_modes; ++m) {
+    if (!tables[m]) continue;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, tables[m]);
+    if (e != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+      cudaGetLastError();
+      return fail(c, GQE_ERR_INVALID, "gqe_bind_tables: table %d is not a device pointer", m);
+    }
+    // a peer shard: mapped by gqe_ipc_open (CUDA reports IPC mappings under the importing
+    // device), or any other pointer that resolves to a different device
+    remote[m] = attr.device != c->device || is_ipc_pointer(tables[m]);
+  }
   c->tables.assign(tables, tables + n_modes);
   c->table_rows.assign(rows, rows + n_modes);
+  c->table_remote.swap(remote);
   c->d = d;
   return GQE_OK;
 }
@@ -221,12 +239,14 @@ static int resolve(gqe_ctx* c, const gqe_plan& pl, SegDev* s) {
   s->n_anchor = na;
   s->tgt_table = c->tables[pl.target_mode];
   if (!s->tgt_table) return fail(c, GQE_ERR_UNBOUND, "target mode %d has no table on this rank", pl.target_mode);
+  if (c->table_remote[pl.target_mode]) s->remote_mask |= 8u;
   for (int k = 0; k < na; ++k) {
     if (pl.anchor_mode[k] < 0 || pl.anchor_mode[k] >= nm)
       return fail(c, GQE_ERR_INVALID, "anchor %d mode %d out of range", k, pl.anchor_mode[k]);
     s->anc_table[k] = c->tables[pl.anchor_mode[k]];
     if (!s->anc_table[k])
       return fail(c, GQE_ERR_UNBOUND, "anchor %d mode %d has no table on this rank", k, pl.anchor_mode[k]);
+    if (c->table_remote[pl.anchor_mode[k]]) s->remote_mask |= 1u << k;
   }
   for (int k = 0; k < nr; ++k) {
     if (pl.rel[k] < 0 || pl.rel[k] >= (int)c->rels.size())
@@ -668,6 +688,11 @@ cuMemGetAddressRange_t address_range_fn() {
 }  // namespace
 
 static_assert(sizeof(cudaIpcMemHandle_t) == GQE_IPC_HANDLE_BYTES, "IPC handle size");
+
+static bool is_ipc_pointer(const void* p) {
+  std::lock_guard<std::mutex> lock(g_ipc_mu);
+  return g_ipc_by_ptr.count(const_cast<void*>(p)) != 0;
+}
 
 extern "C" int gqe_ipc_export(gqe_ctx* c, const void* dev_ptr, uint8_t* handle_out, int64_t* offset_out) {
   if (!c) return GQE_ERR_INVALID;

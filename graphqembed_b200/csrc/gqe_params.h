@@ -21,6 +21,8 @@ constexpr float kCosEps = 1e-8f;  // nn.CosineSimilarity default eps (model.py:6
 struct SegDev {
   int32_t structure;
   int32_t n_anchor;
+  uint32_t remote_mask;  // bit k: anchor table k lives in a PEER GPU's HBM; bit 3: the target table
+  int32_t pad_;
   const float* tgt_table;
   const float* anc_table[GQE_MAX_ANCHORS];
   const float* rel[GQE_MAX_RELS];  // relation parameters in application order

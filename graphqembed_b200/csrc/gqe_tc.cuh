@@ -294,11 +294,14 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
   const bool mine = lane < RPW && my_r < n_valid;
   int32_t gsrc0 = -1, gsrc1 = -1, gsrc2 = -1;      // gather sources: anchors 0..2 or (chains) the targets
   int32_t ssrc0 = -1, ssrc1 = -1;                  // scoring rows: the anchor (chains) or targets 0, 1
+  // (peer shards are never prefetched: a bulk L2 prefetch of a PEER address is ~100x slower
+  // than the NVLink loads it would hide -- profiles/r01_peer_gather_micro.md)
+  const uint32_t rm = s.remote_mask;
   if (chain) {
     if (mine) {
       gsrc0 = __ldg(p.target_rows + row_begin + my_r);
       ssrc0 = __ldg(p.anchor_rows + (row_begin + my_r) / T);
-      ptx::tma_prefetch_l2(s.anc_table[0] + (size_t)ssrc0 * D, D * 4);
+      if (!(rm & 1u)) ptx::tma_prefetch_l2(s.anc_table[0] + (size_t)ssrc0 * D, D * 4);
     }
   } else if (mine) {
     gsrc0 = __ldg(p.anchor_rows + row_begin + my_r);
@@ -306,10 +309,12 @@ __device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, i
     if (n_branch > 2) gsrc2 = __ldg(p.anchor_rows + 2 * p.anchor_stride + row_begin + my_r);
     ssrc0 = __ldg(p.target_rows + (row_begin + my_r) * T);
     if (T > 1) ssrc1 = __ldg(p.target_rows + (row_begin + my_r) * T + 1);
-    ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
-    if (n_branch > 2) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
-    ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
-    if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
+    if (!(rm & 2u)) ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
+    if (n_branch > 2 && !(rm & 4u)) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
+    if (!(rm & 8u)) {
+      ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
+      if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
+    }
   }
 
   for (int st = 0; st < pg.n; ++st) {
