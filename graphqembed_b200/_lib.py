@@ -67,6 +67,7 @@ _SIGNATURES = {
     "gqe_get_precision": (C.c_int, [_P]),
     "gqe_last_error": (C.c_char_p, [_P]),
     "gqe_launch_count": (C.c_int64, [_P]),
+    "gqe_debug_set_phase_log": (C.c_int, [_P, _P, C.c_int64]),
     "gqe_bind_tables": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64), C.c_int32]),
     "gqe_bind_relations": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.c_int32]),
     "gqe_bind_intersection": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(_P), C.c_int32, C.c_int32]),
@@ -205,6 +206,9 @@ class Context(object):
 
     def launch_count(self):
         return int(self._lib.gqe_launch_count(self._h))
+
+    def debug_set_phase_log(self, log_ptr, n_tiles):
+        self._check(self._lib.gqe_debug_set_phase_log(self._h, _P(log_ptr or 0), int(n_tiles)))
 
     # -- binding ------------------------------------------------------------
     def bind_tables(self, table_ptrs, rows, d):

@@ -43,11 +43,16 @@ struct gqe_ctx {
   uint8_t* packed = nullptr;
   size_t packed_cap = 0;
 
+  // diagnostics: per-tile phase stamps of the tensor-core kernel
+  unsigned long long* phase_log = nullptr;
+  int64_t phase_cap = 0;
+
   // margin-loss reduction scratch
   double* partials = nullptr;
   int64_t partials_cap = 0;
   double* loss_acc = nullptr;
   unsigned int* ticket = nullptr;
+  unsigned int* tile_counter = nullptr;
 
   // staging for the *_host entry points (grow on demand)
   void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -115,12 +120,14 @@ extern "C" int gqe_create(int device, void* stream, gqe_ctx** out) {
   c->device = device;
   c->stream = (cudaStream_t)stream;
   if (cudaMalloc(&c->loss_acc, sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&c->ticket, sizeof(unsigned int)) != cudaSuccess) {
+      cudaMalloc(&c->ticket, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMalloc(&c->tile_counter, sizeof(unsigned int)) != cudaSuccess) {
     delete c;
     return fail(nullptr, GQE_ERR_NOMEM, "gqe_create: cudaMalloc failed");
   }
   cudaMemset(c->loss_acc, 0, sizeof(double));
   cudaMemset(c->ticket, 0, sizeof(unsigned int));
+  cudaMemset(c->tile_counter, 0, sizeof(unsigned int));
   *out = c;
   return GQE_OK;
 }
@@ -132,6 +139,7 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   cudaFree(c->packed);
   cudaFree(c->loss_acc);
   cudaFree(c->ticket);
+  cudaFree(c->tile_counter);
   for (void* p : c->stage) cudaFree(p);
   delete c;
 }
@@ -150,6 +158,14 @@ extern "C" int gqe_set_precision(gqe_ctx* c, int32_t precision) {
   return GQE_OK;
 }
 extern "C" int gqe_get_precision(const gqe_ctx* c) { return c ? c->precision : GQE_ERR_INVALID; }
+
+extern "C" int gqe_debug_set_phase_log(gqe_ctx* c, uint64_t* log, int64_t n_tiles) {
+  if (!c) return GQE_ERR_INVALID;
+  if ((log == nullptr) != (n_tiles == 0) || n_tiles < 0) return fail(c, GQE_ERR_INVALID, "gqe_debug_set_phase_log: bad arguments");
+  c->phase_log = reinterpret_cast<unsigned long long*>(log);
+  c->phase_cap = n_tiles;
+  return GQE_OK;
+}
 
 extern "C" const char* gqe_last_error(const gqe_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 extern "C" int64_t gqe_launch_count(const gqe_ctx* c) { return c ? c->launches : 0; }
@@ -317,6 +333,9 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
   lp.inv_q = 1.0 / (double)nq_total;
   lp.loss_acc = c->loss_acc;
   lp.ticket = c->ticket;
+  lp.tile_counter = c->tile_counter;
+  lp.phase_log = c->phase_log;
+  lp.phase_cap = c->phase_cap;
 
   // Bilinear d x d contractions go to the tensor cores (tcgen05, bf16x3 split) unless the
   // context asks for exact fp32; the ragged target layout stays on the fp32 kernels.
@@ -402,6 +421,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       }
     }
     lp.n_segs = n;
+    lp.n_tiles = tiles;
     if (out_loss) {
       int rc = ensure_partials(c, tiles);
       if (rc != GQE_OK) return rc;

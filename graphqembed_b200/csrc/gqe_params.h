@@ -51,7 +51,14 @@ struct LaunchParams {
   double* partials;   // [gridDim.x]
   double* loss_acc;   // running sum across the launches of one call
   unsigned int* ticket;
+  // persistent tensor-core kernel: tiles of this launch and the dynamic tile counter
+  int64_t n_tiles;
+  unsigned int* tile_counter;
+  // diagnostics (gqe_debug_set_phase_log): kPhaseSlots (tag << 56 | clock64) stamps per tile
+  unsigned long long* phase_log;
+  int64_t phase_cap;  // tiles the log has room for
 };
+constexpr int kPhaseSlots = 32;
 
 struct OpParams {
   int32_t op;       // see OP_* below

@@ -67,7 +67,10 @@ struct Ctl {
   uint64_t empty[kStages];
   uint64_t a_ready;
   uint64_t acc_full;
+  uint64_t sched_full[2];   // tile-id ring: scheduler (producer thread) -> workers, MMA issuer
+  uint64_t sched_empty[2];
   double red[16];
+  int64_t tile_id[2];
   uint32_t tmem_base;
   int last;
 };
@@ -163,6 +166,7 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
 #pragma unroll 1
   for (int r0 = 0; r0 < RPW; r0 += U) {
     float4 v[U][NV];
+    float ss[U];
     bool okv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -174,19 +178,27 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int r = wid * RPW + r0 + u;
-      float ss = 0.f;
+      ss[u] = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        ss = fmaf(v[u][j].x, v[u][j].x, ss);
-        ss = fmaf(v[u][j].y, v[u][j].y, ss);
-        ss = fmaf(v[u][j].z, v[u][j].z, ss);
-        ss = fmaf(v[u][j].w, v[u][j].w, ss);
+        ss[u] = fmaf(v[u][j].x, v[u][j].x, ss[u]);
+        ss[u] = fmaf(v[u][j].y, v[u][j].y, ss[u]);
+        ss[u] = fmaf(v[u][j].z, v[u][j].z, ss[u]);
+        ss[u] = fmaf(v[u][j].w, v[u][j].w, ss[u]);
       }
-      ss = warp_sum_f(ss);
-      // x / |x| as x * (1/|x|): one IEEE division per row (|x| = 0 -> inf -> 0*inf = NaN,
-      // the reference's 0/0); the extra rounding is far below the bf16x3 error
-      const float inv = okv[u] ? __fdiv_rn(1.f, sqrtf(ss)) : 0.f;
+    }
+    // the U butterflies run in lockstep so that their shuffle latencies overlap
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = wid * RPW + r0 + u;
+      // x / |x| as x * rsqrt(|x|^2): branch-free (MUFU.RSQ, ~2^-22 relative, far below the
+      // bf16x3 error); |x| = 0 -> inf -> 0 * inf = NaN, the reference's 0/0
+      const float inv = okv[u] ? rsqrtf(ss[u]) : 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         uint2 hi, lo;
@@ -199,6 +211,16 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
       }
     }
   }
+}
+
+// Branch-free cosine pieces of the scoring phase (the compiler cannot interleave rows across
+// the slow-path branches of sqrtf / IEEE division).  All ~2^-22 relative, far below 1e-4.
+//   unit_dot(d, nn) = d / sqrt(nn)   (nn = 0 -> 0 * inf = NaN, the reference's 0/0)
+//   clamped_norm(nn) = max(sqrt(nn), eps)
+__device__ __forceinline__ float unit_dot(float d, float nn) { return d * rsqrtf(nn); }
+__device__ __forceinline__ float clamped_norm(float nn) {
+  const float n = nn > 0.f ? nn * rsqrtf(nn) : nn;  // keeps 0 -> 0 and NaN -> NaN
+  return n >= kCosEps ? n : (n != n ? n : kCosEps);
 }
 
 // 16 fp32 values of (row r, columns col0..col0+15) -> the A operand planes
@@ -226,16 +248,42 @@ __device__ __forceinline__ float hinge_(float margin, float pos, float neg) {
 
 // Deterministic two-level reduction of the per-CTA hinge sums (model.py:126 mean);
 // executed by the worker threads only.
+// ---- tile bookkeeping -------------------------------------------------------------------
+// The kernel is PERSISTENT: one CTA per SM slot walks over tiles handed out by a dynamic
+// scheduler (heaviest structures first, see gqe_capi.cu).  A tile id maps to its segment by
+// a scan of the (<= 32) tile_begin offsets.
+template <int STRUCT>
+__device__ __forceinline__ int seg_of_tile(const LaunchParams& p, int64_t tile) {
+  int si = 0;
+  if (STRUCT < 0) {
+    for (int i = 1; i < p.n_segs; ++i)
+      if (tile >= p.seg[i].tile_begin) si = i;
+  }
+  return si;
+}
+
+struct TileRing {  // consumer side of the tile-id ring
+  uint32_t k = 0;
+  __device__ __forceinline__ int64_t peek(Ctl* ctl, uint32_t ahead) const {
+    const uint32_t kk = k + ahead;
+    ptx::mbar_wait(ptx::smem_u32(&ctl->sched_full[kk & 1]), (kk >> 1) & 1);
+    return *reinterpret_cast<volatile int64_t*>(&ctl->tile_id[kk & 1]);
+  }
+  __device__ __forceinline__ int64_t take(Ctl* ctl) {
+    const int64_t t = peek(ctl, 0);
+    ptx::mbar_arrive(ptx::smem_u32(&ctl->sched_empty[k & 1]));
+    ++k;
+    return t;
+  }
+};
+
+// Final margin-loss reduction, once per CTA after its last tile: per-tile hinge sums were
+// written to p.partials[tile]; the last CTA to finish adds them up in tile order, so the
+// result does not depend on which CTA ran which tile (model.py:126 mean).
 template <int D>
-__device__ __forceinline__ void loss_reduce(const LaunchParams& p, Ctl* ctl, double local, int wid, int lane) {
+__device__ __forceinline__ void loss_finish(const LaunchParams& p, Ctl* ctl, int wid, int lane) {
   using C = Cfg<D>;
-  local = warp_sum_d(local);
-  if (lane == 0) ctl->red[wid] = local;
-  ptx::named_bar_sync(1, C::kWorkerThreads);
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < C::kWorkerWarps; ++w) s += ctl->red[w];
-    p.partials[blockIdx.x] = s;
     __threadfence();
     const unsigned int t = atomicAdd(p.ticket, 1u);
     ctl->last = (t == gridDim.x - 1);
@@ -243,343 +291,475 @@ __device__ __forceinline__ void loss_reduce(const LaunchParams& p, Ctl* ctl, dou
   ptx::named_bar_sync(1, C::kWorkerThreads);
   if (ctl->last && wid == 0) {
     __threadfence();
-    double s = 0.0;
-    for (unsigned int i = lane; i < gridDim.x; i += 32) s += __ldcg(p.partials + i);
-    s = warp_sum_d(s);
-    if (lane == 0) {
-      const double acc = *p.loss_acc + s;
-      *p.loss_acc = acc;
-      *p.out_loss = (float)(acc * p.inv_q);
+    if (p.out_loss) {
+      double s = 0.0;
+      for (int64_t i = lane; i < p.n_tiles; i += 32) s += __ldcg(p.partials + i);
+      s = warp_sum_d(s);
+      if (lane == 0) {
+        const double acc = *p.loss_acc + s;
+        *p.loss_acc = acc;
+        *p.out_loss = (float)(acc * p.inv_q);
+      }
+    }
+    if (lane == 0) {  // leave the scheduler state ready for the next launch
       *p.ticket = 0u;
+      *p.tile_counter = 0u;
     }
   }
 }
 
-// ---- worker warps ---------------------------------------------------------------------
+// float4 chunk c of row r of the transposed query tile (row stride D floats, XOR-swizzled so
+// both the thread-per-row writes and the warp-per-row reads are bank-conflict free)
 template <int D>
-__device__ __forceinline__ void worker(const LaunchParams& p, const SegDev& s, int structure, int64_t tile_in_seg,
-                                       uint8_t* smem, Ctl* ctl) {
+__device__ __forceinline__ float4* q_chunk(float* qsm, int r, int c) {
+  return reinterpret_cast<float4*>(qsm + (size_t)r * D) + (c ^ (r & 7));
+}
+
+// ---- worker warps ---------------------------------------------------------------------
+template <int D, int STRUCT>
+__device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
   constexpr int NCH = C::kColsPerThread / 16;      // 16-column TMEM chunks per thread
   constexpr int RPW = kRows / C::kWorkerWarps;     // tile rows per warp in the warp-per-row phases
   constexpr int NV = D / 128;                      // float4 per lane per table row
-  constexpr int QS = D + 4;                        // fp32 row stride of the transposed query tile
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = 32 * (wid & 3) + lane;           // TMEM lane == tile row (thread-per-row phases)
   const int col_base = (wid >> 2) * C::kColsPerThread;
-  const bool chain = structure <= GQE_CHAIN3;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
   const bool use_min = p.inter == GQE_INTER_DEEPSETS_MIN || p.inter == GQE_INTER_SIMPLE_MIN;
-  const int n_branch = s.n_anchor;
   const int T = p.T;
-
-  // rows of this tile
-  const int64_t row_begin = (chain ? s.q_begin * T : s.q_begin) + tile_in_seg * kRows;
-  const int64_t row_end = chain ? s.q_end * T : s.q_end;
-  const int n_valid = (int)min((int64_t)kRows, row_end - row_begin);
-
-  Prog pg;
-  build_program(pg, structure, deepsets);
-
   const uint32_t tmem_base = ctl->tmem_base;
   const uint32_t t_acc = tmem_base + ((uint32_t)(32 * (wid & 3)) << 16) + col_base;
   const uint32_t t_agg = t_acc + D;
   const uint32_t bar_a_ready = ptx::smem_u32(&ctl->a_ready);
   const uint32_t bar_acc_full = ptx::smem_u32(&ctl->acc_full);
-
-  // ---- every index this warp will need, loaded once, up front (lane i <-> tile row
-  // wid*RPW + i), and an L2 prefetch of the table rows behind them: the DRAM latency of
-  // the later gathers and of the scoring rows overlaps the first contraction ------------
   const int my_r = wid * RPW + lane;               // meaningful for lane < RPW
-  const bool mine = lane < RPW && my_r < n_valid;
-  int32_t gsrc0 = -1, gsrc1 = -1, gsrc2 = -1;      // gather sources: anchors 0..2 or (chains) the targets
-  int32_t ssrc0 = -1, ssrc1 = -1;                  // scoring rows: the anchor (chains) or targets 0, 1
-  // (peer shards are never prefetched: a bulk L2 prefetch of a PEER address is ~100x slower
-  // than the NVLink loads it would hide -- profiles/r01_peer_gather_micro.md)
-  const uint32_t rm = s.remote_mask;
-  if (chain) {
-    if (mine) {
-      gsrc0 = __ldg(p.target_rows + row_begin + my_r);
-      ssrc0 = __ldg(p.anchor_rows + (row_begin + my_r) / T);
-      if (!(rm & 1u)) ptx::tma_prefetch_l2(s.anc_table[0] + (size_t)ssrc0 * D, D * 4);
-    }
-  } else if (mine) {
-    gsrc0 = __ldg(p.anchor_rows + row_begin + my_r);
-    gsrc1 = __ldg(p.anchor_rows + p.anchor_stride + row_begin + my_r);
-    if (n_branch > 2) gsrc2 = __ldg(p.anchor_rows + 2 * p.anchor_stride + row_begin + my_r);
-    ssrc0 = __ldg(p.target_rows + (row_begin + my_r) * T);
-    if (T > 1) ssrc1 = __ldg(p.target_rows + (row_begin + my_r) * T + 1);
-    if (!(rm & 2u)) ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
-    if (n_branch > 2 && !(rm & 4u)) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
-    if (!(rm & 8u)) {
-      ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
-      if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
-    }
-  }
+  float* qsm = reinterpret_cast<float*>(smem);     // overlays the A planes (exactly 128 x D fp32)
 
-  for (int st = 0; st < pg.n; ++st) {
-    const int g = pg.gather[st];
-    if (g != G_NONE) {
-      if (g == G_TARGET) gather_to_a<D>(smem, s.tgt_table, gsrc0, wid, lane);
-      else gather_to_a<D>(smem, s.anc_table[g], g == 0 ? gsrc0 : (g == 1 ? gsrc1 : gsrc2), wid, lane);
+  TileRing ring;
+  uint32_t gs = 0;                                 // steps issued so far (a_ready / acc_full parity)
+  for (;;) {
+    const int64_t tile = ring.take(ctl);
+    if (tile >= p.n_tiles) break;
+    const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
+    const int structure = STRUCT >= 0 ? STRUCT : s.structure;
+    const bool chain = structure <= GQE_CHAIN3;
+    const int n_branch = s.n_anchor;
+
+    // rows of this tile
+    const int64_t row_begin = (chain ? s.q_begin * T : s.q_begin) + (tile - s.tile_begin) * kRows;
+    const int64_t row_end = chain ? s.q_end * T : s.q_end;
+    const int n_valid = (int)min((int64_t)kRows, row_end - row_begin);
+
+    Prog pg;
+    build_program(pg, structure, deepsets);
+
+    // diagnostics: per-tile phase stamps of worker thread 0 (tools/phase_report.py)
+    int n_stamp = 0;
+    unsigned long long* plog = nullptr;
+    if (p.phase_log && threadIdx.x == 0 && tile < p.phase_cap) {
+      plog = p.phase_log + (size_t)tile * kPhaseSlots;
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      plog[kPhaseSlots - 1] = smid;
     }
-    // A operand complete (generic-proxy stores -> async proxy) and this thread's
-    // TMEM reads of the previous accumulator retired: hand over to the MMA issuer
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before_sync();
-    ptx::mbar_arrive(bar_a_ready);
+    auto stamp = [&](unsigned long long tag) {
+      if (plog && n_stamp < kPhaseSlots - 1)
+        plog[n_stamp++] = (tag << 56) | ((unsigned long long)clock64() & 0x00ffffffffffffffull);
+    };
+    stamp(1 + 16 * (unsigned long long)structure);
 
-    ptx::mbar_wait(bar_acc_full, (uint32_t)(st & 1));
-    ptx::tc_fence_after_sync();
+    // ---- every index this warp will need, loaded once, up front (lane i <-> tile row
+    // wid*RPW + i), and an L2 prefetch of the LOCAL table rows behind them: the DRAM latency
+    // of the later gathers and of the scoring rows overlaps the first contraction.  (Peer
+    // shards are never prefetched: a bulk L2 prefetch of a PEER address is ~100x slower than
+    // the NVLink loads it would hide -- profiles/r01_peer_gather_micro.md) ---------------------
+    const bool mine = lane < RPW && my_r < n_valid;
+    const uint32_t rm = s.remote_mask;
+    int32_t gsrc0 = -1, gsrc1 = -1, gsrc2 = -1;      // gather sources: anchors 0..2 or (chains) the targets
+    int32_t ssrc0 = -1, ssrc1 = -1;                  // scoring rows: the anchor (chains) or targets 0, 1
+    if (chain) {
+      if (mine) {
+        gsrc0 = __ldg(p.target_rows + row_begin + my_r);
+        ssrc0 = __ldg(p.anchor_rows + (row_begin + my_r) / T);
+        if (!(rm & 1u)) ptx::tma_prefetch_l2(s.anc_table[0] + (size_t)ssrc0 * D, D * 4);
+      }
+    } else if (mine) {
+      gsrc0 = __ldg(p.anchor_rows + row_begin + my_r);
+      gsrc1 = __ldg(p.anchor_rows + p.anchor_stride + row_begin + my_r);
+      if (n_branch > 2) gsrc2 = __ldg(p.anchor_rows + 2 * p.anchor_stride + row_begin + my_r);
+      ssrc0 = __ldg(p.target_rows + (row_begin + my_r) * T);
+      if (T > 1) ssrc1 = __ldg(p.target_rows + (row_begin + my_r) * T + 1);
+      if (!(rm & 2u)) ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
+      if (n_branch > 2 && !(rm & 4u)) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
+      if (!(rm & 8u)) {
+        ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
+        if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
+      }
+    }
 
-    const int epi = pg.epi[st];
-    const int kind = epi & E_KIND;
-    if (kind == E_SCORE) break;  // scored below, straight from the accumulator
-    const bool agg_read = kind == E_AGG && !(epi & F_FIRST);
-    const float inv_nb = 1.f / (float)n_branch;
-    uint32_t raw[16], araw[16] = {};
-    ptx::tmem_ld16(t_acc, raw);
-    if (agg_read) ptx::tmem_ld16(t_agg, araw);
+    for (int st = 0; st < pg.n; ++st, ++gs) {
+      const int g = pg.gather[st];
+      if (g != G_NONE) {
+        if (g == G_TARGET) gather_to_a<D>(smem, s.tgt_table, gsrc0, wid, lane);
+        else gather_to_a<D>(smem, s.anc_table[g], g == 0 ? gsrc0 : (g == 1 ? gsrc1 : gsrc2), wid, lane);
+        stamp(2);
+      }
+      // A operand complete (generic-proxy stores -> async proxy) and this thread's
+      // TMEM reads of the previous accumulator retired: hand over to the MMA issuer
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(bar_a_ready);
+
+      if (st == 0) {
+        // while the first contraction runs: pull the first-gather rows of the NEXT tile of
+        // this CTA into L2, so that its only exposed gather is an L2 hit
+        const int64_t nt = ring.peek(ctl, 0);
+        if (nt < p.n_tiles && lane < RPW) {
+          const SegDev& s2 = p.seg[seg_of_tile<STRUCT>(p, nt)];
+          const bool chain2 = (STRUCT >= 0 ? STRUCT : s2.structure) <= GQE_CHAIN3;
+          const int64_t rb2 = (chain2 ? s2.q_begin * T : s2.q_begin) + (nt - s2.tile_begin) * kRows;
+          const int64_t re2 = chain2 ? s2.q_end * T : s2.q_end;
+          if (rb2 + my_r < re2 && !(s2.remote_mask & (chain2 ? 8u : 1u))) {
+            const int32_t r2 = __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r);
+            ptx::tma_prefetch_l2((chain2 ? s2.tgt_table : s2.anc_table[0]) + (size_t)r2 * D, D * 4);
+          }
+        }
+      }
+
+      ptx::mbar_wait(bar_acc_full, gs & 1);
+      ptx::tc_fence_after_sync();
+      stamp(3);
+
+      const int epi = pg.epi[st];
+      const int kind = epi & E_KIND;
+      if (kind == E_SCORE) { ++gs; break; }  // scored below, straight from the accumulator
+      const bool agg_read = kind == E_AGG && !(epi & F_FIRST);
+      const float inv_nb = 1.f / (float)n_branch;
+      uint32_t raw[16], araw[16] = {};
+      ptx::tmem_ld16(t_acc, raw);
+      if (agg_read) ptx::tmem_ld16(t_agg, araw);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        float x[16], a[16];
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          x[i] = __uint_as_float(raw[i]);
+          a[i] = __uint_as_float(araw[i]);
+        }
+        if (ch + 1 < NCH) {  // next chunk streams out of TMEM while this one is processed
+          ptx::tmem_ld16(t_acc + 16 * (ch + 1), raw);
+          if (agg_read) ptx::tmem_ld16(t_agg + 16 * (ch + 1), araw);
+        }
+        if (kind == E_AGG) {
+          if (epi & F_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = relu_nan_(x[i]);
+          }
+          if (agg_read) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = use_min ? min_nan_(a[i], x[i]) : a[i] + x[i];
+          }
+          if (!(epi & F_LAST)) {
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(x[i]);
+            ptx::tmem_st16(t_agg + 16 * ch, o);
+            continue;
+          }
+          if (!use_min) {  // torch.mean over the stacked operands
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] *= inv_nb;
+          }
+          if (epi & F_DEST_ACC) {  // combined embedding is the query embedding itself
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(x[i]);
+            ptx::tmem_st16(t_acc + 16 * ch, o);
+            continue;
+          }
+        }
+        store_a16<D>(smem, row, col_base + 16 * ch, x);
+      }
+      ptx::tmem_wait_st();
+      stamp(4);
+      if (kind == E_AGG && (epi & F_DEST_ACC)) { ++gs; break; }
+    }
+
+    // ---- score ------------------------------------------------------------------------
+    // The accumulator row is the projected target (chains) or the query embedding
+    // (intersections).  It is transposed through shared memory (the A planes are dead by
+    // now) so that the table rows it is scored against are read warp-per-row with coalesced
+    // 128-bit loads, like the gathers.
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
-      float x[16], a[16];
+      uint32_t raw[16];
+      ptx::tmem_ld16(t_acc + 16 * ch, raw);
       ptx::tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        x[i] = __uint_as_float(raw[i]);
-        a[i] = __uint_as_float(araw[i]);
-      }
-      if (ch + 1 < NCH) {  // next chunk streams out of TMEM while this one is processed
-        ptx::tmem_ld16(t_acc + 16 * (ch + 1), raw);
-        if (agg_read) ptx::tmem_ld16(t_agg + 16 * (ch + 1), araw);
-      }
-      if (kind == E_AGG) {
-        if (epi & F_RELU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = relu_nan_(x[i]);
-        }
-        if (agg_read) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = use_min ? min_nan_(a[i], x[i]) : a[i] + x[i];
-        }
-        if (!(epi & F_LAST)) {
-          uint32_t o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(x[i]);
-          ptx::tmem_st16(t_agg + 16 * ch, o);
-          continue;
-        }
-        if (!use_min) {  // torch.mean over the stacked operands
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] *= inv_nb;
-        }
-        if (epi & F_DEST_ACC) {  // combined embedding is the query embedding itself
-          uint32_t o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(x[i]);
-          ptx::tmem_st16(t_acc + 16 * ch, o);
-          continue;
-        }
-      }
-      store_a16<D>(smem, row, col_base + 16 * ch, x);
+      for (int i = 0; i < 4; ++i)
+        *q_chunk<D>(qsm, row, (col_base + 16 * ch) / 4 + i) =
+            make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
+                        __uint_as_float(raw[4 * i + 3]));
     }
-    ptx::tmem_wait_st();
-    if (kind == E_AGG && (epi & F_DEST_ACC)) break;
-  }
+    ptx::named_bar_sync(1, C::kWorkerThreads);
+    stamp(5);
 
-  // ---- score ------------------------------------------------------------------------
-  // The accumulator row is the projected target (chains) or the query embedding
-  // (intersections).  It is transposed through shared memory (the A planes and the weight
-  // ring are dead by now) so that the table rows it is scored against are read warp-per-row
-  // with coalesced 128-bit loads, like the gathers.
-  float* qsm = reinterpret_cast<float*>(smem);
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    uint32_t raw[16];
-    ptx::tmem_ld16(t_acc + 16 * ch, raw);
-    ptx::tmem_wait_ld();
-    float4* dst = reinterpret_cast<float4*>(qsm + (size_t)row * QS + col_base + 16 * ch);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      dst[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
-                           __uint_as_float(raw[4 * i + 3]));
-  }
-  ptx::named_bar_sync(1, C::kWorkerThreads);
-
-  double local = 0.0;
-  if (chain) {
-    float s_even = 0.f;
-#pragma unroll 2
-    for (int u = 0; u < RPW; ++u) {
-      const int r = wid * RPW + u;
-      const int32_t arow = __shfl_sync(0xffffffffu, ssrc0, u);
-      if (arow < 0) continue;  // warp-uniform: row past the end of the tile
-      const float4* a_src = reinterpret_cast<const float4*>(s.anc_table[0] + (size_t)arow * D);
-      const float4* q_src = reinterpret_cast<const float4*>(qsm + (size_t)r * QS);
-      float dot = 0.f, yy = 0.f, aa = 0.f;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float4 a = __ldg(a_src + lane + 32 * j);
-        const float4 y = q_src[lane + 32 * j];
-        dot = fmaf(y.x, a.x, dot); dot = fmaf(y.y, a.y, dot); dot = fmaf(y.z, a.z, dot); dot = fmaf(y.w, a.w, dot);
-        yy = fmaf(y.x, y.x, yy); yy = fmaf(y.y, y.y, yy); yy = fmaf(y.z, y.z, yy); yy = fmaf(y.w, y.w, yy);
-        aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
-      }
-      dot = warp_sum_f(dot); yy = warp_sum_f(yy); aa = warp_sum_f(aa);
-      // cos(y, a_hat) with a_hat = a/|a| (unit norm): (y.a/|a|) / max(|y|, eps); a zero
-      // anchor row gives 0/0 = NaN as in the reference
-      const float score = __fdiv_rn(dot, sqrtf(aa)) / fmaxf(sqrtf(yy), kCosEps);
-      if (lane == 0 && p.out_scores) p.out_scores[row_begin + r] = score;
-      if (u & 1) { if (lane == 0) local += (double)hinge_(p.margin, s_even, score); }   // rows (2i, 2i+1) = (pos, neg)
-      else s_even = score;
-    }
-  } else {
+    // Rows are scored SU at a time: all table loads of a batch are issued first and the
+    // warp reductions of the batch run in lockstep (one butterfly level for all values).
+    double local = 0.0;
+    if (chain) {
+      constexpr int SU = 8 / NV;
+      static_assert(RPW % SU == 0 && SU % 2 == 0, "score batch");
 #pragma unroll 1
-    for (int u = 0; u < RPW; ++u) {
-      const int r = wid * RPW + u;
-      int32_t t_a = __shfl_sync(0xffffffffu, ssrc0, u);
-      int32_t t_b = __shfl_sync(0xffffffffu, ssrc1, u);
-      if (t_a < 0) continue;  // warp-uniform: row past the end of the tile
-      const int64_t q = row_begin + r;
-      const float4* q_src = reinterpret_cast<const float4*>(qsm + (size_t)r * QS);
-      float4 y[NV];
-      float qq = 0.f;
+      for (int u0 = 0; u0 < RPW; u0 += SU) {
+        float4 av[SU][NV];
+        int32_t arow[SU];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        y[j] = q_src[lane + 32 * j];
-        qq = fmaf(y[j].x, y[j].x, qq); qq = fmaf(y[j].y, y[j].y, qq); qq = fmaf(y[j].z, y[j].z, qq); qq = fmaf(y[j].w, y[j].w, qq);
-      }
-      qq = warp_sum_f(qq);
-      const float nq = fmaxf(sqrtf(qq), kCosEps);
-      float s_first = 0.f;
-      for (int t0 = 0; t0 < T; t0 += 2) {
-        const bool has1 = t0 + 1 < T;
-        if (t0 > 0) {  // more than one (pos, neg) pair per query: the eval shape
-          t_a = __ldg(p.target_rows + q * T + t0);
-          t_b = has1 ? __ldg(p.target_rows + q * T + t0 + 1) : t_a;
-        }
-        const float4* a_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)t_a * D);
-        const float4* b_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)(has1 ? t_b : t_a) * D);
-        float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+        for (int u = 0; u < SU; ++u) {
+          arow[u] = __shfl_sync(0xffffffffu, ssrc0, u0 + u);  // -1: row past the end of the tile (warp-uniform)
+          const float4* a_src = reinterpret_cast<const float4*>(s.anc_table[0] + (size_t)(arow[u] < 0 ? 0 : arow[u]) * D);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const float4 a = __ldg(a_src + lane + 32 * j);
-          const float4 b = __ldg(b_src + lane + 32 * j);
-          d0 = fmaf(y[j].x, a.x, d0); d0 = fmaf(y[j].y, a.y, d0); d0 = fmaf(y[j].z, a.z, d0); d0 = fmaf(y[j].w, a.w, d0);
-          n0 = fmaf(a.x, a.x, n0); n0 = fmaf(a.y, a.y, n0); n0 = fmaf(a.z, a.z, n0); n0 = fmaf(a.w, a.w, n0);
-          d1 = fmaf(y[j].x, b.x, d1); d1 = fmaf(y[j].y, b.y, d1); d1 = fmaf(y[j].z, b.z, d1); d1 = fmaf(y[j].w, b.w, d1);
-          n1 = fmaf(b.x, b.x, n1); n1 = fmaf(b.y, b.y, n1); n1 = fmaf(b.z, b.z, n1); n1 = fmaf(b.w, b.w, n1);
+          for (int j = 0; j < NV; ++j) av[u][j] = arow[u] < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(a_src + lane + 32 * j);
         }
-        d0 = warp_sum_f(d0); n0 = warp_sum_f(n0); d1 = warp_sum_f(d1); n1 = warp_sum_f(n1);
-        // t_hat = t/|t| has unit norm: cos(t_hat, q) = (t.q/|t|) / max(|q|, eps); a zero
-        // target row gives 0/0 = NaN as in the reference
-        const float s0 = __fdiv_rn(d0, sqrtf(n0)) / nq;
-        const float s1 = __fdiv_rn(d1, sqrtf(n1)) / nq;
-        if (lane == 0 && p.out_scores) {
-          p.out_scores[q * T + t0] = s0;
-          if (has1) p.out_scores[q * T + t0 + 1] = s1;
+        float red[SU][3];  // y.a, |y|^2, |a|^2
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          const int r = wid * RPW + u0 + u;
+          float dot = 0.f, yy = 0.f, aa = 0.f;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const float4 a = av[u][j];
+            const float4 y = *q_chunk<D>(qsm, r, lane + 32 * j);
+            dot = fmaf(y.x, a.x, dot); dot = fmaf(y.y, a.y, dot); dot = fmaf(y.z, a.z, dot); dot = fmaf(y.w, a.w, dot);
+            yy = fmaf(y.x, y.x, yy); yy = fmaf(y.y, y.y, yy); yy = fmaf(y.z, y.z, yy); yy = fmaf(y.w, y.w, yy);
+            aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
+          }
+          red[u][0] = dot; red[u][1] = yy; red[u][2] = aa;
         }
-        if (t0 == 0) s_first = hinge_(p.margin, s0, s1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < SU; ++u)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) red[u][k] += __shfl_xor_sync(0xffffffffu, red[u][k], o);
+        }
+        float sc[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          // cos(y, a_hat) with a_hat = a/|a| (unit norm): (y.a/|a|) / max(|y|, eps); a zero
+          // anchor row gives 0/0 = NaN as in the reference
+          sc[u] = __fdividef(unit_dot(red[u][0], red[u][2]), clamped_norm(red[u][1]));
+          if (lane == 0 && p.out_scores && arow[u] >= 0) p.out_scores[row_begin + wid * RPW + u0 + u] = sc[u];
+        }
+        if (lane == 0) {  // rows (2i, 2i+1) = (pos, neg) of one query (T == 2 whenever the loss is on)
+#pragma unroll
+          for (int u = 0; u < SU; u += 2)
+            if (arow[u + 1] >= 0) local += (double)hinge_(p.margin, sc[u], sc[u + 1]);
+        }
       }
-      if (lane == 0) local += (double)s_first;
+    } else {
+      constexpr int SU = 4 / NV;
+      static_assert(RPW % SU == 0, "score batch");
+#pragma unroll 1
+      for (int u0 = 0; u0 < RPW; u0 += SU) {
+        float4 ta[SU][NV], tb[SU][NV];
+        int32_t ra[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          ra[u] = __shfl_sync(0xffffffffu, ssrc0, u0 + u);    // -1: row past the end of the tile (warp-uniform)
+          const int32_t rb = __shfl_sync(0xffffffffu, ssrc1, u0 + u);
+          const bool ok = ra[u] >= 0;
+          const float4* a_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)(ok ? ra[u] : 0) * D);
+          const float4* b_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)(ok ? (T > 1 ? rb : ra[u]) : 0) * D);
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            ta[u][j] = ok ? __ldg(a_src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tb[u][j] = ok ? __ldg(b_src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float red[SU][5];  // |q|^2, q.a, |a|^2, q.b, |b|^2
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          const int r = wid * RPW + u0 + u;
+          float qq = 0.f, d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const float4 y = *q_chunk<D>(qsm, r, lane + 32 * j);
+            const float4 a = ta[u][j], b = tb[u][j];
+            qq = fmaf(y.x, y.x, qq); qq = fmaf(y.y, y.y, qq); qq = fmaf(y.z, y.z, qq); qq = fmaf(y.w, y.w, qq);
+            d0 = fmaf(y.x, a.x, d0); d0 = fmaf(y.y, a.y, d0); d0 = fmaf(y.z, a.z, d0); d0 = fmaf(y.w, a.w, d0);
+            n0 = fmaf(a.x, a.x, n0); n0 = fmaf(a.y, a.y, n0); n0 = fmaf(a.z, a.z, n0); n0 = fmaf(a.w, a.w, n0);
+            d1 = fmaf(y.x, b.x, d1); d1 = fmaf(y.y, b.y, d1); d1 = fmaf(y.z, b.z, d1); d1 = fmaf(y.w, b.w, d1);
+            n1 = fmaf(b.x, b.x, n1); n1 = fmaf(b.y, b.y, n1); n1 = fmaf(b.z, b.z, n1); n1 = fmaf(b.w, b.w, n1);
+          }
+          red[u][0] = qq; red[u][1] = d0; red[u][2] = n0; red[u][3] = d1; red[u][4] = n1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < SU; ++u)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) red[u][k] += __shfl_xor_sync(0xffffffffu, red[u][k], o);
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+          if (ra[u] < 0) continue;
+          const int r = wid * RPW + u0 + u;
+          const int64_t q = row_begin + r;
+          const float nq = clamped_norm(red[u][0]);
+          // t_hat = t/|t| has unit norm: cos(t_hat, q) = (t.q/|t|) / max(|q|, eps); a zero
+          // target row gives 0/0 = NaN as in the reference
+          const float s0 = __fdividef(unit_dot(red[u][1], red[u][2]), nq);
+          const float s1 = __fdividef(unit_dot(red[u][3], red[u][4]), nq);
+          if (lane == 0) {
+            if (p.out_scores) {
+              p.out_scores[q * T] = s0;
+              if (T > 1) p.out_scores[q * T + 1] = s1;
+            }
+            local += (double)hinge_(p.margin, s0, s1);
+          }
+          // more than one (pos, neg) pair per query (the eval shape): the remaining targets
+          for (int t0 = 2; t0 < T; ++t0) {
+            const float4* c_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)__ldg(p.target_rows + q * T + t0) * D);
+            float d2 = 0.f, n2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+              const float4 c = __ldg(c_src + lane + 32 * j);
+              const float4 y = *q_chunk<D>(qsm, r, lane + 32 * j);
+              d2 = fmaf(y.x, c.x, d2); d2 = fmaf(y.y, c.y, d2); d2 = fmaf(y.z, c.z, d2); d2 = fmaf(y.w, c.w, d2);
+              n2 = fmaf(c.x, c.x, n2); n2 = fmaf(c.y, c.y, n2); n2 = fmaf(c.z, c.z, n2); n2 = fmaf(c.w, c.w, n2);
+            }
+            d2 = warp_sum_f(d2); n2 = warp_sum_f(n2);
+            if (lane == 0 && p.out_scores) p.out_scores[q * T + t0] = __fdividef(unit_dot(d2, n2), nq);
+          }
+        }
+      }
     }
+    stamp(6);
+    // every warp is done with the transposed tile (the next gather overwrites it) and, for the
+    // loss, the per-tile hinge sum goes to its own slot: partials[tile]
+    if (p.out_loss && lane == 0) ctl->red[wid] = local;
+    ptx::named_bar_sync(1, C::kWorkerThreads);
+    if (p.out_loss && threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int w = 0; w < C::kWorkerWarps; ++w) sum += ctl->red[w];
+      p.partials[tile] = sum;
+    }
+    stamp(7);
   }
-  if (p.out_loss) loss_reduce<D>(p, ctl, local, wid, lane);
+  loss_finish<D>(p, ctl, wid, lane);
 }
 
-// ---- TMA producer: streams the packed planes of every step's matrix -------------------
-template <int D>
-__device__ __forceinline__ void producer(const LaunchParams& p, const SegDev& s, int structure, uint8_t* smem, Ctl* ctl) {
+// ---- TMA producer + tile scheduler: streams the packed planes of every step's matrix ---
+template <int D, int STRUCT>
+__device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
-  Prog pg;
-  build_program(pg, structure, deepsets);
   uint32_t slot = 0, phase = 0;
-  for (int st = 0; st < pg.n; ++st) {
-    const uint8_t* src = step_matrix(s, pg.mat[st]);
+  // tile k of this CTA: the first is blockIdx.x, the rest come from the global counter.
+  // Tile k+1 is published while tile k's weights are being streamed, so the workers can
+  // prefetch its rows; an id >= n_tiles is the stop marker.
+  auto publish = [&](uint32_t k, int64_t id) {
+    ptx::mbar_wait(ptx::smem_u32(&ctl->sched_empty[k & 1]), ((k >> 1) & 1) ^ 1);
+    *reinterpret_cast<volatile int64_t*>(&ctl->tile_id[k & 1]) = id;
+    __threadfence_block();
+    ptx::mbar_arrive(ptx::smem_u32(&ctl->sched_full[k & 1]));
+  };
+  int64_t tile = blockIdx.x;
+  publish(0, tile);
+  for (uint32_t k = 0; tile < p.n_tiles; ++k) {
+    const int64_t next = (int64_t)gridDim.x + (int64_t)atomicAdd(p.tile_counter, 1u);
+    publish(k + 1, next < p.n_tiles ? next : p.n_tiles);
+    const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
+    Prog pg;
+    build_program(pg, STRUCT >= 0 ? STRUCT : s.structure, deepsets);
+    for (int st = 0; st < pg.n; ++st) {
+      const uint8_t* src = step_matrix(s, pg.mat[st]);
 #pragma unroll 1
-    for (int i = 0; i < 2 * C::kKB; ++i) {
-      const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
-      ptx::mbar_wait(empty, phase ^ 1);
-      ptx::mbar_arrive_expect_tx(full, C::kStageBytes);
-      ptx::tma_bulk_g2s(ptx::smem_u32(smem + C::kOffB + slot * C::kStageBytes), src + (size_t)i * C::kStageBytes,
-                        C::kStageBytes, full);
-      if (++slot == kStages) { slot = 0; phase ^= 1; }
+      for (int i = 0; i < 2 * C::kKB; ++i) {
+        const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
+        ptx::mbar_wait(empty, phase ^ 1);
+        ptx::mbar_arrive_expect_tx(full, C::kStageBytes);
+        ptx::tma_bulk_g2s(ptx::smem_u32(smem + C::kOffB + slot * C::kStageBytes), src + (size_t)i * C::kStageBytes,
+                          C::kStageBytes, full);
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      }
     }
+    tile = next;
   }
 }
 
 // ---- MMA issuer ------------------------------------------------------------------------
-template <int D>
-__device__ __forceinline__ void mma_issuer(const LaunchParams& p, int structure, uint8_t* smem, Ctl* ctl) {
+template <int D, int STRUCT>
+__device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
-  Prog pg;
-  build_program(pg, structure, deepsets);
   constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, D);
   const uint32_t tmem_acc = ctl->tmem_base;
   const uint32_t a_hi = ptx::smem_u32(smem + C::kOffAhi), a_lo = ptx::smem_u32(smem + C::kOffAlo);
   const uint32_t b0 = ptx::smem_u32(smem + C::kOffB);
   const uint32_t bar_a_ready = ptx::smem_u32(&ctl->a_ready), bar_acc_full = ptx::smem_u32(&ctl->acc_full);
-  uint32_t slot = 0, phase = 0;
-  for (int st = 0; st < pg.n; ++st) {
-    ptx::mbar_wait(bar_a_ready, (uint32_t)(st & 1));
-    ptx::tc_fence_after_sync();
+  uint32_t slot = 0, phase = 0, gs = 0;
+  TileRing ring;
+  for (;;) {
+    const int64_t tile = ring.take(ctl);
+    if (tile >= p.n_tiles) break;
+    const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
+    Prog pg;
+    build_program(pg, STRUCT >= 0 ? STRUCT : s.structure, deepsets);
+    for (int st = 0; st < pg.n; ++st, ++gs) {
+      ptx::mbar_wait(bar_a_ready, gs & 1);
+      ptx::tc_fence_after_sync();
 #pragma unroll 1
-    for (int kb = 0; kb < C::kKB; ++kb) {
-      // plane 0 of this K block: B_hi, used by A_hi and A_lo
-      {
-        const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
-        ptx::mbar_wait(full, phase);
-        ptx::tc_fence_after_sync();
-        const uint32_t b = b0 + slot * C::kStageBytes;
+      for (int kb = 0; kb < C::kKB; ++kb) {
+        // plane 0 of this K block: B_hi, used by A_hi and A_lo
+        {
+          const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
+          ptx::mbar_wait(full, phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t b = b0 + slot * C::kStageBytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
-                            ptx::umma_desc_sw128(b + 32 * k), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
+                              ptx::umma_desc_sw128(b + 32 * k), idesc, (kb | k) != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_lo + kb * C::kABlockBytes + 32 * k),
-                            ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
-        ptx::umma_commit(empty);
-        if (++slot == kStages) { slot = 0; phase ^= 1; }
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_lo + kb * C::kABlockBytes + 32 * k),
+                              ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
+          ptx::umma_commit(empty);
+          if (++slot == kStages) { slot = 0; phase ^= 1; }
+        }
+        // plane 1: B_lo, used by A_hi
+        {
+          const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
+          ptx::mbar_wait(full, phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t b = b0 + slot * C::kStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
+                              ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
+          ptx::umma_commit(empty);
+          if (++slot == kStages) { slot = 0; phase ^= 1; }
+        }
       }
-      // plane 1: B_lo, used by A_hi
-      {
-        const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
-        ptx::mbar_wait(full, phase);
-        ptx::tc_fence_after_sync();
-        const uint32_t b = b0 + slot * C::kStageBytes;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
-                            ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
-        ptx::umma_commit(empty);
-        if (++slot == kStages) { slot = 0; phase ^= 1; }
-      }
+      ptx::umma_commit(bar_acc_full);
     }
-    ptx::umma_commit(bar_acc_full);
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // STRUCT >= 0: the single-formula kernel of that query structure; STRUCT < 0: the grouped
-// kernel, which looks its segment's structure up at run time (CTA-uniform).
+// kernel, which looks its tile's structure up at run time (CTA-uniform).  Persistent:
+// launched with min(n_tiles, SMs x CTAs/SM) CTAs.
 template <int D, int STRUCT>
 __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fused_tc(const __grid_constant__ LaunchParams p) {
   using C = Cfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + C::kOffCtl);
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  int si = 0;
-  if (STRUCT < 0) {
-    for (int i = 1; i < p.n_segs; ++i)
-      if ((int64_t)blockIdx.x >= p.seg[i].tile_begin) si = i;
-  }
-  const SegDev& s = p.seg[si];
-  const int structure = STRUCT >= 0 ? STRUCT : s.structure;
-  const int64_t tile_in_seg = (int64_t)blockIdx.x - s.tile_begin;
 
   if (wid == C::kWorkerWarps && lane == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -589,6 +769,10 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
     }
     ptx::mbar_init(ptx::smem_u32(&ctl->a_ready), C::kWorkerThreads);
     ptx::mbar_init(ptx::smem_u32(&ctl->acc_full), 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&ctl->sched_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ctl->sched_empty[i]), C::kWorkerThreads + 1);  // workers + MMA issuer
+    }
     ptx::fence_mbar_init();
   } else if (wid == C::kWorkerWarps + 1) {
     ptx::tmem_alloc(ptx::smem_u32(&ctl->tmem_base), C::kTmemCols);
@@ -599,12 +783,12 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
   ptx::tc_fence_after_sync();
 
   if (wid < C::kWorkerWarps) {
-    worker<D>(p, s, structure, tile_in_seg, smem, ctl);
+    worker<D, STRUCT>(p, smem, ctl);
   } else if (wid == C::kWorkerWarps) {
-    if (lane == 0) producer<D>(p, s, structure, smem, ctl);
+    if (lane == 0) producer<D, STRUCT>(p, smem, ctl);
     __syncwarp();
   } else {
-    if (lane == 0) mma_issuer<D>(p, structure, smem, ctl);
+    if (lane == 0) mma_issuer<D, STRUCT>(p, smem, ctl);
     __syncwarp();
   }
 

@@ -12,16 +12,23 @@ static int tc_current_device() {
   return dev & 63;
 }
 
+// Persistent launch: one CTA per SM slot (SMs x CTAs/SM), never more CTAs than tiles.
 template <int D, int STRUCT>
-static cudaError_t tc_launch_one(const LaunchParams& lp, int64_t grid, cudaStream_t st) {
+static cudaError_t tc_launch_one(const LaunchParams& lp, int64_t tiles, cudaStream_t st) {
   static bool configured[64] = {false};
+  static int slots[64] = {0};
   auto kern = tc::gqe_fused_tc<D, STRUCT>;
   const int dev = tc_current_device();
   if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<D>::kSmemBytes);
     if (e != cudaSuccess) return e;
+    int sms = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    slots[dev] = sms * tc::Cfg<D>::kCtasPerSm;
     configured[dev] = true;
   }
+  const int64_t grid = tiles < slots[dev] ? tiles : slots[dev];
   kern<<<(unsigned)grid, tc::Cfg<D>::kThreads, tc::Cfg<D>::kSmemBytes, st>>>(lp);
   return cudaGetLastError();
 }

@@ -129,6 +129,11 @@ int gqe_set_precision(gqe_ctx* ctx, int32_t precision);
 int gqe_get_precision(const gqe_ctx* ctx);
 /* Message of the last failure on ctx (ctx == NULL: last gqe_create failure). */
 const char* gqe_last_error(const gqe_ctx* ctx);
+/* Diagnostics: while `log` (DEVICE uint64 [n_tiles][32]) is set, thread 0 of every tile of the
+ * tensor-core kernel records (tag << 56 | SM clock) stamps at its phase boundaries
+ * (tags: 1+16*structure start, 2 gather done, 3 contraction done, 4 epilogue done,
+ * 5 transposed, 6 scored, 7 end); tools/phase_report.py decodes them.  NULL / 0 turns it off. */
+int gqe_debug_set_phase_log(gqe_ctx* ctx, uint64_t* log, int64_t n_tiles);
 /* Number of kernels this context has launched so far (bench bookkeeping). */
 int64_t gqe_launch_count(const gqe_ctx* ctx);
 
