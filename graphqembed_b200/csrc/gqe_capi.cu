@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,6 +48,10 @@ struct gqe_ctx {
   unsigned long long* phase_log = nullptr;
   int64_t phase_cap = 0;
 
+  // query embeddings of the many-targets-per-query path (fp32 [n_queries, d], grows on demand)
+  float* qbuf = nullptr;
+  size_t qbuf_cap = 0;
+
   // margin-loss reduction scratch
   double* partials = nullptr;
   int64_t partials_cap = 0;
@@ -77,6 +82,15 @@ static int fail(gqe_ctx* c, int code, const char* fmt, ...) {
     if (e_ != cudaSuccess)                                                                       \
       return fail((c), GQE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+// The runtime keeps ONE "last error"; a launcher that reads it would otherwise report an
+// error some earlier, unrelated call left behind.  Entry points drop (and, with
+// GQE_DEBUG_ERRORS set, name) such leftovers before they launch anything.
+static void drop_stale_error(const char* where) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess && getenv("GQE_DEBUG_ERRORS"))
+    fprintf(stderr, "[gqe] stale CUDA error seen at %s: %s\n", where, cudaGetErrorString(e));
+}
 
 static bool is_ipc_pointer(const void* p);  // defined with the IPC entry points below
 
@@ -128,6 +142,7 @@ extern "C" int gqe_create(int device, void* stream, gqe_ctx** out) {
   cudaMemset(c->loss_acc, 0, sizeof(double));
   cudaMemset(c->ticket, 0, sizeof(unsigned int));
   cudaMemset(c->tile_counter, 0, sizeof(unsigned int));
+  drop_stale_error("gqe_create (end)");
   *out = c;
   return GQE_OK;
 }
@@ -137,10 +152,12 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->partials);
   cudaFree(c->packed);
+  cudaFree(c->qbuf);
   cudaFree(c->loss_acc);
   cudaFree(c->ticket);
   cudaFree(c->tile_counter);
   for (void* p : c->stage) cudaFree(p);
+  drop_stale_error("gqe_destroy (end)");
   delete c;
 }
 
@@ -200,6 +217,7 @@ extern "C" int gqe_bind_tables(gqe_ctx* c, int32_t n_modes, const float* const* 
   c->table_rows.assign(rows, rows + n_modes);
   c->table_remote.swap(remote);
   c->d = d;
+  drop_stale_error("gqe_bind_tables (end)");
   return GQE_OK;
 }
 
@@ -306,6 +324,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
   if (target_offsets && n_segs != 1) return fail(c, GQE_ERR_INVALID, "ragged targets need a single formula");
   if (target_offsets && out_loss) return fail(c, GQE_ERR_INVALID, "margin loss needs the regular (pos,neg) layout");
   if (out_loss && T != 2) return fail(c, GQE_ERR_INVALID, "margin loss needs exactly 2 targets per query");
+  drop_stale_error("fused entry");
   if (!target_offsets && T <= 0 && nq_total > 0) return fail(c, GQE_ERR_INVALID, "targets per query must be positive");
   GQE_CUDA(c, cudaSetDevice(c->device));
 
@@ -339,8 +358,25 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
 
   // Bilinear d x d contractions go to the tensor cores (tcgen05, bf16x3 split) unless the
   // context asks for exact fp32; the ragged target layout stays on the fp32 kernels.
+  const bool ragged_chain = target_offsets != nullptr && segs[0].plan.structure <= GQE_CHAIN3;
   const bool use_tc = c->precision == GQE_PREC_BF16X3 && c->decoder == GQE_DEC_BILINEAR && tc_dim_supported(c->d) &&
-                      target_offsets == nullptr;
+                      !ragged_chain;
+  // More than (positive, negative) per query -- the evaluation shape (utils.py:70-91): the
+  // intersection structures build each query embedding once, leave it in HBM and a second,
+  // purely HBM-bound kernel scores every (query, target) pair against it.
+  const bool pairs_mode = (target_offsets != nullptr || T > 2) && out_scores != nullptr;
+  if (pairs_mode) {
+    const size_t need = (size_t)nq_total * c->d * sizeof(float);
+    if (c->qbuf_cap < need) {
+      GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->qbuf);
+      c->qbuf = nullptr;
+      c->qbuf_cap = 0;
+      GQE_CUDA(c, cudaMalloc(&c->qbuf, need + need / 4));
+      c->qbuf_cap = need + need / 4;
+    }
+    lp.q_out = c->qbuf;
+  }
   const int64_t tile_rows = use_tc ? kTcTileRows : kTileRows;
   if (use_tc) {
     const size_t need = (size_t)kMaxPack * tc_packed_bytes(c->d);
@@ -437,6 +473,29 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     } else {
       GQE_CUDA(c, launch_fused_simt(c->d, structure, lp, tiles, c->stream));
       c->launches += 1;
+    }
+    if (pairs_mode) {
+      PairParams qp;
+      std::memset(&qp, 0, sizeof qp);
+      int64_t n_p = 0;
+      for (int k = 0; k < n; ++k) {
+        if (lp.seg[k].structure <= GQE_CHAIN3) continue;  // chain tiles scored their own pairs
+        PairSeg& ps = qp.seg[qp.n_segs++];
+        ps.tgt_table = lp.seg[k].tgt_table;
+        ps.q_begin = lp.seg[k].q_begin;
+        ps.q_end = lp.seg[k].q_end;
+        n_p += target_offsets ? n_pairs : (ps.q_end - ps.q_begin) * T;
+      }
+      if (qp.n_segs > 0) {
+        qp.T = T;
+        qp.q = c->qbuf;
+        qp.target_rows = target_rows;
+        qp.target_offsets = target_offsets;
+        qp.n_pairs = n_pairs;
+        qp.out_scores = out_scores;
+        GQE_CUDA(c, launch_score_pairs(c->d, qp, n_p, c->stream));
+        c->launches += 1;
+      }
     }
   }
   return GQE_OK;
@@ -576,6 +635,7 @@ static int launch_op(gqe_ctx* c, int d, const OpParams& op) {
   if (op.n < 0) return fail(c, GQE_ERR_INVALID, "negative column count");
   GQE_CUDA(c, cudaSetDevice(c->device));
   if (!dim_supported(d)) return fail(c, GQE_ERR_UNSUPPORTED, "dimension %d not supported (32/64/128/256)", d);
+  drop_stale_error("operator entry");
   cudaError_t e = launch_op_simt(d, op, c->stream);
   if (e != cudaSuccess) return fail(c, GQE_ERR_CUDA, "operator launch failed: %s", cudaGetErrorString(e));
   c->launches += 1;

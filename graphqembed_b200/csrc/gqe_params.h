@@ -51,6 +51,10 @@ struct LaunchParams {
   double* partials;   // [gridDim.x]
   double* loss_acc;   // running sum across the launches of one call
   unsigned int* ticket;
+  // many targets per query (the eval shape): intersection tiles write their query
+  // embedding rows here (fp32 [n_queries_total, D]) instead of scoring; gqe_score_pairs
+  // then scores every (query, target) pair against them
+  float* q_out;
   // persistent tensor-core kernel: tiles of this launch and the dynamic tile counter
   int64_t n_tiles;
   unsigned int* tile_counter;
@@ -89,6 +93,22 @@ constexpr int kMaxPack = 5 * kMaxSegs;
 struct PackParams {
   PackEntry e[kMaxPack];
   uint8_t* dst;
+};
+
+// gqe_score_pairs: one formula segment's (query, target) pairs against stored query embeddings
+struct PairSeg {
+  const float* tgt_table;
+  int64_t q_begin, q_end;
+};
+struct PairParams {
+  PairSeg seg[kMaxSegs];
+  int32_t n_segs;
+  int32_t T;                      // regular layout: targets per query (offsets == null)
+  const float* q;                 // fp32 [n_queries_total, D] query embeddings
+  const int32_t* target_rows;
+  const int64_t* target_offsets;  // ragged layout (single segment) or null
+  int64_t n_pairs;                // ragged: total pairs
+  float* out_scores;
 };
 
 enum { OP_ENCODE = 0, OP_PROJECT = 1, OP_PATH_SCORE = 2, OP_INTERSECT = 3, OP_COSINE = 4 };

@@ -337,6 +337,13 @@ __device__ __forceinline__ void inter_tile(const LaunchParams& p, const SegDev& 
   if (deepsets) tile_matmul<D, true, EPI_NONE>(sm.A, sm.P, s.post);  // post.mm(combined) decoders.py:299
   if (structure == GQE_CHAIN_INTER3) tile_project<D>(sm.A, sm.P, s.rel[2], p.decoder);  // model.py:107
 
+  if (p.q_out) {  // many targets per query: hand the query embedding rows to gqe_score_pairs
+    for (int idx = threadIdx.x; idx < D * kTileRows; idx += kThreads) {
+      const int r = idx / D, k = idx % D;
+      if (r < n_valid) p.q_out[(size_t)(q0 + r) * D + k] = sm.A[k][r];
+    }
+    return;
+  }
   double local = 0.0;
 #pragma unroll 1
   for (int rr = 0; rr < kRowsPerWarp; ++rr) {

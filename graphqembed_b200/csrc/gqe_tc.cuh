@@ -388,11 +388,13 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       gsrc0 = __ldg(p.anchor_rows + row_begin + my_r);
       gsrc1 = __ldg(p.anchor_rows + p.anchor_stride + row_begin + my_r);
       if (n_branch > 2) gsrc2 = __ldg(p.anchor_rows + 2 * p.anchor_stride + row_begin + my_r);
-      ssrc0 = __ldg(p.target_rows + (row_begin + my_r) * T);
-      if (T > 1) ssrc1 = __ldg(p.target_rows + (row_begin + my_r) * T + 1);
+      if (!p.q_out) {
+        ssrc0 = __ldg(p.target_rows + (row_begin + my_r) * T);
+        if (T > 1) ssrc1 = __ldg(p.target_rows + (row_begin + my_r) * T + 1);
+      }
       if (!(rm & 2u)) ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
       if (n_branch > 2 && !(rm & 4u)) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
-      if (!(rm & 8u)) {
+      if (!(rm & 8u) && !p.q_out) {
         ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
         if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
       }
@@ -558,6 +560,16 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           for (int u = 0; u < SU; u += 2)
             if (arow[u + 1] >= 0) local += (double)hinge_(p.margin, sc[u], sc[u + 1]);
         }
+      }
+    } else if (p.q_out) {
+      // many targets per query: hand the query embedding rows to gqe_score_pairs
+#pragma unroll 1
+      for (int u = 0; u < RPW; ++u) {
+        const int r = wid * RPW + u;
+        if (r >= n_valid) break;  // warp-uniform
+        float4* dst = reinterpret_cast<float4*>(p.q_out + (size_t)(row_begin + r) * D);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) dst[lane + 32 * j] = *q_chunk<D>(qsm, r, lane + 32 * j);
       }
     } else {
       constexpr int SU = 4 / NV;

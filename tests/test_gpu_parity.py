@@ -222,7 +222,9 @@ def test_host_buffer_entry_points_match_device_ones(small):
         offsets = np.arange(batch.n_queries + 1, dtype=np.int64) * 2
         out2 = np.empty(batch.n_pairs, dtype=np.float32)
         ctx.score_host(plan, a, t, offsets, out2)
-        np.testing.assert_array_equal(out2, dev)
+        # ragged intersections go through the pair-scoring kernel (different fp32 summation
+        # order than the fused epilogue): equal to rounding, not to the bit
+        np.testing.assert_allclose(out2, dev, rtol=0, atol=2e-6)
 
 
 # ---------------------------------------------------------------------------
