@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--tables", choices=("replicated", "p2p", "staged"), default=None,
                     help="table placement (default: replicated; p2p for the 10M-node workload at N>1)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded 10M-node leg at N>1")
+    ap.add_argument("--no-eval-shape", action="store_true", help="skip the 1 query x 101 targets leg at N=1")
     ap.add_argument("--with-sharded", action="store_true", help="also run the 10M-node workload at N=1")
     ap.add_argument("--sharded-formulas", type=int, default=4, help="formulas per structure of the 10M-node leg")
     return ap.parse_args()
@@ -324,6 +325,64 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
     return res
 
 
+def measure_eval_shape(args, tm, local_rank, n_queries=8192, n_neg=100, d=256):
+    """Scores only (no loss): every query of an intersection mix against 1 + n_neg targets."""
+    import numpy as np
+    import torch
+
+    import graphqembed_b200 as gqe
+    from graphqembed_b200 import _lib
+    from graphqembed_b200.lowering import lower_formula
+    from graphqembed_b200.query import Formula
+    from graphqembed_b200.synth import bio_shaped
+    from graphqembed_b200.workloads import Workload
+
+    device, stream = tm.device, tm.stream
+    kg = bio_shaped(seed=0)
+    rng = np.random.RandomState(4242)
+    T = n_neg + 1
+    structures = ("2-inter", "3-inter", "3-inter_chain")
+    wl = Workload("eval", kg, d, "bilinear", "mean", [])
+    tables, rels, pre, post = device_parameters(wl, torch, device, seed=1234)
+    lookup = gqe.RowLookup(kg.node_ids)
+    mode_ids = {m: i for i, m in enumerate(kg.modes)}
+    rel_ids = {r: i for i, r in enumerate(kg.rel_keys)}
+    per = n_queries // len(structures)
+    anchor_rows = np.zeros((_lib.GQE_MAX_ANCHORS, per * len(structures)), dtype=np.int32)
+    target_rows = np.empty((per * len(structures), T), dtype=np.int32)
+    items, n_rows = [], 0
+    for i, s in enumerate(structures):
+        f = Formula(s, kg.sample_rels(s, rng))
+        b = kg.sample_batch(s, f.rels, per, n_neg, rng)
+        q0 = i * per
+        for k, mode in enumerate(f.anchor_modes):
+            anchor_rows[k, q0:q0 + per] = lookup.rows(b["anchors"][k], mode)
+        target_rows[q0:q0 + per, 0] = lookup.rows(b["target"], f.target_mode)
+        target_rows[q0:q0 + per, 1:] = lookup.rows(b["negs"], f.target_mode)
+        items.append((lower_formula(f, mode_ids, rel_ids), q0, q0 + per))
+        n_rows += per * (len(f.anchor_modes) + T)
+    nq = per * len(structures)
+    segs = _lib.make_segments(items)
+    ctx = gqe.Context(local_rank, stream.cuda_stream)
+    ctx.bind_tables([t.data_ptr() for t in tables], [t.size(0) for t in tables], d)
+    ctx.bind_relations(_lib.DECODER_ID["bilinear"], [r.data_ptr() for r in rels], d)
+    ctx.bind_intersection(_lib.INTER_ID["mean"], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], d)
+    d_anchor = torch.from_numpy(anchor_rows).to(device)
+    d_targets = torch.from_numpy(target_rows).to(device)
+    d_scores = torch.empty(nq * T, dtype=torch.float32, device=device)
+
+    def step():
+        ctx.score_grouped_device(segs, nq, d_anchor.data_ptr(), d_targets.data_ptr(), T, d_scores.data_ptr(), 1.0, None)
+
+    l0 = ctx.launch_count()
+    step()
+    launches = ctx.launch_count() - l0
+    ms = tm.device_ms(step, max(10, args.steps // 4), 3)
+    assert bool(torch.isfinite(d_scores).all())
+    return {"ms": ms, "nq": nq, "T": T, "pairs": nq * T, "d": d, "launches": int(launches),
+            "bytes": int(n_rows * (4 * d + 4) + nq * T * 4)}
+
+
 def roofline_of(wl, name, ms_per_step, pk, world=1):
     """Roofline of the fused kernel for one step of `wl` on one GPU."""
     bytes_alg, flops_alg = wl.algorithmic_bytes(), wl.algorithmic_flops()
@@ -402,6 +461,11 @@ def run_native(args):
             extra[mode] = r
             torch.cuda.empty_cache()
 
+    # the evaluation shape (utils.py:70-91): one query against its positive + 100 negatives
+    eval_res = None
+    if world == 1 and not args.no_eval_shape:
+        eval_res = measure_eval_shape(args, tm, local_rank)
+
     line = None
     if rank == 0:
         pk = peaks()
@@ -440,6 +504,17 @@ def run_native(args):
                            "achieved_gbs_in": round(nv_bytes / sec / 1e9, 2), "peak_gbs": NVLINK_PEER_GBS,
                            "frac": round(nv_bytes / sec / 1e9 / NVLINK_PEER_GBS, 4),
                            "note": "inbound row bytes of rank 0 / step time vs the measured peer-copy bandwidth"}}
+        if eval_res is not None:
+            sec = eval_res["ms"] * 1e-3
+            line["eval_shape"] = {
+                "workload": "Bio KG 2/3-inter + 3-inter_chain, d=%d, %d queries x (1 positive + %d negatives)" % (
+                    eval_res["d"], eval_res["nq"], eval_res["T"] - 1),
+                "pairs_per_s": round(eval_res["pairs"] / sec, 1), "queries_per_s": round(eval_res["nq"] / sec, 1),
+                "ms_per_step": round(eval_res["ms"], 5), "gpu_launches_per_step": eval_res["launches"],
+                "hbm": {"algorithmic_bytes": eval_res["bytes"], "achieved_gbs": round(eval_res["bytes"] / sec / 1e9, 2),
+                        "frac": round(eval_res["bytes"] / sec / 1e9 / pk["hbm_gbs"], 4),
+                        "note": "gather-bound: one table row per (query, target) pair; Bio-size tables are "
+                                "L2-resident after first touch, so this can exceed the DRAM roofline"}}
         if world == 1 and not args.no_cpu_baseline:
             tables, rels, pre, post = res["params"]
             line["cpu_baseline"] = cpu_reference(args, name, tables=[t.cpu() for t in tables],

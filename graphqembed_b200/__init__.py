@@ -17,13 +17,14 @@ __all__ = ["Context", "GqeError", "Plan", "Segment", "build", "load", "make_segm
            "relation_order", "Formula", "Query", "QueryBatch", "reverse_relation", "DirectEncoder",
            "BilinearMetapathDecoder", "TransEMetapathDecoder", "BilinearDiagMetapathDecoder", "SetIntersection",
            "SimpleSetIntersection", "QueryEncoderDecoder", "get_encoder", "get_metapath_decoder",
-           "get_intersection_decoder"]
+           "get_intersection_decoder", "eval_auc_queries", "eval_perc_queries"]
 
 _TORCH_SIDE = {
     "DirectEncoder": "operators", "BilinearMetapathDecoder": "operators", "TransEMetapathDecoder": "operators",
     "BilinearDiagMetapathDecoder": "operators", "SetIntersection": "operators", "SimpleSetIntersection": "operators",
     "get_encoder": "operators", "get_metapath_decoder": "operators", "get_intersection_decoder": "operators",
     "cosine_similarity_dim0": "operators", "QueryEncoderDecoder": "scorer",
+    "eval_auc_queries": "evaluation", "eval_perc_queries": "evaluation",
 }
 
 

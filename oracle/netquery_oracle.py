@@ -280,3 +280,49 @@ def eval_pairs(formula_queries, offset, batch_size, hard_negatives, one_negative
         negatives = [n for q in batch for n in pick(q)]
     rep = [q for i, q in enumerate(batch) for _ in range(lengths[i])]
     return batch + rep, [q.target_node for q in batch] + negatives, lengths
+
+
+def get_perc_scores(scores, lengths):
+    """utils.py:26-33: percentile of each positive among its own negatives."""
+    from scipy import stats
+    out, cum = [], 0
+    neg_scores = scores[len(lengths):]
+    for i, length in enumerate(lengths):
+        out.append(stats.percentileofscore(neg_scores[cum:cum + length], scores[i]))
+        cum += length
+    return out
+
+
+def eval_auc_queries(test_queries, enc_dec, batch_size=1000, hard_negatives=False, seed=0):
+    """utils.py:35-68, through ``enc_dec.forward`` with the repeated query list."""
+    import numpy as np
+    from sklearn.metrics import roc_auc_score
+    predictions, labels, formula_aucs = [], [], {}
+    random.seed(seed)
+    for formula in test_queries:
+        f_labels, f_pred = [], []
+        formula_queries = test_queries[formula]
+        offset = 0
+        while offset < len(formula_queries):
+            qs, targets, lengths = eval_pairs(formula_queries, offset, batch_size, hard_negatives, True)
+            offset += batch_size
+            f_labels.extend([1] * len(lengths) + [0] * len(lengths))
+            f_pred.extend(enc_dec.forward(formula, qs, targets).data.tolist())
+        formula_aucs[formula] = roc_auc_score(f_labels, np.nan_to_num(f_pred))
+        labels.extend(f_labels)
+        predictions.extend(f_pred)
+    return roc_auc_score(labels, np.nan_to_num(predictions)), formula_aucs
+
+
+def eval_perc_queries(test_queries, enc_dec, batch_size=1000, hard_negatives=False):
+    """utils.py:70-91."""
+    import numpy as np
+    perc = []
+    for formula in test_queries:
+        formula_queries = test_queries[formula]
+        offset = 0
+        while offset < len(formula_queries):
+            qs, targets, lengths = eval_pairs(formula_queries, offset, batch_size, hard_negatives, False)
+            offset += batch_size
+            perc.extend(get_perc_scores(enc_dec.forward(formula, qs, targets).data.tolist(), lengths))
+    return np.mean(perc)

@@ -134,3 +134,20 @@ def build_reference_model(tables, node_maps, relations, rel_params, decoder, int
             idec.post_mats[m].data.copy_(post[m])
     model = M.QueryEncoderDecoder(GraphLike(full_lists), enc, dec, idec)
     return model, g
+
+
+def reference_eval_functions():
+    """``eval_auc_queries`` / ``eval_perc_queries`` / ``_get_perc_scores`` of the reference,
+    executed from its own source: netquery/utils.py cannot be imported under py3 (``cPickle``,
+    utils.py:9), so lines 26-91 are exec'd verbatim in a namespace that supplies the names the
+    module header would have imported (and py2's ``xrange``)."""
+    import random as _random
+
+    import numpy as _np
+    from scipy import stats as _stats
+    from sklearn.metrics import roc_auc_score as _auc
+    src = open(os.path.join(REFERENCE_ROOT, "netquery", "utils.py")).read().split("\n")
+    body = "\n".join(src[25:91])
+    ns = {"np": _np, "stats": _stats, "roc_auc_score": _auc, "random": _random, "xrange": range}
+    exec(compile(body, "netquery/utils.py[26:91]", "exec"), ns)
+    return ns["eval_auc_queries"], ns["eval_perc_queries"]

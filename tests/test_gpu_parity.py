@@ -359,3 +359,33 @@ def test_identity_relation_self_match_scores_one():
     b = case.batches["1-chain"]
     batch = gqe.QueryBatch(case.formula("1-chain", cls=gqe.Formula), b["target"][None, :], b["target"])
     np.testing.assert_allclose(_np(model.score_batch(batch)), 1.0, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("d,inter", [(64, "min"), (128, "mean"), (256, "mean-simple")])
+def test_eval_auc_and_percentile_match_the_oracle(d, inter):
+    """evaluation.eval_auc_queries / eval_perc_queries (utils.py:35-91) on the GPU vs the
+    oracle's restatement on the CPU: same negative draws, ranks computed from scores that
+    agree to ~1e-6, so the metrics agree unless two scores are closer than that."""
+    import random
+    from oracle import netquery_oracle as O
+    case = make_case(seed=77 + d, d=d, decoder="bilinear", inter=inter, n_queries=150, n_neg=7, nodes_per_mode=400)
+    model = build_package_model(case)
+    orc = case.oracle()
+    structures = ("1-chain", "3-chain", "2-inter", "3-inter", "3-chain_inter")
+    # ragged negative lists: query i keeps 1 + i % 7 of its negatives
+    def queries(cls, s):
+        qs = case.queries(s, cls=cls)
+        for i, q in enumerate(qs):
+            q.neg_samples = q.neg_samples[:1 + i % 7]
+            q.hard_neg_samples = q.hard_neg_samples[:1 + (i + 3) % 7]
+        return qs
+    tq_gpu = {case.formula(s, cls=gqe.Formula): queries(gqe.Query, s) for s in structures}
+    tq_orc = {case.formula(s): queries(O.Query, s) for s in structures}
+    for hard in (False, True):
+        auc, fauc = gqe.eval_auc_queries(tq_gpu, model, batch_size=64, hard_negatives=hard, seed=5)
+        want, fwant = O.eval_auc_queries(tq_orc, orc, batch_size=64, hard_negatives=hard, seed=5)
+        assert abs(auc - want) < 2e-3
+        for fg, fo in zip(tq_gpu, tq_orc):
+            assert abs(fauc[fg] - fwant[fo]) < 5e-3
+        perc = gqe.eval_perc_queries(tq_gpu, model, batch_size=64, hard_negatives=hard)
+        assert abs(perc - O.eval_perc_queries(tq_orc, orc, batch_size=64, hard_negatives=hard)) < 0.2

@@ -122,3 +122,27 @@ def test_synthetic_graph_is_closed_under_reversal():
             rels = kg.sample_rels(s, rng)
             for r in gqe.relation_order(gqe.Formula(s, rels)):
                 assert r in keys
+
+
+def test_eval_batch_layout_is_positive_then_negatives_per_query():
+    """evaluation._batch_arrays: one flat ragged batch per eval batch (utils.py:78-88 without
+    the K-fold repetition of the query objects)."""
+    from graphqembed_b200.evaluation import _batch_arrays
+    import graphqembed_b200 as gqe
+
+    class Q(object):
+        def __init__(self, t, a):
+            self.target_node, self.anchor_nodes = t, a
+    f = gqe.Formula("2-inter", (("a", "r0", "b"), ("a", "r1", "c")))
+    qs = [Q(10, (1, 2)), Q(11, (3, 4)), Q(12, (5, 6))]
+    batch, offsets = _batch_arrays(f, qs, [100, 101, 200, 300, 301, 302], [2, 1, 3])
+    assert offsets.tolist() == [0, 3, 5, 9]
+    assert batch.targets.tolist() == [10, 100, 101, 11, 200, 12, 300, 301, 302]
+    assert batch.anchors.tolist() == [[1, 3, 5], [2, 4, 6]]
+    assert batch.offsets.tolist() == offsets.tolist()
+    # equal lengths -> the regular layout (no offsets), which the tensor-core path takes
+    batch, offsets = _batch_arrays(f, qs, [100, 200, 300], [1, 1, 1])
+    assert batch.offsets is None and batch.targets.tolist() == [10, 100, 11, 200, 12, 300]
+    # a query without negatives keeps its positive
+    batch, offsets = _batch_arrays(f, qs, [100], [0, 1, 0])
+    assert batch.targets.tolist() == [10, 11, 100, 12] and offsets.tolist() == [0, 1, 3, 4]

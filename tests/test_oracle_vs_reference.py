@@ -67,3 +67,26 @@ def test_unknown_query_type_returns_none_like_reference():
     of = case.formula("2-chain")
     of.query_type = "4-chain"
     assert case.oracle().forward(of, [], []) is None
+
+
+def test_eval_restatement_matches_reference_eval_functions():
+    """oracle eval_auc_queries / eval_perc_queries vs the reference's own utils.py:26-91
+    (exec'd from source), each driving its own model on the same queries."""
+    from oracle import netquery_oracle as O
+    g = ref_shim.load()[0]
+    ref_auc, ref_perc = ref_shim.reference_eval_functions()
+    case = make_case(seed=11, d=32, decoder="bilinear", inter="mean", n_queries=57, n_neg=6)
+    ref, _ = ref_shim.build_reference_model(case.tables, case.kg.node_maps(), case.kg.relations, case.rel_params,
+                                            "bilinear", "mean", case.pre, case.post, full_lists=case.kg.full_lists())
+    orc = case.oracle()
+    structures = ("2-chain", "2-inter", "3-inter_chain")
+    tq_ref = {case.formula(s, cls=g.Formula): case.queries(s, cls=g.Query) for s in structures}
+    tq_orc = {case.formula(s): case.queries(s) for s in structures}
+    with torch.no_grad():
+        for hard in (False, True):
+            a, fa = ref_auc(tq_ref, ref, batch_size=20, hard_negatives=hard, seed=3)
+            b, fb = O.eval_auc_queries(tq_orc, orc, batch_size=20, hard_negatives=hard, seed=3)
+            assert a == b
+            assert [fa[f] for f in tq_ref] == [fb[f] for f in tq_orc]
+            assert ref_perc(tq_ref, ref, batch_size=20, hard_negatives=hard) == \
+                O.eval_perc_queries(tq_orc, orc, batch_size=20, hard_negatives=hard)
