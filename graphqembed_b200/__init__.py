@@ -17,7 +17,8 @@ __all__ = ["Context", "GqeError", "Plan", "Segment", "build", "load", "make_segm
            "relation_order", "Formula", "Query", "QueryBatch", "reverse_relation", "DirectEncoder",
            "BilinearMetapathDecoder", "TransEMetapathDecoder", "BilinearDiagMetapathDecoder", "SetIntersection",
            "SimpleSetIntersection", "QueryEncoderDecoder", "get_encoder", "get_metapath_decoder",
-           "get_intersection_decoder", "eval_auc_queries", "eval_perc_queries"]
+           "get_intersection_decoder", "eval_auc_queries", "eval_perc_queries", "load_graph", "load_queries",
+           "load_queries_by_formula", "load_queries_by_type", "load_test_queries_by_formula", "run_batch", "pick_batch"]
 
 _TORCH_SIDE = {
     "DirectEncoder": "operators", "BilinearMetapathDecoder": "operators", "TransEMetapathDecoder": "operators",
@@ -25,6 +26,8 @@ _TORCH_SIDE = {
     "get_encoder": "operators", "get_metapath_decoder": "operators", "get_intersection_decoder": "operators",
     "cosine_similarity_dim0": "operators", "QueryEncoderDecoder": "scorer",
     "eval_auc_queries": "evaluation", "eval_perc_queries": "evaluation",
+    "load_graph": "data", "load_queries": "data", "load_queries_by_formula": "data", "load_queries_by_type": "data",
+    "load_test_queries_by_formula": "data", "run_batch": "data", "pick_batch": "data",
 }
 
 

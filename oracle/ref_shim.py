@@ -151,3 +151,14 @@ def reference_eval_functions():
     ns = {"np": _np, "stats": _stats, "roc_auc_score": _auc, "random": _random, "xrange": range}
     exec(compile(body, "netquery/utils.py[26:91]", "exec"), ns)
     return ns["eval_auc_queries"], ns["eval_perc_queries"]
+
+
+def reference_run_batch():
+    """``run_batch`` of the reference (netquery/train_helpers.py:95-107) executed from its own
+    source.  The module cannot be imported under py3 (implicit relative import, ``xrange``), and
+    line 100 indexes ``dict.keys()`` -- callers pass a dict whose ``keys()`` returns a list."""
+    import numpy as _np
+    src = open(os.path.join(REFERENCE_ROOT, "netquery", "train_helpers.py")).read().split("\n")
+    ns = {"np": _np}
+    exec(compile("\n".join(src[94:107]), "netquery/train_helpers.py[95:107]", "exec"), ns)
+    return ns["run_batch"]
