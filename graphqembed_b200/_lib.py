@@ -34,6 +34,7 @@ STRUCTURE_ID = {"1-chain": 0, "2-chain": 1, "3-chain": 2, "2-inter": 3, "3-inter
 DECODER_ID = {"bilinear": 0, "transe": 1, "bilinear-diag": 2}
 INTER_ID = {"mean": 0, "min": 1, "mean-simple": 2, "min-simple": 3}
 PRECISION_ID = {"bf16x3": 0, "fp32": 1}
+COMPOSE_ID = {"off": 0, "auto": 1, "always": 2}
 ABI_VERSION = 3
 
 
@@ -65,6 +66,7 @@ _SIGNATURES = {
     "gqe_set_stream": (C.c_int, [_P, _P]),
     "gqe_set_precision": (C.c_int, [_P, C.c_int32]),
     "gqe_get_precision": (C.c_int, [_P]),
+    "gqe_set_compose": (C.c_int, [_P, C.c_int32]),
     "gqe_last_error": (C.c_char_p, [_P]),
     "gqe_launch_count": (C.c_int64, [_P]),
     "gqe_debug_set_phase_log": (C.c_int, [_P, _P, C.c_int64]),
@@ -203,6 +205,10 @@ class Context(object):
     def get_precision(self):
         code = int(self._lib.gqe_get_precision(self._h))
         return [k for k, v in PRECISION_ID.items() if v == code][0]
+
+    def set_compose(self, mode):
+        """Operator pre-composition on the tensor-core path: "off", "auto" (default), "always"."""
+        self._check(self._lib.gqe_set_compose(self._h, COMPOSE_ID[mode]))
 
     def launch_count(self):
         return int(self._lib.gqe_launch_count(self._h))

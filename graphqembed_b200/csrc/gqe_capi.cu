@@ -48,6 +48,11 @@ struct gqe_ctx {
   unsigned long long* phase_log = nullptr;
   int64_t phase_cap = 0;
 
+  // operator pre-composition on the tensor-core path (gqe_compose_mode) and its fp32 scratch
+  int compose = GQE_COMPOSE_AUTO;
+  float* compose_buf = nullptr;
+  size_t compose_cap = 0;
+
   // query embeddings of the many-targets-per-query path (fp32 [n_queries, d], grows on demand)
   float* qbuf = nullptr;
   size_t qbuf_cap = 0;
@@ -153,6 +158,7 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   cudaFree(c->partials);
   cudaFree(c->packed);
   cudaFree(c->qbuf);
+  cudaFree(c->compose_buf);
   cudaFree(c->loss_acc);
   cudaFree(c->ticket);
   cudaFree(c->tile_counter);
@@ -175,6 +181,14 @@ extern "C" int gqe_set_precision(gqe_ctx* c, int32_t precision) {
   return GQE_OK;
 }
 extern "C" int gqe_get_precision(const gqe_ctx* c) { return c ? c->precision : GQE_ERR_INVALID; }
+
+extern "C" int gqe_set_compose(gqe_ctx* c, int32_t mode) {
+  if (!c) return GQE_ERR_INVALID;
+  if (mode < GQE_COMPOSE_OFF || mode > GQE_COMPOSE_ALWAYS)
+    return fail(c, GQE_ERR_INVALID, "gqe_set_compose: unknown mode %d", mode);
+  c->compose = mode;
+  return GQE_OK;
+}
 
 extern "C" int gqe_debug_set_phase_log(gqe_ctx* c, uint64_t* log, int64_t n_tiles) {
   if (!c) return GQE_ERR_INVALID;
@@ -378,6 +392,17 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     lp.q_out = c->qbuf;
   }
   const int64_t tile_rows = use_tc ? kTcTileRows : kTileRows;
+  if (use_tc && c->compose != GQE_COMPOSE_OFF) {
+    const size_t need = (size_t)kMaxCompose * c->d * c->d * sizeof(float);
+    if (c->compose_cap < need) {
+      GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->compose_buf);
+      c->compose_buf = nullptr;
+      c->compose_cap = 0;
+      GQE_CUDA(c, cudaMalloc(&c->compose_buf, need));
+      c->compose_cap = need;
+    }
+  }
   if (use_tc) {
     const size_t need = (size_t)kMaxPack * tc_packed_bytes(c->d);
     if (c->packed_cap < need) {
@@ -409,6 +434,20 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       }
       return reinterpret_cast<const float*>(c->packed + (size_t)k * tc_packed_bytes(c->d));
     };
+    // fp32 products of runs of linear operators (deduplicated per launch); a 3-factor run
+    // takes two dependent waves: t = a.b, then t.c or c.t
+    ComposeParams cw[2];
+    int n_cw[2] = {0, 0};
+    auto product = [&](const float* a, const float* b, int wave) -> const float* {
+      for (int k = 0; k < n_cw[wave]; ++k)
+        if (cw[wave].e[k].a == a && cw[wave].e[k].b == b) return cw[wave].e[k].dst;
+      ComposeEntry& e = cw[wave].e[n_cw[wave]];
+      e.a = a;
+      e.b = b;
+      e.dst = c->compose_buf + (size_t)(wave * (kMaxCompose / 2) + n_cw[wave]) * c->d * c->d;
+      ++n_cw[wave];
+      return e.dst;
+    };
     int first_structure = -1;
     bool uniform = true;
     while (i < n_segs && n < kMaxSegs) {
@@ -427,10 +466,45 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       const int64_t rows = g.plan.structure <= GQE_CHAIN3 ? (target_offsets ? n_pairs : nq * T) : nq;
       tiles += (rows + tile_rows - 1) / tile_rows;
       if (use_tc) {
-        const int chain_form = g.plan.structure <= GQE_CHAIN3 ? 1 : 0;
-        for (int k = 0; k < n_rels_of(g.plan.structure); ++k) s->rel[k] = packed_of(s->rel[k], chain_form);
-        if (s->pre) s->pre = packed_of(s->pre, 0);
-        if (s->post) s->post = packed_of(s->post, 0);
+        const int st = g.plan.structure;
+        const int chain_form = st <= GQE_CHAIN3 ? 1 : 0;
+        // composing pays off once a few tiles share the product (d^3 fp32 FMAs per product)
+        const bool compose = c->compose == GQE_COMPOSE_ALWAYS || (c->compose == GQE_COMPOSE_AUTO && rows >= 8 * kTcTileRows);
+        const bool ds = s->pre != nullptr;
+        if (!compose || st == GQE_CHAIN1 || (!ds && st != GQE_INTER_CHAIN3)) {
+          // nothing to merge: one contraction per operator, as written in the reference
+          for (int k = 0; k < n_rels_of(st); ++k) s->rel[k] = packed_of(s->rel[k], chain_form);
+          if (s->pre) s->pre = packed_of(s->pre, 0);
+          if (s->post) s->post = packed_of(s->post, 0);
+        } else {
+          s->composed = 1;
+          const float *r0 = s->rel[0], *r1 = s->rel[1], *r2 = s->rel[2], *pre = s->pre, *post = s->post;
+          s->rel[0] = s->rel[1] = s->rel[2] = s->pre = s->post = nullptr;
+          if (st <= GQE_CHAIN3) {                       // act.mm(M1).mm(M2)[.mm(M3)]  (decoders.py:143-145)
+            const float* w = product(r0, r1, 0);
+            if (st == GQE_CHAIN3) w = product(w, r2, 1);
+            s->rel[0] = packed_of(w, 1);
+          } else if (st == GQE_INTER2 || st == GQE_INTER3) {   // relu(pre.mm(R_b.mm(e)))  (decoders.py:289-292)
+            s->rel[0] = packed_of(product(pre, r0, 0), 0);
+            s->rel[1] = packed_of(product(pre, r1, 0), 0);
+            if (st == GQE_INTER3) s->rel[2] = packed_of(product(pre, r2, 0), 0);
+            s->post = packed_of(post, 0);
+          } else if (st == GQE_INTER_CHAIN3) {          // branch 1: R2a.mm(R2b.mm(e))  (model.py:84-86)
+            const float* t = product(r2, r1, 0);
+            if (ds) {
+              s->rel[0] = packed_of(product(pre, r0, 0), 0);
+              s->rel[1] = packed_of(product(pre, t, 1), 0);
+              s->post = packed_of(post, 0);
+            } else {
+              s->rel[0] = packed_of(r0, 0);
+              s->rel[1] = packed_of(t, 0);
+            }
+          } else {                                      // 3-chain_inter (DeepSets): R1.mm(post.mm(.))  (model.py:106-107)
+            s->rel[0] = packed_of(product(pre, r0, 0), 0);
+            s->rel[1] = packed_of(product(pre, r1, 0), 0);
+            s->post = packed_of(product(r2, post, 0), 0);
+          }
+        }
       }
       if (first_structure < 0) first_structure = g.plan.structure;
       else if (first_structure != g.plan.structure) uniform = false;
@@ -466,6 +540,11 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     // single formula -> that structure's own kernel; otherwise the grouped kernel
     const int structure = (n == 1 && uniform) ? first_structure : -1;
     if (use_tc) {
+      for (int w = 0; w < 2; ++w) {
+        if (n_cw[w] == 0) continue;
+        GQE_CUDA(c, launch_compose(c->d, cw[w], n_cw[w], c->stream));
+        c->launches += 1;
+      }
       pp.dst = c->packed;
       GQE_CUDA(c, launch_pack(c->d, pp, n_pack, c->stream));
       GQE_CUDA(c, launch_fused_tc(c->d, structure, lp, tiles, c->stream));

@@ -1,0 +1,116 @@
+// gqe_compose.cu -- products of the (tiny) operator matrices of a formula.
+//
+// Consecutive linear operators of a query structure (relation projections, DeepSets pre /
+// post; reference netquery/decoders.py:145,150,289,299) are multiplied together ONCE per
+// call so that the fused tensor-core kernel runs one contraction per run instead of one per
+// operator.  A product is d x d x d (d = 128 / 256): far too small for the tcgen05 pipeline of
+// the fused kernel to pay off, and latency-bound on the CUDA cores (17 us per 64x64 tile with
+// FFMA), so it runs on the warp-level tensor-core path (wmma, bf16 operands, fp32 accumulate)
+// with the same hi/lo split as the fused kernel: c = a_hi b_hi + a_lo b_hi + a_hi b_lo,
+// ~2^-17 relative.  One CTA = one 64x64 tile of one product; the whole K extent of both
+// operands is fetched in one round of loads; a launch computes up to 64 independent products.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <mma.h>
+#include <stdint.h>
+
+#include "gqe_launch.h"
+
+namespace gqe {
+
+template <int D>
+struct ComposeSmem {
+  __nv_bfloat16 a_hi[64][D + 8], a_lo[64][D + 8];   // a[i0 .. i0+64)[0 .. D)
+  __nv_bfloat16 b_hi[D][64 + 8], b_lo[D][64 + 8];   // b[0 .. D)[j0 .. j0+64)
+};
+
+__device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* lo, const float4 v) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+  const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+  reinterpret_cast<__nv_bfloat162*>(hi)[0] = h0;
+  reinterpret_cast<__nv_bfloat162*>(hi)[1] = h1;
+  reinterpret_cast<__nv_bfloat162*>(lo)[0] = l0;
+  reinterpret_cast<__nv_bfloat162*>(lo)[1] = l1;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) gqe_compose(const __grid_constant__ ComposeParams p) {
+  using namespace nvcuda;
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  ComposeSmem<D>& sm = *reinterpret_cast<ComposeSmem<D>*>(smem_raw);
+  const ComposeEntry& e = p.e[blockIdx.z];
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  // every load of the tile is issued before the first shared store (8 x 128 bits per
+  // operand per thread at a time), so the CTA pays ~one memory latency per half
+  constexpr int NA = 64 * D / 4 / 256;   // float4 per thread per operand (16 at d = 256)
+  static_assert(NA % 8 == 0, "tile loads");
+#pragma unroll 1
+  for (int it0 = 0; it0 < NA; it0 += 8) {
+    float4 va[8], vb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = threadIdx.x + (it0 + u) * 256;
+      va[u] = __ldg(reinterpret_cast<const float4*>(e.a + (size_t)(i0 + idx / (D / 4)) * D) + idx % (D / 4));
+      vb[u] = __ldg(reinterpret_cast<const float4*>(e.b + (size_t)(idx / 16) * D + j0) + idx % 16);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = threadIdx.x + (it0 + u) * 256;
+      split_store4(&sm.a_hi[idx / (D / 4)][4 * (idx % (D / 4))], &sm.a_lo[idx / (D / 4)][4 * (idx % (D / 4))], va[u]);
+      split_store4(&sm.b_hi[idx / 16][4 * (idx % 16)], &sm.b_lo[idx / 16][4 * (idx % 16)], vb[u]);
+    }
+  }
+  __syncthreads();
+  // warp w: rows 16 (w / 2) .. +16, columns 32 (w % 2) .. +32  (two 16x16 accumulators)
+  const int w = threadIdx.x >> 5;
+  const int r0 = 16 * (w >> 1), c0 = 32 * (w & 1);
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2];
+  wmma::fill_fragment(acc[0], 0.f);
+  wmma::fill_fragment(acc[1], 0.f);
+#pragma unroll 2
+  for (int k = 0; k < D; k += 16) {
+    wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> ah, al;
+    wmma::load_matrix_sync(ah, &sm.a_hi[r0][k], D + 8);
+    wmma::load_matrix_sync(al, &sm.a_lo[r0][k], D + 8);
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bh, bl;
+      wmma::load_matrix_sync(bh, &sm.b_hi[k][c0 + 16 * n], 64 + 8);
+      wmma::load_matrix_sync(bl, &sm.b_lo[k][c0 + 16 * n], 64 + 8);
+      wmma::mma_sync(acc[n], ah, bh, acc[n]);
+      wmma::mma_sync(acc[n], al, bh, acc[n]);
+      wmma::mma_sync(acc[n], ah, bl, acc[n]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+    wmma::store_matrix_sync(e.dst + (size_t)(i0 + r0) * D + j0 + c0 + 16 * n, acc[n], D, wmma::mem_row_major);
+}
+
+template <int D>
+static cudaError_t launch_compose_t(const ComposeParams& cp, int n_entries, cudaStream_t st) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gqe_compose<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ComposeSmem<D>));
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  const dim3 grid(D / 64, D / 64, (unsigned)n_entries);
+  gqe_compose<D><<<grid, 256, sizeof(ComposeSmem<D>), st>>>(cp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compose(int d, const ComposeParams& cp, int n_entries, cudaStream_t st) {
+  if (n_entries <= 0) return cudaSuccess;
+  switch (d) {
+    case 128: return launch_compose_t<128>(cp, n_entries, st);
+    case 256: return launch_compose_t<256>(cp, n_entries, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace gqe

@@ -28,6 +28,9 @@ cudaError_t launch_gather_rows(const float* table, const int32_t* rows, int64_t 
 // (query, target) pair scoring against stored query embeddings (gqe_pairs.cu)
 cudaError_t launch_score_pairs(int d, const PairParams& pp, int64_t n_pairs_total, cudaStream_t st);
 
+// fp32 products of operator matrices (gqe_compose.cu), d = 128 / 256
+cudaError_t launch_compose(int d, const ComposeParams& cp, int n_entries, cudaStream_t st);
+
 inline bool tc_dim_supported(int d) { return d == 128 || d == 256; }
 inline size_t tc_packed_bytes(int d) { return (size_t)4 * d * d; }
 inline cudaError_t launch_fused_tc(int d, int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {

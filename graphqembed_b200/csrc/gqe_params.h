@@ -22,7 +22,7 @@ struct SegDev {
   int32_t structure;
   int32_t n_anchor;
   uint32_t remote_mask;  // bit k: anchor table k lives in a PEER GPU's HBM; bit 3: the target table
-  int32_t pad_;
+  int32_t composed;      // tensor-core path: runs of linear operators were pre-multiplied (gqe_compose)
   const float* tgt_table;
   const float* anc_table[GQE_MAX_ANCHORS];
   const float* rel[GQE_MAX_RELS];  // relation parameters in application order
@@ -90,6 +90,16 @@ struct PackEntry {
   int32_t pad_;
 };
 constexpr int kMaxPack = 5 * kMaxSegs;
+// gqe_compose: dst = a . b (fp32 [d,d] row-major), one product per blockIdx.z
+struct ComposeEntry {
+  const float* a;
+  const float* b;
+  float* dst;
+};
+constexpr int kMaxCompose = 4 * kMaxSegs;
+struct ComposeParams {
+  ComposeEntry e[kMaxCompose];
+};
 struct PackParams {
   PackEntry e[kMaxPack];
   uint8_t* dst;

@@ -89,7 +89,14 @@ struct Prog {
 };
 
 // Operator order of reference netquery/model.py:70-109 (see include/gqe.h gqe_plan).
-__device__ __forceinline__ void build_program(Prog& pg, int structure, bool deepsets) {
+// `composed`: the host pre-multiplied every run of consecutive linear operators of this
+// formula into one matrix (gqe_compose, fp32), so a run is ONE contraction here:
+//   chains          act.mm(M1).mm(M2).mm(M3)      -> act.mm(M1 M2 M3)          rel[0]
+//   DeepSets branch relu(pre.mm(R.mm(e)))         -> relu((pre R).mm(e))       rel[b]
+//   3-inter_chain   pre.mm(R2a.mm(R2b.mm(e)))     -> (pre R2a R2b).mm(e)       rel[1]
+//   3-chain_inter   R1.mm(post.mm(combined))      -> (R1 post).mm(combined)    post
+// Same algebra, different fp32 rounding (~1e-7 relative), far inside the 1e-4 bound.
+__device__ __forceinline__ void build_program(Prog& pg, int structure, bool deepsets, bool composed) {
   int n = 0;
   auto push = [&](int mat, int gather, int epi) {
     pg.mat[n] = (uint8_t)mat;
@@ -98,13 +105,17 @@ __device__ __forceinline__ void build_program(Prog& pg, int structure, bool deep
     ++n;
   };
   if (structure <= GQE_CHAIN3) {
-    const int hops = structure + 1;
+    const int hops = composed ? 1 : structure + 1;
     for (int h = 0; h < hops; ++h) push(h, h == 0 ? G_TARGET : G_NONE, h == hops - 1 ? E_SCORE : E_TO_A);
   } else {
     const int nb = structure == GQE_INTER3 ? 3 : 2;
     for (int b = 0; b < nb; ++b) {
       const int pos = (b == 0 ? F_FIRST : 0) | (b == nb - 1 ? F_LAST : 0);
       const int agg_simple = E_AGG | pos | ((b == nb - 1 && structure != GQE_CHAIN_INTER3) ? F_DEST_ACC : 0);
+      if (composed) {
+        push(b, b, deepsets ? (E_AGG | F_RELU | pos) : agg_simple);
+        continue;
+      }
       if (structure == GQE_INTER_CHAIN3 && b == 1) {
         push(M_REL1, b, E_TO_A);                               // reverse(r2b) first (model.py:85)
         push(M_REL2, G_NONE, deepsets ? E_TO_A : agg_simple);  // then reverse(r2a)
@@ -113,8 +124,13 @@ __device__ __forceinline__ void build_program(Prog& pg, int structure, bool deep
       }
       if (deepsets) push(M_PRE, G_NONE, E_AGG | F_RELU | pos);  // relu(pre.mm(e)) decoders.py:289-292
     }
-    if (deepsets) push(M_POST, G_NONE, structure == GQE_CHAIN_INTER3 ? E_TO_A : E_SCORE);  // decoders.py:299
-    if (structure == GQE_CHAIN_INTER3) push(M_REL2, G_NONE, E_SCORE);                      // model.py:107
+    if (composed) {
+      if (deepsets) push(M_POST, G_NONE, E_SCORE);                          // post, or R1 post for 3-chain_inter
+      else if (structure == GQE_CHAIN_INTER3) push(M_REL2, G_NONE, E_SCORE);
+    } else {
+      if (deepsets) push(M_POST, G_NONE, structure == GQE_CHAIN_INTER3 ? E_TO_A : E_SCORE);  // decoders.py:299
+      if (structure == GQE_CHAIN_INTER3) push(M_REL2, G_NONE, E_SCORE);                      // model.py:107
+    }
   }
   pg.n = n;
 }
@@ -352,7 +368,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     const int n_valid = (int)min((int64_t)kRows, row_end - row_begin);
 
     Prog pg;
-    build_program(pg, structure, deepsets);
+    build_program(pg, structure, deepsets, s.composed != 0);
 
     // diagnostics: per-tile phase stamps of worker thread 0 (tools/phase_report.py)
     int n_stamp = 0;
@@ -686,7 +702,7 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
     publish(k + 1, next < p.n_tiles ? next : p.n_tiles);
     const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
     Prog pg;
-    build_program(pg, STRUCT >= 0 ? STRUCT : s.structure, deepsets);
+    build_program(pg, STRUCT >= 0 ? STRUCT : s.structure, deepsets, s.composed != 0);
     for (int st = 0; st < pg.n; ++st) {
       const uint8_t* src = step_matrix(s, pg.mat[st]);
 #pragma unroll 1
@@ -720,7 +736,7 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
     if (tile >= p.n_tiles) break;
     const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
     Prog pg;
-    build_program(pg, STRUCT >= 0 ? STRUCT : s.structure, deepsets);
+    build_program(pg, STRUCT >= 0 ? STRUCT : s.structure, deepsets, s.composed != 0);
     for (int st = 0; st < pg.n; ++st, ++gs) {
       ptx::mbar_wait(bar_a_ready, gs & 1);
       ptx::tc_fence_after_sync();

@@ -46,6 +46,9 @@ class QueryEncoderDecoder(nn.Module):
         # arithmetic of the d x d contractions: "bf16x3" = tcgen05 tensor cores with
         # split-bf16 operands (default), "fp32" = exact CUDA-core FMA (include/gqe.h)
         self.precision = "bf16x3"
+        # tensor-core path only: pre-multiply runs of linear operators once per call
+        # ("auto": when >= 1024 rows of a formula share the product; "off"; "always")
+        self.compose = "auto"
 
     # ---- context / binding ---------------------------------------------------
     def _signature(self):
@@ -73,6 +76,7 @@ class QueryEncoderDecoder(nn.Module):
             st[2] = sig
         st[0].set_stream(torch.cuda.current_stream(dev).cuda_stream)
         st[0].set_precision(self.precision)
+        st[0].set_compose(self.compose)
         return st[0]
 
     @property

@@ -127,6 +127,14 @@ int gqe_set_stream(gqe_ctx* ctx, void* stream);
 /* Select / query the arithmetic of the contractions (gqe_precision). */
 int gqe_set_precision(gqe_ctx* ctx, int32_t precision);
 int gqe_get_precision(const gqe_ctx* ctx);
+/* Operator pre-composition on the tensor-core path.  Runs of consecutive linear operators of
+ * a formula (chained relation matrices; DeepSets pre x relation; relation x post) are
+ * multiplied together in fp32 once per call, so the fused kernel runs one contraction per run:
+ * a 3-chain costs one contraction per (query, target) pair instead of three.  Same algebra
+ * as reference netquery/decoders.py:143-150,289-299, different fp32 rounding (~1e-7 relative).
+ * AUTO (default) composes when at least 8 tiles (1024 rows) of a formula share the product. */
+typedef enum gqe_compose_mode { GQE_COMPOSE_OFF = 0, GQE_COMPOSE_AUTO = 1, GQE_COMPOSE_ALWAYS = 2 } gqe_compose_mode;
+int gqe_set_compose(gqe_ctx* ctx, int32_t mode);
 /* Message of the last failure on ctx (ctx == NULL: last gqe_create failure). */
 const char* gqe_last_error(const gqe_ctx* ctx);
 /* Diagnostics: while `log` (DEVICE uint64 [n_tiles][32]) is set, thread 0 of every tile of the

@@ -389,3 +389,28 @@ def test_eval_auc_and_percentile_match_the_oracle(d, inter):
             assert abs(fauc[fg] - fwant[fo]) < 5e-3
         perc = gqe.eval_perc_queries(tq_gpu, model, batch_size=64, hard_negatives=hard)
         assert abs(perc - O.eval_perc_queries(tq_orc, orc, batch_size=64, hard_negatives=hard)) < 0.2
+
+
+@pytest.mark.parametrize("d", [128, 256])
+@pytest.mark.parametrize("inter", INTERS)
+def test_operator_precomposition_stays_within_tolerance(d, inter):
+    """Tensor-core path with runs of linear operators pre-multiplied in fp32 (gqe_set_compose
+    ALWAYS; AUTO only does it for >= 1024 rows per formula): all 7 structures vs the oracle."""
+    nq = 150
+    case = make_case(seed=500 + d + len(inter), d=d, decoder="bilinear", inter=inter, n_queries=nq, n_neg=1,
+                     nodes_per_mode=300)
+    model = build_package_model(case)
+    model.compose = "always"
+    orc = case.oracle()
+    for s in case.batches:
+        b = case.batches[s]
+        targets = np.concatenate([b["target"][:, None], b["negs"]], axis=1)      # [Q, 2]
+        want = _oracle_scores(case, orc, s, targets)
+        batch = query_batch(case, s, targets)
+        loss, scores = model.margin_loss_batch(batch, margin=1, return_scores=True)
+        np.testing.assert_allclose(_np(scores), want.reshape(nq, 2), rtol=0, atol=1e-4, err_msg=s)
+        assert abs(loss.item() - np.maximum(0, 1 - (want[:, 0] - want[:, 1])).mean()) < 1e-4
+        model.compose = "off"
+        plain = _np(model.score_batch(batch)).reshape(nq, 2)
+        model.compose = "always"
+        assert np.abs(_np(scores) - plain).max() < 2e-5, s

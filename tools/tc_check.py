@@ -15,11 +15,13 @@ from oracle.cases import make_case  # noqa: E402
 dims = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["128", "256"])]
 inters = sys.argv[2].split(",") if len(sys.argv) > 2 else ["mean", "min", "mean-simple", "min-simple"]
 nq = int(sys.argv[3]) if len(sys.argv) > 3 else 300
+compose = sys.argv[4] if len(sys.argv) > 4 else "auto"
 worst = 0.0
 for d in dims:
     for inter in inters:
         case = make_case(seed=3 + d, d=d, decoder="bilinear", inter=inter, n_queries=nq, n_neg=3, nodes_per_mode=500)
         model = build_package_model(case)
+        model.compose = compose
         for s in case.batches:
             b = case.batches[s]
             targets = np.concatenate([b["target"][:, None], b["negs"]], axis=1)
