@@ -416,9 +416,13 @@ def roofline_of(wl, name, ms_per_step, pk, world=1):
             "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_flops_per_launch": flops_alg,
             "hbm": {"achieved_gbs": round(gbs, 2), "frac": round(gbs / pk["hbm_gbs"], 4)},
             "tensor": {"executed_tflops": round(tfl_exec, 3), "algorithmic_tflops": round(tfl, 3),
+                       "issued_tflops": round(passes * wl.composed_flops() / sec / 1e12, 3),
                        "peak_tflops": pk["bf16_tflops"], "frac": round(tfl_exec / pk["bf16_tflops"], 4),
                        "note": "d x d contractions as bf16x3 split products on tcgen05 (3 MMAs per algorithmic "
-                               "product); executed = 3 x algorithmic; peak = measured sustained bf16 dense"}}
+                               "product): executed = 3 x algorithmic (SURVEY 8d: the 3-pass scheme divides the "
+                               "usable ceiling by 3); issued = what the tensor pipe really ran after runs of "
+                               "linear operators were pre-multiplied (gqe_compose); peak = measured sustained "
+                               "bf16 dense"}}
 
 
 NVLINK_PEER_GBS = 770.0     # /opt/skills/guides/B200_PROFILING.md: measured peer copy, per direction per GPU

@@ -52,6 +52,7 @@ struct gqe_ctx {
   int compose = GQE_COMPOSE_AUTO;
   float* compose_buf = nullptr;
   size_t compose_cap = 0;
+  unsigned int* compose_done = nullptr;   // per-product tile counters of one compose launch
 
   // query embeddings of the many-targets-per-query path (fp32 [n_queries, d], grows on demand)
   float* qbuf = nullptr;
@@ -159,6 +160,7 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   cudaFree(c->packed);
   cudaFree(c->qbuf);
   cudaFree(c->compose_buf);
+  cudaFree(c->compose_done);
   cudaFree(c->loss_acc);
   cudaFree(c->ticket);
   cudaFree(c->tile_counter);
@@ -402,6 +404,10 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       GQE_CUDA(c, cudaMalloc(&c->compose_buf, need));
       c->compose_cap = need;
     }
+    if (!c->compose_done) {
+      GQE_CUDA(c, cudaMalloc(&c->compose_done, kMaxCompose * sizeof(unsigned int)));
+      GQE_CUDA(c, cudaMemsetAsync(c->compose_done, 0, kMaxCompose * sizeof(unsigned int), c->stream));
+    }
   }
   if (use_tc) {
     const size_t need = (size_t)kMaxPack * tc_packed_bytes(c->d);
@@ -434,18 +440,23 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       }
       return reinterpret_cast<const float*>(c->packed + (size_t)k * tc_packed_bytes(c->d));
     };
-    // fp32 products of runs of linear operators (deduplicated per launch); a 3-factor run
-    // takes two dependent waves: t = a.b, then t.c or c.t
-    ComposeParams cw[2];
-    int n_cw[2] = {0, 0};
-    auto product = [&](const float* a, const float* b, int wave) -> const float* {
-      for (int k = 0; k < n_cw[wave]; ++k)
-        if (cw[wave].e[k].a == a && cw[wave].e[k].b == b) return cw[wave].e[k].dst;
-      ComposeEntry& e = cw[wave].e[n_cw[wave]];
+    // fp32 products of runs of linear operators (deduplicated per launch).  A 3-factor run is
+    // two entries, the second naming the first as its operand (dep): ONE launch computes both.
+    ComposeParams cw;
+    int n_cw = 0;
+    auto product = [&](const float* a, const float* b) -> const float* {
+      for (int k = 0; k < n_cw; ++k)
+        if (cw.e[k].a == a && cw.e[k].b == b) return cw.e[k].dst;
+      ComposeEntry& e = cw.e[n_cw];
       e.a = a;
       e.b = b;
-      e.dst = c->compose_buf + (size_t)(wave * (kMaxCompose / 2) + n_cw[wave]) * c->d * c->d;
-      ++n_cw[wave];
+      e.dep_a = e.dep_b = -1;
+      for (int k = 0; k < n_cw; ++k) {
+        if (cw.e[k].dst == a) e.dep_a = k;
+        if (cw.e[k].dst == b) e.dep_b = k;
+      }
+      e.dst = c->compose_buf + (size_t)n_cw * c->d * c->d;
+      ++n_cw;
       return e.dst;
     };
     int first_structure = -1;
@@ -471,7 +482,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
         // composing pays off once a few tiles share the product (d^3 fp32 FMAs per product)
         const bool compose = c->compose == GQE_COMPOSE_ALWAYS || (c->compose == GQE_COMPOSE_AUTO && rows >= 8 * kTcTileRows);
         const bool ds = s->pre != nullptr;
-        if (!compose || st == GQE_CHAIN1 || (!ds && st != GQE_INTER_CHAIN3)) {
+        if (!compose || st == GQE_CHAIN1 || (st >= GQE_INTER2 && !ds && st != GQE_INTER_CHAIN3)) {
           // nothing to merge: one contraction per operator, as written in the reference
           for (int k = 0; k < n_rels_of(st); ++k) s->rel[k] = packed_of(s->rel[k], chain_form);
           if (s->pre) s->pre = packed_of(s->pre, 0);
@@ -481,28 +492,28 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
           const float *r0 = s->rel[0], *r1 = s->rel[1], *r2 = s->rel[2], *pre = s->pre, *post = s->post;
           s->rel[0] = s->rel[1] = s->rel[2] = s->pre = s->post = nullptr;
           if (st <= GQE_CHAIN3) {                       // act.mm(M1).mm(M2)[.mm(M3)]  (decoders.py:143-145)
-            const float* w = product(r0, r1, 0);
-            if (st == GQE_CHAIN3) w = product(w, r2, 1);
+            const float* w = product(r0, r1);
+            if (st == GQE_CHAIN3) w = product(w, r2);
             s->rel[0] = packed_of(w, 1);
           } else if (st == GQE_INTER2 || st == GQE_INTER3) {   // relu(pre.mm(R_b.mm(e)))  (decoders.py:289-292)
-            s->rel[0] = packed_of(product(pre, r0, 0), 0);
-            s->rel[1] = packed_of(product(pre, r1, 0), 0);
-            if (st == GQE_INTER3) s->rel[2] = packed_of(product(pre, r2, 0), 0);
+            s->rel[0] = packed_of(product(pre, r0), 0);
+            s->rel[1] = packed_of(product(pre, r1), 0);
+            if (st == GQE_INTER3) s->rel[2] = packed_of(product(pre, r2), 0);
             s->post = packed_of(post, 0);
           } else if (st == GQE_INTER_CHAIN3) {          // branch 1: R2a.mm(R2b.mm(e))  (model.py:84-86)
-            const float* t = product(r2, r1, 0);
+            const float* t = product(r2, r1);
             if (ds) {
-              s->rel[0] = packed_of(product(pre, r0, 0), 0);
-              s->rel[1] = packed_of(product(pre, t, 1), 0);
+              s->rel[0] = packed_of(product(pre, r0), 0);
+              s->rel[1] = packed_of(product(pre, t), 0);
               s->post = packed_of(post, 0);
             } else {
               s->rel[0] = packed_of(r0, 0);
               s->rel[1] = packed_of(t, 0);
             }
           } else {                                      // 3-chain_inter (DeepSets): R1.mm(post.mm(.))  (model.py:106-107)
-            s->rel[0] = packed_of(product(pre, r0, 0), 0);
-            s->rel[1] = packed_of(product(pre, r1, 0), 0);
-            s->post = packed_of(product(r2, post, 0), 0);
+            s->rel[0] = packed_of(product(pre, r0), 0);
+            s->rel[1] = packed_of(product(pre, r1), 0);
+            s->post = packed_of(product(r2, post), 0);
           }
         }
       }
@@ -540,9 +551,15 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     // single formula -> that structure's own kernel; otherwise the grouped kernel
     const int structure = (n == 1 && uniform) ? first_structure : -1;
     if (use_tc) {
-      for (int w = 0; w < 2; ++w) {
-        if (n_cw[w] == 0) continue;
-        GQE_CUDA(c, launch_compose(c->d, cw[w], n_cw[w], c->stream));
+      if (n_cw > 0) {
+        bool deps = false;
+        for (int k = 0; k < n_cw; ++k) deps = deps || cw.e[k].dep_a >= 0 || cw.e[k].dep_b >= 0;
+        // tile counters of this launch's products start at zero (only read when a product
+        // depends on another one)
+        if (deps) GQE_CUDA(c, cudaMemsetAsync(c->compose_done, 0, n_cw * sizeof(unsigned int), c->stream));
+        cw.done = c->compose_done;
+        cw.target = (unsigned int)((c->d / 64) * (c->d / 64));
+        GQE_CUDA(c, launch_compose(c->d, cw, n_cw, c->stream));
         c->launches += 1;
       }
       pp.dst = c->packed;

@@ -41,6 +41,19 @@ __global__ void __launch_bounds__(256) gqe_compose(const __grid_constant__ Compo
   ComposeSmem<D>& sm = *reinterpret_cast<ComposeSmem<D>*>(smem_raw);
   const ComposeEntry& e = p.e[blockIdx.z];
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  // Three-factor runs: an operand that is itself a product of this launch.  Its CTAs have a
+  // LOWER blockIdx.z, so they were dispatched before this one and cannot be starved by it;
+  // wait until all of its (D/64)^2 tiles are stored.
+  if (e.dep_a >= 0 || e.dep_b >= 0) {
+    if (threadIdx.x == 0) {
+      if (e.dep_a >= 0)
+        while ((int)(*reinterpret_cast<volatile unsigned int*>(p.done + e.dep_a) - p.target) < 0) __nanosleep(64);
+      if (e.dep_b >= 0)
+        while ((int)(*reinterpret_cast<volatile unsigned int*>(p.done + e.dep_b) - p.target) < 0) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+  }
   // every load of the tile is issued before the first shared store (8 x 128 bits per
   // operand per thread at a time), so the CTA pays ~one memory latency per half
   constexpr int NA = 64 * D / 4 / 256;   // float4 per thread per operand (16 at d = 256)
@@ -51,8 +64,9 @@ __global__ void __launch_bounds__(256) gqe_compose(const __grid_constant__ Compo
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int idx = threadIdx.x + (it0 + u) * 256;
-      va[u] = __ldg(reinterpret_cast<const float4*>(e.a + (size_t)(i0 + idx / (D / 4)) * D) + idx % (D / 4));
-      vb[u] = __ldg(reinterpret_cast<const float4*>(e.b + (size_t)(idx / 16) * D + j0) + idx % 16);
+      // (__ldcg: an operand produced by this very launch must not come from a stale L1 line)
+      va[u] = __ldcg(reinterpret_cast<const float4*>(e.a + (size_t)(i0 + idx / (D / 4)) * D) + idx % (D / 4));
+      vb[u] = __ldcg(reinterpret_cast<const float4*>(e.b + (size_t)(idx / 16) * D + j0) + idx % 16);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -86,6 +100,10 @@ __global__ void __launch_bounds__(256) gqe_compose(const __grid_constant__ Compo
 #pragma unroll
   for (int n = 0; n < 2; ++n)
     wmma::store_matrix_sync(e.dst + (size_t)(i0 + r0) * D + j0 + c0 + 16 * n, acc[n], D, wmma::mem_row_major);
+  // publish this tile
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(p.done + blockIdx.z, 1u);
 }
 
 template <int D>

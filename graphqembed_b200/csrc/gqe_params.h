@@ -90,21 +90,25 @@ struct PackEntry {
   int32_t pad_;
 };
 constexpr int kMaxPack = 5 * kMaxSegs;
-// gqe_compose: dst = a . b (fp32 [d,d] row-major), one product per blockIdx.z
-struct ComposeEntry {
-  const float* a;
-  const float* b;
-  float* dst;
-};
-constexpr int kMaxCompose = 4 * kMaxSegs;
-struct ComposeParams {
-  ComposeEntry e[kMaxCompose];
-};
 struct PackParams {
   PackEntry e[kMaxPack];
   uint8_t* dst;
 };
-
+// gqe_compose: dst = a . b (fp32 [d,d] row-major), one product per blockIdx.z.  A product
+// whose operand is itself a product of the same launch (three-factor runs) names it in
+// dep_a / dep_b (index into e[], always a LOWER index) and waits for its tiles.
+struct ComposeEntry {
+  const float* a;
+  const float* b;
+  float* dst;
+  int32_t dep_a, dep_b;  // -1: operand is a plain parameter matrix
+};
+constexpr int kMaxCompose = 3 * kMaxSegs;  // a structure needs at most three products
+struct ComposeParams {
+  ComposeEntry e[kMaxCompose];
+  unsigned int* done;     // per-product counters of stored tiles (zeroed before the launch)
+  unsigned int target;    // tiles per product
+};
 // gqe_score_pairs: one formula segment's (query, target) pairs against stored query embeddings
 struct PairSeg {
   const float* tgt_table;

@@ -77,6 +77,33 @@ class Workload(object):
         return sum(b.n_queries * per[b.formula.query_type] for b in self.batches)
 
 
+    def composed_flops(self, min_rows=1024):
+        """Contraction flops the tensor-core path actually runs once runs of linear operators
+        are pre-multiplied (gqe_compose; formulas with >= min_rows tile rows): one contraction
+        per (query, target) pair for chains, one per branch + post for DeepSets intersections."""
+        if self.decoder != "bilinear":
+            return 0
+        d2 = self.d * self.d
+        simple = self.inter.endswith("-simple")
+        total = 0
+        for b in self.batches:
+            qt, nq = b.formula.query_type, b.n_queries
+            chain = qt.endswith("-chain") and qt[0] in "123"
+            rows = 2 * nq if chain else nq
+            if rows < min_rows:
+                per = {"1-chain": 4, "2-chain": 8, "3-chain": 12, "2-inter": 4 if simple else 10,
+                       "3-inter": 6 if simple else 14, "3-inter_chain": 6 if simple else 12,
+                       "3-chain_inter": 6 if simple else 12}[qt]
+            elif chain:
+                per = 4
+            elif simple:
+                per = {"2-inter": 4, "3-inter": 6, "3-inter_chain": 4, "3-chain_inter": 6}[qt]
+            else:
+                per = {"2-inter": 6, "3-inter": 8, "3-inter_chain": 6, "3-chain_inter": 6}[qt]
+            total += nq * per * d2
+        return total
+
+
 def make_workload(name=DEFAULT_WORKLOAD, seed=0, kg=None, formulas_per_structure=1, total=None):
     desc, d, n_total, structures, decoder, inter = WORKLOADS[name]
     if total is not None:
