@@ -314,6 +314,8 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
     dev_ms = tm.device_ms(step_device, args.steps, 0, sampler)
     launches = sum(c.launch_count() for c in launch_ctxs) - launches0
     assert float(d_loss.item()) == loss_ref, "non-deterministic loss"
+    if sampler is not None:
+        sampler.stop()      # the NVML polling thread must not compete with the host-timed loop
     e2e_ms = tm.host_ms(step_host, args.steps)
     assert float(h_loss[0]) == loss_ref, "host entry point disagrees with the device one"
     tm.barrier()

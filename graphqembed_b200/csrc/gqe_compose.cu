@@ -34,72 +34,72 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* l
   reinterpret_cast<__nv_bfloat162*>(lo)[1] = l1;
 }
 
+constexpr int kComposeThreads = 512;
+
 template <int D>
-__global__ void __launch_bounds__(256) gqe_compose(const __grid_constant__ ComposeParams p) {
+__global__ void __launch_bounds__(kComposeThreads, 1) gqe_compose(const __grid_constant__ ComposeParams p) {
   using namespace nvcuda;
   extern __shared__ __align__(32) unsigned char smem_raw[];
   ComposeSmem<D>& sm = *reinterpret_cast<ComposeSmem<D>*>(smem_raw);
   const ComposeEntry& e = p.e[blockIdx.z];
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
-  // Three-factor runs: an operand that is itself a product of this launch.  Its CTAs have a
-  // LOWER blockIdx.z, so they were dispatched before this one and cannot be starved by it;
-  // wait until all of its (D/64)^2 tiles are stored.
-  if (e.dep_a >= 0 || e.dep_b >= 0) {
+  // Every load of an operand tile is issued before its first shared store (N float4 per thread
+  // in registers), so the CTA pays ~one memory latency per operand.  A three-factor run names
+  // the product it consumes (dep_a / dep_b): its CTAs have a LOWER blockIdx.z, were dispatched
+  // before this one and cannot be starved by it; the plain operand is fetched first, then the
+  // CTA waits until all (D/64)^2 tiles of the other one are stored.
+  constexpr int N = 64 * D / 4 / kComposeThreads;   // float4 per thread per operand (8 at d = 256)
+  auto wait_for = [&](int dep) {
     if (threadIdx.x == 0) {
-      if (e.dep_a >= 0)
-        while ((int)(*reinterpret_cast<volatile unsigned int*>(p.done + e.dep_a) - p.target) < 0) __nanosleep(64);
-      if (e.dep_b >= 0)
-        while ((int)(*reinterpret_cast<volatile unsigned int*>(p.done + e.dep_b) - p.target) < 0) __nanosleep(64);
+      while ((int)(*reinterpret_cast<volatile unsigned int*>(p.done + dep) - p.target) < 0) __nanosleep(32);
       __threadfence();
     }
     __syncthreads();
-  }
-  // every load of the tile is issued before the first shared store (8 x 128 bits per
-  // operand per thread at a time), so the CTA pays ~one memory latency per half
-  constexpr int NA = 64 * D / 4 / 256;   // float4 per thread per operand (16 at d = 256)
-  static_assert(NA % 8 == 0, "tile loads");
-#pragma unroll 1
-  for (int it0 = 0; it0 < NA; it0 += 8) {
-    float4 va[8], vb[8];
+  };
+  auto load_a = [&](float4 (&v)[N]) {   // (__ldcg: a product of this very launch must not come from a stale L1 line)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = threadIdx.x + (it0 + u) * 256;
-      // (__ldcg: an operand produced by this very launch must not come from a stale L1 line)
-      va[u] = __ldcg(reinterpret_cast<const float4*>(e.a + (size_t)(i0 + idx / (D / 4)) * D) + idx % (D / 4));
-      vb[u] = __ldcg(reinterpret_cast<const float4*>(e.b + (size_t)(idx / 16) * D + j0) + idx % 16);
+    for (int u = 0; u < N; ++u) {
+      const int idx = threadIdx.x + u * kComposeThreads;
+      v[u] = __ldcg(reinterpret_cast<const float4*>(e.a + (size_t)(i0 + idx / (D / 4)) * D) + idx % (D / 4));
     }
+  };
+  auto load_b = [&](float4 (&v)[N]) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = threadIdx.x + (it0 + u) * 256;
-      split_store4(&sm.a_hi[idx / (D / 4)][4 * (idx % (D / 4))], &sm.a_lo[idx / (D / 4)][4 * (idx % (D / 4))], va[u]);
-      split_store4(&sm.b_hi[idx / 16][4 * (idx % 16)], &sm.b_lo[idx / 16][4 * (idx % 16)], vb[u]);
+    for (int u = 0; u < N; ++u) {
+      const int idx = threadIdx.x + u * kComposeThreads;
+      v[u] = __ldcg(reinterpret_cast<const float4*>(e.b + (size_t)(idx / 16) * D + j0) + idx % 16);
     }
+  };
+  float4 va[N], vb[N];
+  if (e.dep_a < 0) load_a(va);
+  if (e.dep_b < 0) load_b(vb);
+  if (e.dep_a >= 0) { wait_for(e.dep_a); load_a(va); }
+  if (e.dep_b >= 0) { wait_for(e.dep_b); load_b(vb); }
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const int idx = threadIdx.x + u * kComposeThreads;
+    split_store4(&sm.a_hi[idx / (D / 4)][4 * (idx % (D / 4))], &sm.a_lo[idx / (D / 4)][4 * (idx % (D / 4))], va[u]);
+    split_store4(&sm.b_hi[idx / 16][4 * (idx % 16)], &sm.b_lo[idx / 16][4 * (idx % 16)], vb[u]);
   }
   __syncthreads();
-  // warp w: rows 16 (w / 2) .. +16, columns 32 (w % 2) .. +32  (two 16x16 accumulators)
+  // warp w (16 warps): rows 16 (w / 4) .. +16, columns 16 (w % 4) .. +16
   const int w = threadIdx.x >> 5;
-  const int r0 = 16 * (w >> 1), c0 = 32 * (w & 1);
-  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2];
-  wmma::fill_fragment(acc[0], 0.f);
-  wmma::fill_fragment(acc[1], 0.f);
-#pragma unroll 2
+  const int r0 = 16 * (w >> 2), c0 = 16 * (w & 3);
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+  wmma::fill_fragment(acc, 0.f);
+#pragma unroll 4
   for (int k = 0; k < D; k += 16) {
     wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> ah, al;
+    wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bh, bl;
     wmma::load_matrix_sync(ah, &sm.a_hi[r0][k], D + 8);
     wmma::load_matrix_sync(al, &sm.a_lo[r0][k], D + 8);
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bh, bl;
-      wmma::load_matrix_sync(bh, &sm.b_hi[k][c0 + 16 * n], 64 + 8);
-      wmma::load_matrix_sync(bl, &sm.b_lo[k][c0 + 16 * n], 64 + 8);
-      wmma::mma_sync(acc[n], ah, bh, acc[n]);
-      wmma::mma_sync(acc[n], al, bh, acc[n]);
-      wmma::mma_sync(acc[n], ah, bl, acc[n]);
-    }
+    wmma::load_matrix_sync(bh, &sm.b_hi[k][c0], 64 + 8);
+    wmma::load_matrix_sync(bl, &sm.b_lo[k][c0], 64 + 8);
+    wmma::mma_sync(acc, ah, bh, acc);
+    wmma::mma_sync(acc, al, bh, acc);
+    wmma::mma_sync(acc, ah, bl, acc);
   }
-#pragma unroll
-  for (int n = 0; n < 2; ++n)
-    wmma::store_matrix_sync(e.dst + (size_t)(i0 + r0) * D + j0 + c0 + 16 * n, acc[n], D, wmma::mem_row_major);
+  wmma::store_matrix_sync(e.dst + (size_t)(i0 + r0) * D + j0 + c0, acc, D, wmma::mem_row_major);
   // publish this tile
   __threadfence();
   __syncthreads();
@@ -118,7 +118,7 @@ static cudaError_t launch_compose_t(const ComposeParams& cp, int n_entries, cuda
     configured[dev] = true;
   }
   const dim3 grid(D / 64, D / 64, (unsigned)n_entries);
-  gqe_compose<D><<<grid, 256, sizeof(ComposeSmem<D>), st>>>(cp);
+  gqe_compose<D><<<grid, kComposeThreads, sizeof(ComposeSmem<D>), st>>>(cp);
   return cudaGetLastError();
 }
 

@@ -386,10 +386,10 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     stamp(1 + 16 * (unsigned long long)structure);
 
     // ---- every index this warp will need, loaded once, up front (lane i <-> tile row
-    // wid*RPW + i), and an L2 prefetch of the LOCAL table rows behind them: the DRAM latency
-    // of the later gathers and of the scoring rows overlaps the first contraction.  (Peer
-    // shards are never prefetched: a bulk L2 prefetch of a PEER address is ~100x slower than
-    // the NVLink loads it would hide -- profiles/r01_peer_gather_micro.md) ---------------------
+    // wid*RPW + i).  The LOCAL table rows behind them are pulled into L2 during the first
+    // contraction (below), so the DRAM latency of the later gathers and of the scoring rows
+    // is hidden.  (Peer shards are never prefetched: a bulk L2 prefetch of a PEER address is
+    // ~100x slower than the NVLink loads it would hide -- profiles/r01_peer_gather_micro.md)
     const bool mine = lane < RPW && my_r < n_valid;
     const uint32_t rm = s.remote_mask;
     int32_t gsrc0 = -1, gsrc1 = -1, gsrc2 = -1;      // gather sources: anchors 0..2 or (chains) the targets
@@ -398,7 +398,6 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       if (mine) {
         gsrc0 = __ldg(p.target_rows + row_begin + my_r);
         ssrc0 = __ldg(p.anchor_rows + (row_begin + my_r) / T);
-        if (!(rm & 1u)) ptx::tma_prefetch_l2(s.anc_table[0] + (size_t)ssrc0 * D, D * 4);
       }
     } else if (mine) {
       gsrc0 = __ldg(p.anchor_rows + row_begin + my_r);
@@ -407,12 +406,6 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       if (!p.q_out) {
         ssrc0 = __ldg(p.target_rows + (row_begin + my_r) * T);
         if (T > 1) ssrc1 = __ldg(p.target_rows + (row_begin + my_r) * T + 1);
-      }
-      if (!(rm & 2u)) ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
-      if (n_branch > 2 && !(rm & 4u)) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
-      if (!(rm & 8u) && !p.q_out) {
-        ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
-        if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
       }
     }
 
@@ -430,8 +423,22 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       ptx::mbar_arrive(bar_a_ready);
 
       if (st == 0) {
-        // while the first contraction runs: pull the first-gather rows of the NEXT tile of
-        // this CTA into L2, so that its only exposed gather is an L2 hit
+        // while the first contraction runs: the L2 prefetches of this tile's later rows (issued
+        // only now, so that they do not queue in front of the first gather's own loads) ...
+        if (mine) {
+          if (chain) {
+            if (!(rm & 1u)) ptx::tma_prefetch_l2(s.anc_table[0] + (size_t)ssrc0 * D, D * 4);
+          } else {
+            if (!(rm & 2u)) ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
+            if (n_branch > 2 && !(rm & 4u)) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
+            if (!(rm & 8u) && !p.q_out) {
+              ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
+              if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
+            }
+          }
+        }
+        // ... and the first-gather rows of the NEXT tile of this CTA, so that its only exposed
+        // gather is an L2 hit
         const int64_t nt = ring.peek(ctl, 0);
         if (nt < p.n_tiles && lane < RPW) {
           const SegDev& s2 = p.seg[seg_of_tile<STRUCT>(p, nt)];
