@@ -86,6 +86,14 @@ _SIGNATURES = {
     "gqe_path_score_device": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int64, _P, _P, C.c_int32, _P]),
     "gqe_intersect_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "gqe_cosine_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+    "gqe_matmul_device": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P]),
+    "gqe_matmul_wgrad_device": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
+    "gqe_rowsum_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+    "gqe_aggregate_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "gqe_aggregate_bwd_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "gqe_dot_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+    "gqe_cosine_bwd_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, C.c_int32, _P, _P]),
+    "gqe_encode_bwd_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "gqe_ipc_export": (C.c_int, [_P, _P, C.c_char_p, C.POINTER(C.c_int64)]),
     "gqe_ipc_open": (C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(_P)]),
     "gqe_ipc_close": (C.c_int, [_P, _P]),
@@ -284,6 +292,31 @@ class Context(object):
 
     def cosine_device(self, d, n, x, y, out):
         self._check(self._lib.gqe_cosine_device(self._h, d, n, x, y, out))
+
+    # -- differentiable operator surface (raw device pointers as ints) ---------------------------
+    def matmul_device(self, w, transpose, d, n, src, out):
+        self._check(self._lib.gqe_matmul_device(self._h, w, int(transpose), d, n, src, out))
+
+    def matmul_wgrad_device(self, transpose, d, n, gy, x, gw):
+        self._check(self._lib.gqe_matmul_wgrad_device(self._h, int(transpose), d, n, gy, x, gw))
+
+    def rowsum_device(self, d, n, gy, x, gv):
+        self._check(self._lib.gqe_rowsum_device(self._h, d, n, gy, x, gv))
+
+    def aggregate_device(self, d, n, e1, e2, e3, relu, use_min, out):
+        self._check(self._lib.gqe_aggregate_device(self._h, d, n, e1, e2, e3, int(relu), int(use_min), out))
+
+    def aggregate_bwd_device(self, d, n, e1, e2, e3, relu, use_min, gout, g1, g2, g3):
+        self._check(self._lib.gqe_aggregate_bwd_device(self._h, d, n, e1, e2, e3, int(relu), int(use_min), gout, g1, g2, g3))
+
+    def dot_device(self, d, n, x, y, out):
+        self._check(self._lib.gqe_dot_device(self._h, d, n, x, y, out))
+
+    def cosine_bwd_device(self, d, n, x, y, gout, raw_dot, gx, gy):
+        self._check(self._lib.gqe_cosine_bwd_device(self._h, d, n, x, y, gout, int(raw_dot), gx, gy))
+
+    def encode_bwd_device(self, mode, n, rows, gout, gtable):
+        self._check(self._lib.gqe_encode_bwd_device(self._h, int(mode), n, rows, gout, gtable))
 
     # -- node-type-sharded tables ---------------------------------------------------------
     def ipc_export(self, dev_ptr):

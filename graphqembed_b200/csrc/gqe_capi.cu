@@ -828,6 +828,97 @@ extern "C" int gqe_cosine_device(gqe_ctx* c, int32_t d, int64_t n, const float* 
   return launch_op(c, d, op);
 }
 
+// ---- differentiable operator surface: forward pieces + vector-Jacobian products -----------
+static int bwd_common(gqe_ctx* c, int d, int64_t n, const char* who) {
+  if (!c) return GQE_ERR_INVALID;
+  if (n < 0) return fail(c, GQE_ERR_INVALID, "%s: negative column count", who);
+  if (!dim_supported(d)) return fail(c, GQE_ERR_UNSUPPORTED, "%s: dimension %d not supported (32/64/128/256)", who, d);
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  drop_stale_error(who);
+  return GQE_OK;
+}
+#define GQE_BWD_LAUNCH(c, call)                                                                 \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) return fail((c), GQE_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    (c)->launches += 1;                                                                         \
+  } while (0)
+
+extern "C" int gqe_matmul_device(gqe_ctx* c, const float* w, int32_t transpose, int32_t d, int64_t n, const float* in,
+                                 float* out) {
+  int rc = bwd_common(c, d, n, "gqe_matmul_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!w || !in || !out) return fail(c, GQE_ERR_INVALID, "gqe_matmul_device: null argument");
+  OpParams op;
+  std::memset(&op, 0, sizeof op);
+  op.op = OP_MATMUL;
+  op.mutate = transpose;
+  op.n = n;
+  op.rel[0] = w;
+  op.in0 = in;
+  op.out = out;
+  return launch_op(c, d, op);
+}
+extern "C" int gqe_matmul_wgrad_device(gqe_ctx* c, int32_t transpose, int32_t d, int64_t n, const float* gy,
+                                       const float* x, float* gw) {
+  int rc = bwd_common(c, d, n, "gqe_matmul_wgrad_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!gy || !x || !gw) return fail(c, GQE_ERR_INVALID, "gqe_matmul_wgrad_device: null argument");
+  GQE_BWD_LAUNCH(c, launch_matmul_wgrad(d, n, gy, x, transpose ? 1 : 0, gw, c->stream));
+  return GQE_OK;
+}
+extern "C" int gqe_rowsum_device(gqe_ctx* c, int32_t d, int64_t n, const float* gy, const float* x, float* gv) {
+  int rc = bwd_common(c, d, n, "gqe_rowsum_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!gy || !gv) return fail(c, GQE_ERR_INVALID, "gqe_rowsum_device: null argument");
+  GQE_BWD_LAUNCH(c, launch_rowsum(d, n, gy, x, gv, c->stream));
+  return GQE_OK;
+}
+extern "C" int gqe_aggregate_device(gqe_ctx* c, int32_t d, int64_t n, const float* e1, const float* e2, const float* e3,
+                                    int32_t relu, int32_t use_min, float* out) {
+  int rc = bwd_common(c, d, n, "gqe_aggregate_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!e1 || !e2 || !out) return fail(c, GQE_ERR_INVALID, "gqe_aggregate_device: null argument");
+  GQE_BWD_LAUNCH(c, launch_aggregate((int64_t)d * n, e1, e2, e3, relu, use_min, out, c->stream));
+  return GQE_OK;
+}
+extern "C" int gqe_aggregate_bwd_device(gqe_ctx* c, int32_t d, int64_t n, const float* e1, const float* e2,
+                                        const float* e3, int32_t relu, int32_t use_min, const float* gout, float* g1,
+                                        float* g2, float* g3) {
+  int rc = bwd_common(c, d, n, "gqe_aggregate_bwd_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!e1 || !e2 || !gout || !g1 || !g2 || (e3 && !g3)) return fail(c, GQE_ERR_INVALID, "gqe_aggregate_bwd_device: null argument");
+  GQE_BWD_LAUNCH(c, launch_aggregate_bwd((int64_t)d * n, e1, e2, e3, relu, use_min, gout, g1, g2, g3, c->stream));
+  return GQE_OK;
+}
+extern "C" int gqe_dot_device(gqe_ctx* c, int32_t d, int64_t n, const float* x, const float* y, float* out) {
+  int rc = bwd_common(c, d, n, "gqe_dot_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!x || !y || !out) return fail(c, GQE_ERR_INVALID, "gqe_dot_device: null argument");
+  GQE_BWD_LAUNCH(c, launch_dot(d, n, x, y, out, c->stream));
+  return GQE_OK;
+}
+extern "C" int gqe_cosine_bwd_device(gqe_ctx* c, int32_t d, int64_t n, const float* x, const float* y, const float* gout,
+                                     int32_t raw_dot, float* gx, float* gy) {
+  int rc = bwd_common(c, d, n, "gqe_cosine_bwd_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!x || !y || !gout || (!gx && !gy)) return fail(c, GQE_ERR_INVALID, "gqe_cosine_bwd_device: null argument");
+  GQE_BWD_LAUNCH(c, launch_cosine_bwd(d, n, x, y, gout, raw_dot, gx, gy, c->stream));
+  return GQE_OK;
+}
+extern "C" int gqe_encode_bwd_device(gqe_ctx* c, int32_t mode, int64_t n, const int32_t* rows, const float* gout,
+                                     float* gtable) {
+  if (!c) return GQE_ERR_INVALID;
+  if (c->tables.empty()) return fail(c, GQE_ERR_UNBOUND, "embedding tables are not bound");
+  if (mode < 0 || mode >= (int)c->tables.size()) return fail(c, GQE_ERR_INVALID, "mode %d out of range", mode);
+  if (!c->tables[mode]) return fail(c, GQE_ERR_UNBOUND, "mode %d has no table on this rank", mode);
+  int rc = bwd_common(c, c->d, n, "gqe_encode_bwd_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!rows || !gout || !gtable) return fail(c, GQE_ERR_INVALID, "gqe_encode_bwd_device: null argument");
+  GQE_BWD_LAUNCH(c, launch_encode_bwd(c->d, n, c->tables[mode], rows, gout, gtable, c->stream));
+  return GQE_OK;
+}
+
 // ---- node-type-sharded tables: CUDA IPC mapping of peer shards ----------------------
 #include <map>
 #include <mutex>

@@ -28,6 +28,19 @@ cudaError_t launch_gather_rows(const float* table, const int32_t* rows, int64_t 
 // (query, target) pair scoring against stored query embeddings (gqe_pairs.cu)
 cudaError_t launch_score_pairs(int d, const PairParams& pp, int64_t n_pairs_total, cudaStream_t st);
 
+// operator-level backward kernels (gqe_bwd.cu), any supported d
+cudaError_t launch_matmul_wgrad(int d, int64_t n, const float* gy, const float* x, int form, float* gw, cudaStream_t st);
+cudaError_t launch_rowsum(int d, int64_t n, const float* gy, const float* x, float* gv, cudaStream_t st);
+cudaError_t launch_aggregate(int64_t total, const float* e1, const float* e2, const float* e3, int relu, int use_min,
+                             float* out, cudaStream_t st);
+cudaError_t launch_aggregate_bwd(int64_t total, const float* e1, const float* e2, const float* e3, int relu, int use_min,
+                                 const float* gout, float* g1, float* g2, float* g3, cudaStream_t st);
+cudaError_t launch_cosine_bwd(int d, int64_t n, const float* x, const float* y, const float* gout, int raw_dot, float* gx,
+                              float* gy, cudaStream_t st);
+cudaError_t launch_dot(int d, int64_t n, const float* x, const float* y, float* out, cudaStream_t st);
+cudaError_t launch_encode_bwd(int d, int64_t n, const float* table, const int32_t* rows, const float* gout, float* gtable,
+                              cudaStream_t st);
+
 // fp32 products of operator matrices (gqe_compose.cu), d = 128 / 256
 cudaError_t launch_compose(int d, const ComposeParams& cp, int n_entries, cudaStream_t st);
 

@@ -125,6 +125,6 @@ struct PairParams {
   float* out_scores;
 };
 
-enum { OP_ENCODE = 0, OP_PROJECT = 1, OP_PATH_SCORE = 2, OP_INTERSECT = 3, OP_COSINE = 4 };
+enum { OP_ENCODE = 0, OP_PROJECT = 1, OP_PATH_SCORE = 2, OP_INTERSECT = 3, OP_COSINE = 4, OP_MATMUL = 5 };
 
 }  // namespace gqe

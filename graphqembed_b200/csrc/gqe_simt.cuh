@@ -498,6 +498,13 @@ __global__ void __launch_bounds__(kThreads, (D <= 128 ? 2 : 1)) gqe_op_simt(cons
       store_fm<D>(p.out, sm.A, p.n, c0, n_valid);
       break;
     }
+    case OP_MATMUL:  // out = W in (mutate == 0) or W^T in (mutate != 0), any [d,d] matrix (rel[0])
+      load_fm<D>(sm.X, p.in0, p.n, c0, n_valid);
+      __syncthreads();
+      if (p.mutate) tile_matmul<D, false, EPI_NONE>(sm.X, sm.P, p.rel[0]);
+      else tile_matmul<D, true, EPI_NONE>(sm.X, sm.P, p.rel[0]);
+      store_fm<D>(p.out, sm.X, p.n, c0, n_valid);
+      break;
     case OP_COSINE:
       load_fm<D>(sm.X, p.in0, p.n, c0, n_valid);
       load_fm<D>(sm.A, p.in1, p.n, c0, n_valid);

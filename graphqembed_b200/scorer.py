@@ -9,8 +9,12 @@ L2 normalisation, the chained relation operators, the intersection, the
 cosine against every target and (for the loss) the hinge + mean all happen on
 chip (``csrc/gqe_simt.cuh``).
 
-Forward only: gradients are not produced (backward is the first item of the
-"next" list).
+``forward`` and the ``*_batch`` / ``*_grouped`` calls never build an autograd
+graph.  ``margin_loss`` does when gradients are enabled and a parameter
+requires them (the training loop of reference train_helpers.py:76-79): it then
+runs the differentiable operator chain of ``autograd.py`` (exact fp32, un-fused)
+so that ``loss.backward(); optimizer.step()`` works unchanged; under
+``torch.no_grad()`` it is the single fused launch.
 """
 import random
 
@@ -145,6 +149,11 @@ class QueryEncoderDecoder(nn.Module):
         """model.py:112-127 in one launch: the query side is built once and
         scored against the positive and the negative; hinge + mean are fused."""
         neg_nodes = self.pick_negatives(formula, queries, hard_negatives)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training: the differentiable operator chain (autograd.py); its backward runs the
+            # hand-written VJP kernels and leaves dense .grad tensors for any torch optimiser
+            from . import autograd
+            return autograd.margin_loss(self, formula, queries, neg_nodes, margin)
         n = len(queries)
         anchors = np.empty((len(formula.anchor_modes), n), dtype=np.int64)
         for k in range(anchors.shape[0]):

@@ -243,6 +243,37 @@ int gqe_intersect_device(gqe_ctx* ctx, int32_t mode, int64_t n, const float* emb
 /* nn.CosineSimilarity(dim=0, eps=1e-8) as used at model.py:68,97,108. */
 int gqe_cosine_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* x, const float* y, float* out /*[n]*/);
 
+/* ---- differentiable operator surface ----------------------------------------
+ * The training step of the reference is loss.backward() through the operators above
+ * (netquery/train_helpers.py:78).  These are the forward pieces autograd needs as separate
+ * calls and the vector-Jacobian product of each operator, all on feature-major fp32 [d, n]
+ * DEVICE tensors; graphqembed_b200/autograd.py chains them the way torch.autograd chains
+ * the reference's ops.  Parameter gradients (gw, gv, gtable) are ACCUMULATED into their
+ * destination with atomicAdd; zero it first. */
+/* out = W in (transpose == 0: M.mm(embeds), decoders.py:150,289,299) or W^T in
+ * (transpose != 0: act.mm(M), decoders.py:145); w: DEVICE [d,d] row-major. */
+int gqe_matmul_device(gqe_ctx* ctx, const float* w, int32_t transpose, int32_t d, int64_t n, const float* in, float* out);
+/* gw += gy x^T (transpose == 0) or x gy^T (transpose != 0): gradient of the matrix above. */
+int gqe_matmul_wgrad_device(gqe_ctx* ctx, int32_t transpose, int32_t d, int64_t n, const float* gy, const float* x,
+                            float* gw);
+/* gv[i] += sum_c gy[i][c] * (x ? x[i][c] : 1): gradient of a TransE / BilinearDiag relation
+ * vector (decoders.py:203,208 / 231,236). */
+int gqe_rowsum_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* gy, const float* x, float* gv);
+/* out = agg_k act(e_k): act = relu (DeepSets, decoders.py:289-296) or identity
+ * (SimpleSetIntersection, decoders.py:311-316); agg = mean (use_min == 0) or min; e3 may be NULL. */
+int gqe_aggregate_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* e1, const float* e2, const float* e3,
+                         int32_t relu, int32_t use_min, float* out);
+int gqe_aggregate_bwd_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* e1, const float* e2, const float* e3,
+                             int32_t relu, int32_t use_min, const float* gout, float* g1, float* g2, float* g3);
+/* out[c] = sum_k x[k][c] y[k][c]: the un-normalised BilinearDiag chain score (decoders.py:232). */
+int gqe_dot_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* x, const float* y, float* out);
+/* VJP of gqe_cosine_device (raw_dot == 0) or gqe_dot_device (raw_dot != 0); gx or gy may be NULL. */
+int gqe_cosine_bwd_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* x, const float* y, const float* gout,
+                          int32_t raw_dot, float* gx, float* gy);
+/* VJP of gqe_encode_device: gtable[rows[c], :] += (g_c - x_hat (x_hat . g_c)) / |t|, gtable: DEVICE
+ * [table rows, d] dense gradient of the mode's table (what nn.Embedding's backward produces). */
+int gqe_encode_bwd_device(gqe_ctx* ctx, int32_t mode, int64_t n, const int32_t* rows, const float* gout, float* gtable);
+
 /* ---- node-type-sharded tables across the GPUs of one box -------------------
  * (no counterpart in the reference, which is single-process: this is the
  * multi-GPU form of the `features` lookup of netquery/bio/data_utils.py:20-21.)
