@@ -52,6 +52,7 @@ def parse_args():
                     help="table placement (default: replicated; p2p for the 10M-node workload at N>1)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded 10M-node leg at N>1")
     ap.add_argument("--no-eval-shape", action="store_true", help="skip the 1 query x 101 targets leg at N=1")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the configs[0] training-step leg at N=1")
     ap.add_argument("--with-sharded", action="store_true", help="also run the 10M-node workload at N=1")
     ap.add_argument("--sharded-formulas", type=int, default=4, help="formulas per structure of the 10M-node leg")
     return ap.parse_args()
@@ -385,6 +386,100 @@ def measure_eval_shape(args, tm, local_rank, n_queries=8192, n_neg=100, d=256):
             "bytes": int(n_rows * (4 * d + 4) + nq * T * 4)}
 
 
+def measure_train_step(args, tm, local_rank, batch=512, d=128, steps=30, cpu_steps=4):
+    """BASELINE.json configs[0], as a TRAINING step (reference train_helpers.py:49-79): zero_grad,
+    margin_loss on a 1-chain batch of 512, backward, Adam step over every parameter (dense table
+    gradients, like the reference's nn.Embedding).  GPU: the drop-in modules (autograd.py + the VJP
+    kernels); CPU: the oracle's torch ops with autograd on this box's host cores."""
+    import random
+    import numpy as np
+    import torch
+
+    import graphqembed_b200 as gqe
+    from graphqembed_b200.synth import SynthKG, bio_shaped
+    from oracle import netquery_oracle as O
+
+    device = tm.device
+    kg = bio_shaped(seed=0)
+    rng = np.random.RandomState(7)
+    rels = kg.sample_rels("1-chain", rng)
+    b = kg.sample_batch("1-chain", rels, batch, 1, rng)
+
+    class G(object):
+        pass
+    graph = G()
+    graph.full_lists = kg.full_lists()
+    graph.relations = kg.relations
+    graph.features = gqe.RowLookup(kg.node_ids)
+    dims = {m: d for m in kg.modes}
+    torch.manual_seed(0)
+    feature_modules = {m: torch.nn.Embedding(kg.sizes[m] + 2, d) for m in kg.modes}
+    for m in kg.modes:
+        feature_modules[m].weight.data.normal_(0, 1.0 / d)
+    enc = gqe.get_encoder(0, graph, dims, feature_modules)
+    dec = gqe.get_metapath_decoder(graph, dims, "bilinear")
+    idec = gqe.get_intersection_decoder(graph, dims, "mean")
+    model = gqe.QueryEncoderDecoder(graph, enc, dec, idec).to(device)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    f = gqe.Formula("1-chain", rels)
+    qs = [gqe.Query(SynthKG.query_graph("1-chain", rels, b["target"][i], b["anchors"][:, i]), None, None)
+          for i in range(batch)]
+
+    def step():
+        opt.zero_grad()
+        loss = model.margin_loss(f, qs)
+        loss.backward()
+        opt.step()
+        return loss
+
+    random.seed(0)
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize(device)
+    l0 = model.context().launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = step()
+    last = float(loss.item())
+    torch.cuda.synchronize(device)
+    gpu_ms = (time.perf_counter() - t0) * 1e3 / steps
+    launches = (model.context().launch_count() - l0) / steps
+
+    # the reference's path on the host: same shapes, dense Adam over every tensor
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tables = {m: feature_modules[m].weight.detach().cpu().clone() for m in kg.modes}
+    relp = {r: dec.mats[r].detach().cpu().clone() for r in kg.rel_keys}
+    pre = {m: idec.pre_mats[m].detach().cpu().clone() for m in kg.modes}
+    post = {m: idec.post_mats[m].detach().cpu().clone() for m in kg.modes}
+    orc = O.OracleScorer(tables, kg.node_maps(), relp, "bilinear", "mean", pre, post, full_lists=kg.full_lists())
+    leaves = list(orc.tables.values()) + list(orc.rel_params.values()) + list(orc.pre.values()) + list(orc.post.values())
+    for t in leaves:
+        t.requires_grad_(True)
+    copt = torch.optim.Adam(leaves, lr=0.01)
+    of = O.Formula("1-chain", rels)
+    oqs = [O.Query(SynthKG.query_graph("1-chain", rels, b["target"][i], b["anchors"][:, i]), None, None)
+           for i in range(batch)]
+
+    def cpu_step():
+        copt.zero_grad()
+        loss = orc.margin_loss(of, oqs)
+        loss.backward()
+        copt.step()
+
+    cpu_step()
+    t0 = time.perf_counter()
+    for _ in range(cpu_steps):
+        cpu_step()
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / cpu_steps
+    return {"workload": "Bio KG 1-chain, Bilinear, d=%d, batch=%d: zero_grad + margin_loss + backward + Adam step "
+                        "(dense table gradients)" % (d, batch),
+            "gpu_ms_per_step": round(gpu_ms, 3), "gpu_queries_per_s": round(batch / gpu_ms * 1e3, 1),
+            "gpu_kernels_per_step": round(launches, 1), "loss_after": last,
+            "cpu_ms_per_step": round(cpu_ms, 3), "cpu_queries_per_s": round(batch / cpu_ms * 1e3, 1), "cpu_cores": cores,
+            "note": "wall clock per step incl. Python; CPU = oracle port with torch autograd + torch.optim.Adam"}
+
+
 def roofline_of(wl, name, ms_per_step, pk, world=1):
     """Roofline of the fused kernel for one step of `wl` on one GPU."""
     bytes_alg, flops_alg = wl.algorithmic_bytes(), wl.algorithmic_flops()
@@ -472,6 +567,10 @@ def run_native(args):
     if world == 1 and not args.no_eval_shape:
         eval_res = measure_eval_shape(args, tm, local_rank)
 
+    train_res = None
+    if world == 1 and not args.no_train_step:
+        train_res = measure_train_step(args, tm, local_rank)
+
     line = None
     if rank == 0:
         pk = peaks()
@@ -521,6 +620,8 @@ def run_native(args):
                         "frac": round(eval_res["bytes"] / sec / 1e9 / pk["hbm_gbs"], 4),
                         "note": "gather-bound: one table row per (query, target) pair; Bio-size tables are "
                                 "L2-resident after first touch, so this can exceed the DRAM roofline"}}
+        if train_res is not None:
+            line["train_step"] = train_res
         if world == 1 and not args.no_cpu_baseline:
             tables, rels, pre, post = res["params"]
             line["cpu_baseline"] = cpu_reference(args, name, tables=[t.cpu() for t in tables],

@@ -14,7 +14,7 @@ python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.e
 kill $smi
 cat gpurun_out/${tag}_bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-eval-shape "$@" > gpurun_out/${tag}_launches.log 2>&1
+    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-eval-shape --no-train-step "$@" > gpurun_out/${tag}_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gqe_fused -s 4 -c 1 -f -o gpurun_out/${tag}_fused_full \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-eval-shape "$@" > gpurun_out/${tag}_full.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-eval-shape --no-train-step "$@" > gpurun_out/${tag}_full.log 2>&1
 ls -la gpurun_out | tail -12
