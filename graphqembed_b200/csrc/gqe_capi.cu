@@ -65,6 +65,14 @@ struct gqe_ctx {
   unsigned int* ticket = nullptr;
   unsigned int* tile_counter = nullptr;
 
+  // *_host entry points: the index H2D copies run on their own stream so that they overlap the
+  // weight preparation kernels (gqe_compose / gqe_pack) of the same call; the fused kernel
+  // waits for `h2d_done`
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t h2d_done = nullptr;
+  cudaEvent_t stream_idle = nullptr;
+  bool wait_h2d = false;
+
   // staging for the *_host entry points (grow on demand)
   void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t stage_cap[6] = {0, 0, 0, 0, 0, 0};
@@ -165,6 +173,9 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   cudaFree(c->ticket);
   cudaFree(c->tile_counter);
   for (void* p : c->stage) cudaFree(p);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->h2d_done) cudaEventDestroy(c->h2d_done);
+  if (c->stream_idle) cudaEventDestroy(c->stream_idle);
   drop_stale_error("gqe_destroy (end)");
   delete c;
 }
@@ -550,6 +561,13 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     }
     // single formula -> that structure's own kernel; otherwise the grouped kernel
     const int structure = (n == 1 && uniform) ? first_structure : -1;
+    auto wait_for_indices = [&]() -> int {
+      if (c->wait_h2d) {
+        GQE_CUDA(c, cudaStreamWaitEvent(c->stream, c->h2d_done, 0));
+        c->wait_h2d = false;
+      }
+      return GQE_OK;
+    };
     if (use_tc) {
       if (n_cw > 0) {
         bool deps = false;
@@ -564,9 +582,11 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       }
       pp.dst = c->packed;
       GQE_CUDA(c, launch_pack(c->d, pp, n_pack, c->stream));
+      if (int rc = wait_for_indices()) return rc;
       GQE_CUDA(c, launch_fused_tc(c->d, structure, lp, tiles, c->stream));
       c->launches += 2;
     } else {
+      if (int rc = wait_for_indices()) return rc;
       GQE_CUDA(c, launch_fused_simt(c->d, structure, lp, tiles, c->stream));
       c->launches += 1;
     }
@@ -672,17 +692,31 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
   if (out_loss && (rc = stage_reserve(c, ST_LOSS, sizeof(float))) != GQE_OK) return rc;
   if (nq > 0) {
     if (!anchor_rows || !target_rows) return fail(c, GQE_ERR_INVALID, "index arrays are null");
+    if (!c->copy_stream) {
+      GQE_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      GQE_CUDA(c, cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming));
+      GQE_CUDA(c, cudaEventCreateWithFlags(&c->stream_idle, cudaEventDisableTiming));
+    }
+    // the staging buffers may still be read by work queued earlier on the compute stream
+    GQE_CUDA(c, cudaEventRecord(c->stream_idle, c->stream));
+    GQE_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->stream_idle, 0));
     GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_ANCHOR], anchor_rows, sizeof(int32_t) * (size_t)na * nq,
-                                cudaMemcpyHostToDevice, c->stream));
+                                cudaMemcpyHostToDevice, c->copy_stream));
     GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_TARGET], target_rows, sizeof(int32_t) * (size_t)n_pairs,
-                                cudaMemcpyHostToDevice, c->stream));
+                                cudaMemcpyHostToDevice, c->copy_stream));
     if (target_offsets)
       GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_OFFSETS], target_offsets, sizeof(int64_t) * (size_t)(nq + 1),
-                                  cudaMemcpyHostToDevice, c->stream));
+                                  cudaMemcpyHostToDevice, c->copy_stream));
+    GQE_CUDA(c, cudaEventRecord(c->h2d_done, c->copy_stream));
+    c->wait_h2d = true;   // consumed by the first kernel of run_fused that reads the indices
   }
   rc = run_fused(c, segs, n_segs, nq, (const int32_t*)c->stage[ST_ANCHOR], n_pairs, (const int32_t*)c->stage[ST_TARGET],
                  target_offsets ? (const int64_t*)c->stage[ST_OFFSETS] : nullptr, T,
                  out_scores ? (float*)c->stage[ST_SCORES] : nullptr, margin, out_loss ? (float*)c->stage[ST_LOSS] : nullptr);
+  if (c->wait_h2d) {   // nothing consumed the indices (empty batch / early error): keep the streams ordered
+    cudaStreamWaitEvent(c->stream, c->h2d_done, 0);
+    c->wait_h2d = false;
+  }
   if (rc != GQE_OK) return rc;
   if (out_scores && n_pairs > 0)
     GQE_CUDA(c, cudaMemcpyAsync(out_scores, c->stage[ST_SCORES], sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost,
