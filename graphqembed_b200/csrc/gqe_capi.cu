@@ -439,14 +439,16 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     PackParams pp;
     int n_pack = 0;
     // packed copy of one matrix in the orientation its use needs (deduplicated per launch)
-    auto packed_of = [&](const float* src, int chain_form) -> const float* {
+    // `perm`: the matrix of a contraction whose accumulator is scored in the TMEM fragment
+    // layout (the last hop of a chain) has its output columns permuted at packing time
+    auto packed_of = [&](const float* src, int chain_form, int perm = 0) -> const float* {
       int k = 0;
       for (; k < n_pack; ++k)
-        if (pp.e[k].src == src && pp.e[k].chain_form == chain_form) break;
+        if (pp.e[k].src == src && pp.e[k].chain_form == chain_form && pp.e[k].perm == perm) break;
       if (k == n_pack) {
         pp.e[k].src = src;
         pp.e[k].chain_form = chain_form;
-        pp.e[k].pad_ = 0;
+        pp.e[k].perm = perm;
         ++n_pack;
       }
       return reinterpret_cast<const float*>(c->packed + (size_t)k * tc_packed_bytes(c->d));
@@ -493,11 +495,18 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
         // composing pays off once a few tiles share the product (d^3 fp32 FMAs per product)
         const bool compose = c->compose == GQE_COMPOSE_ALWAYS || (c->compose == GQE_COMPOSE_AUTO && rows >= 8 * kTcTileRows);
         const bool ds = s->pre != nullptr;
+        // the contraction whose accumulator the kernel scores in the TMEM fragment layout
+        // (tc::score_frag: the last hop of a chain) is packed with permuted output columns;
+        // the intersections are scored through the transposed tile (fp = 0)
+        const int fp = 0;
         if (!compose || st == GQE_CHAIN1 || (st >= GQE_INTER2 && !ds && st != GQE_INTER_CHAIN3)) {
           // nothing to merge: one contraction per operator, as written in the reference
-          for (int k = 0; k < n_rels_of(st); ++k) s->rel[k] = packed_of(s->rel[k], chain_form);
+          for (int k = 0; k < n_rels_of(st); ++k) {
+            const bool last = k == n_rels_of(st) - 1;
+            s->rel[k] = packed_of(s->rel[k], chain_form, last && (st <= GQE_CHAIN3 || (st == GQE_CHAIN_INTER3 && fp)));
+          }
           if (s->pre) s->pre = packed_of(s->pre, 0);
-          if (s->post) s->post = packed_of(s->post, 0);
+          if (s->post) s->post = packed_of(s->post, 0, st != GQE_CHAIN_INTER3 && fp);
         } else {
           s->composed = 1;
           const float *r0 = s->rel[0], *r1 = s->rel[1], *r2 = s->rel[2], *pre = s->pre, *post = s->post;
@@ -505,18 +514,18 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
           if (st <= GQE_CHAIN3) {                       // act.mm(M1).mm(M2)[.mm(M3)]  (decoders.py:143-145)
             const float* w = product(r0, r1);
             if (st == GQE_CHAIN3) w = product(w, r2);
-            s->rel[0] = packed_of(w, 1);
+            s->rel[0] = packed_of(w, 1, 1);
           } else if (st == GQE_INTER2 || st == GQE_INTER3) {   // relu(pre.mm(R_b.mm(e)))  (decoders.py:289-292)
             s->rel[0] = packed_of(product(pre, r0), 0);
             s->rel[1] = packed_of(product(pre, r1), 0);
             if (st == GQE_INTER3) s->rel[2] = packed_of(product(pre, r2), 0);
-            s->post = packed_of(post, 0);
+            s->post = packed_of(post, 0, fp);
           } else if (st == GQE_INTER_CHAIN3) {          // branch 1: R2a.mm(R2b.mm(e))  (model.py:84-86)
             const float* t = product(r2, r1);
             if (ds) {
               s->rel[0] = packed_of(product(pre, r0), 0);
               s->rel[1] = packed_of(product(pre, t), 0);
-              s->post = packed_of(post, 0);
+              s->post = packed_of(post, 0, fp);
             } else {
               s->rel[0] = packed_of(r0, 0);
               s->rel[1] = packed_of(t, 0);
@@ -524,7 +533,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
           } else {                                      // 3-chain_inter (DeepSets): R1.mm(post.mm(.))  (model.py:106-107)
             s->rel[0] = packed_of(product(pre, r0), 0);
             s->rel[1] = packed_of(product(pre, r1), 0);
-            s->post = packed_of(product(r2, post), 0);
+            s->post = packed_of(product(r2, post), 0, fp);
           }
         }
       }

@@ -87,7 +87,8 @@ constexpr int kTcTileRows = 128;
 struct PackEntry {
   const float* src;
   int32_t chain_form;  // 1: B[n][k] = M[k][n] (act.mm(M)); 0: B[n][k] = M[n][k] (M.mm(embeds))
-  int32_t pad_;
+  int32_t perm;        // 1: output columns permuted inside 16-column blocks for the fragment-layout
+                       //    scoring of the accumulator (tc::score_col_src)
 };
 constexpr int kMaxPack = 5 * kMaxSegs;
 struct PackParams {

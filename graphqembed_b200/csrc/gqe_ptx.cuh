@@ -119,6 +119,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       ::GQE_I8(v, 0), GQE_I8(v, 8), "r"(taddr)
       : "memory");
 }
+// 16 TMEM lanes x 32 fp32 columns per warp in the matrix-fragment layout: lane t of the warp
+// receives, for repeat j = 0..3, v[4j + 0/1] = (row t/4,     columns 8j + 2(t%4) + 0/1) and
+//                                v[4j + 2/3] = (row t/4 + 8, same columns); rows relative to the
+// lane field of taddr (a multiple of 16 inside the warp's own 32-lane quarter).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : GQE_R8(v, 0), GQE_R8(v, 8)
+      : "r"(taddr)
+      : "memory");
+}
 #undef GQE_R8
 #undef GQE_I8
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

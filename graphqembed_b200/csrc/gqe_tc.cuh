@@ -55,8 +55,11 @@ struct Cfg {
   static constexpr int kOffAlo = kAPlaneBytes;
   static constexpr int kOffB = 2 * kAPlaneBytes;
   static constexpr int kOffCtl = kOffB + kStages * kStageBytes;
-  static constexpr int kCtlBytes = 256;
-  static constexpr int kSmemBytes = kOffCtl + kCtlBytes;
+  static constexpr int kCtlBytes = 512;
+  static constexpr int kOffScratch = kOffCtl + kCtlBytes;  // [128 rows][3] fp32 partial sums (score_frag)
+  static constexpr int kScratchBytes = kRows * 3 * 4;
+  static constexpr int kSmemBytes = kOffScratch + kScratchBytes;
+  static_assert(kSmemBytes <= 232448, "dynamic shared memory per CTA");
   static constexpr int kTmemCols = 2 * D;              // accumulator + aggregation region
   static constexpr int kPackedBytes = 4 * D * D;       // one packed matrix (2 planes x bf16)
   static constexpr int kCtasPerSm = (D <= 128) ? 2 : 1;
@@ -74,7 +77,7 @@ struct Ctl {
   uint32_t tmem_base;
   int last;
 };
-static_assert(sizeof(Ctl) <= 256, "control block");
+static_assert(sizeof(Ctl) <= 512, "control block");
 
 // ---- the per-structure program --------------------------------------------------
 enum { G_NONE = 7, G_TARGET = 3 };                       // gather source: anchor 0..2, target, none
@@ -331,6 +334,161 @@ __device__ __forceinline__ float4* q_chunk(float* qsm, int r, int c) {
   return reinterpret_cast<float4*>(qsm + (size_t)r * D) + (c ^ (r & 7));
 }
 
+// ---- chain scoring straight from the accumulator ---------------------------------------
+// The final accumulator row of a chain tile is the projected target y; it is scored against
+// the anchor row of its query (decoders.py:146):
+//     s = (y . a / |a|) / max(|y|, eps)
+// The accumulator is read from TMEM in the 16x256b fragment layout (4 lanes share a row) and
+// the anchor rows with 128-bit loads in the matching layout (score_col_src: every 32-byte
+// sector fetched is fully used), so nothing goes through shared memory: the A planes stay free
+// and the tile is scored while the NEXT tile's first contraction is on the tensor pipe.  Warp
+// (quarter q, half hh, column half ch) owns TMEM lanes 32q+16hh .. +15 and 128 columns; at
+// d = 256 the two column halves of a row are combined through `scratch` in a fixed order
+// (deterministic).  [The same scheme for the intersections' two target rows per query is
+// slower than the transposed tile: 8 distinct lines per load instruction, measured 8-9 us per
+// tile against 7.4.]
+//
+// Column permutation of a scored accumulator (applied to the weights by gqe_pack): lane t owns
+// accumulator columns 8j + 2(t%4) + {0,1}; with accumulator column 16b + 8j' + 2m + e holding
+// output column 16b + 4m + 2j' + e, the four columns a lane owns in repeats (2b, 2b+1) are the
+// CONTIGUOUS output columns 16b + 4m .. +3.
+__host__ __device__ constexpr int score_col_src(int n) {
+  return (n & ~15) | (((n >> 1) & 3) << 2) | (((n >> 3) & 1) << 1) | (n & 1);
+}
+
+struct PendTile {
+  int64_t tile;
+  int64_t row_begin;
+  const float* table;   // the anchor table
+  int32_t idx[2];       // anchor rows of this thread's two accumulator rows
+  int32_t n_valid;
+  uint32_t region;      // TMEM region (0 / 1) holding the tile's final accumulator
+  bool valid;
+};
+
+// this thread's two accumulator rows in the fragment layout
+__device__ __forceinline__ int frag_row(int wid, int lane, int rs) {
+  return 32 * (wid & 3) + 16 * ((wid >> 2) & 1) + (lane >> 2) + 8 * rs;
+}
+
+template <int D>
+__device__ __forceinline__ void score_frag(const LaunchParams& p, Ctl* ctl, float* scratch, uint32_t tmem_base,
+                                           const PendTile& pt, int wid, int lane) {
+  using C = Cfg<D>;
+  constexpr int NCH = C::kColGroups / 2;   // warps sharing one 16-lane half (1 at d=128, 2 at d=256)
+  constexpr int COLS = D / NCH;            // columns per warp (128)
+  const int ch = wid >> 3;
+  const int g = lane >> 2, c4 = 4 * (lane & 3);
+  int rr[2];
+  bool ok[2];
+  const float* pr[2];
+#pragma unroll
+  for (int rs = 0; rs < 2; ++rs) {
+    rr[rs] = frag_row(wid, lane, rs);
+    ok[rs] = rr[rs] < pt.n_valid;
+    pr[rs] = pt.table + (size_t)(ok[rs] ? pt.idx[rs] : 0) * D + COLS * ch + c4;
+  }
+  float yy[2] = {0.f, 0.f}, dt[2] = {0.f, 0.f}, nn[2] = {0.f, 0.f};
+  const uint32_t taddr = tmem_base + pt.region * D + ((uint32_t)(32 * (wid & 3) + 16 * ((wid >> 2) & 1)) << 16) + COLS * ch;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < COLS / 32; c += 2) {   // two 32-column rounds of loads in flight
+    float4 av[2][2][2];  // [round][row slot][16-column block]
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int rs = 0; rs < 2; ++rs)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+          av[r][rs][b] = ok[rs] ? __ldg(reinterpret_cast<const float4*>(pr[rs] + 32 * (c + r) + 16 * b)) : zero4;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      uint32_t raw[16];
+      ptx::tmem_ld_16x256b_x4(taddr + 32 * (c + r), raw);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          // repeats 2b, 2b+1 of this row slot = output columns 16b + c4 .. +3 (score_col_src)
+          const float y0 = __uint_as_float(raw[8 * b + 2 * rs]), y1 = __uint_as_float(raw[8 * b + 2 * rs + 1]);
+          const float y2 = __uint_as_float(raw[8 * b + 4 + 2 * rs]), y3 = __uint_as_float(raw[8 * b + 4 + 2 * rs + 1]);
+          const float4 a = av[r][rs][b];
+          dt[rs] = fmaf(y0, a.x, dt[rs]); dt[rs] = fmaf(y1, a.y, dt[rs]);
+          dt[rs] = fmaf(y2, a.z, dt[rs]); dt[rs] = fmaf(y3, a.w, dt[rs]);
+          nn[rs] = fmaf(a.x, a.x, nn[rs]); nn[rs] = fmaf(a.y, a.y, nn[rs]);
+          nn[rs] = fmaf(a.z, a.z, nn[rs]); nn[rs] = fmaf(a.w, a.w, nn[rs]);
+          yy[rs] = fmaf(y0, y0, yy[rs]); yy[rs] = fmaf(y1, y1, yy[rs]);
+          yy[rs] = fmaf(y2, y2, yy[rs]); yy[rs] = fmaf(y3, y3, yy[rs]);
+        }
+    }
+  }
+  // the four lanes of a row
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1)
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs) {
+      yy[rs] += __shfl_xor_sync(0xffffffffu, yy[rs], o);
+      dt[rs] += __shfl_xor_sync(0xffffffffu, dt[rs], o);
+      nn[rs] += __shfl_xor_sync(0xffffffffu, nn[rs], o);
+    }
+  if (NCH > 1) {  // second column half -> scratch -> first column half (fixed order)
+    if (ch == 1 && (lane & 3) == 0) {
+#pragma unroll
+      for (int rs = 0; rs < 2; ++rs) {
+        float* dst = scratch + 3 * rr[rs];
+        dst[0] = yy[rs]; dst[1] = dt[rs]; dst[2] = nn[rs];
+      }
+    }
+    ptx::named_bar_sync(1, C::kWorkerThreads);
+    if (ch == 0) {
+#pragma unroll
+      for (int rs = 0; rs < 2; ++rs) {
+        const float* src = scratch + 3 * rr[rs];
+        yy[rs] += src[0]; dt[rs] += src[1]; nn[rs] += src[2];
+      }
+    }
+  }
+  double local = 0.0;
+#pragma unroll
+  for (int rs = 0; rs < 2; ++rs) {
+    // a_hat = a/|a| has unit norm: cos = (y.a/|a|) / max(|y|, eps); a zero anchor row gives
+    // 0/0 = NaN as in the reference
+    const float s0 = __fdividef(unit_dot(dt[rs], nn[rs]), clamped_norm(yy[rs]));
+    const float s0_next = __shfl_xor_sync(0xffffffffu, s0, 4);   // accumulator row + 1 (same slot, next lane group)
+    if (ch == 0 && (lane & 3) == 0) {
+      if (ok[rs] && p.out_scores) p.out_scores[pt.row_begin + rr[rs]] = s0;
+      // rows (2i, 2i+1) = (pos, neg) of one query (T == 2 whenever the loss is on)
+      if (!(g & 1) && rr[rs] + 1 < pt.n_valid) local += (double)hinge_(p.margin, s0, s0_next);
+    }
+  }
+  if (p.out_loss) {
+    local = warp_sum_d(local);
+    if (lane == 0) ctl->red[wid] = local;
+    ptx::named_bar_sync(1, C::kWorkerThreads);
+    if (threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int w = 0; w < C::kWorkerWarps; ++w) sum += ctl->red[w];
+      p.partials[pt.tile] = sum;
+    }
+  } else if (NCH == 1) {
+    // every thread's TMEM reads are done before the next tile's epilogue may overwrite the region
+    ptx::named_bar_sync(1, C::kWorkerThreads);
+  }
+}
+
+// diagnostics: CTA-level stamps (%globaltimer ns, clock64) in the LAST 256 records of the phase
+// log: record phase_cap-1-blockIdx.x, slots 2i / 2i+1 for point i (0 entry, 1 set-up done, 2 first
+// tile taken, 3 tile loop left, 4 exit)
+__device__ __forceinline__ void cta_stamp(const LaunchParams& p, int point) {
+  if (!p.phase_log || p.phase_cap < 512 || blockIdx.x >= 256) return;
+  unsigned long long* rec = p.phase_log + (size_t)(p.phase_cap - 1 - blockIdx.x) * kPhaseSlots;
+  unsigned long long gt;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+  rec[2 * point] = gt;
+  rec[2 * point + 1] = (unsigned long long)clock64();
+}
+
 // ---- worker warps ---------------------------------------------------------------------
 template <int D, int STRUCT>
 __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
@@ -345,8 +503,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
   const bool use_min = p.inter == GQE_INTER_DEEPSETS_MIN || p.inter == GQE_INTER_SIMPLE_MIN;
   const int T = p.T;
   const uint32_t tmem_base = ctl->tmem_base;
-  const uint32_t t_acc = tmem_base + ((uint32_t)(32 * (wid & 3)) << 16) + col_base;
-  const uint32_t t_agg = t_acc + D;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(32 * (wid & 3)) << 16) + col_base;
+  float* scratch = reinterpret_cast<float*>(smem + C::kOffScratch);
   const uint32_t bar_a_ready = ptx::smem_u32(&ctl->a_ready);
   const uint32_t bar_acc_full = ptx::smem_u32(&ctl->acc_full);
   const int my_r = wid * RPW + lane;               // meaningful for lane < RPW
@@ -354,6 +512,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 
   TileRing ring;
   uint32_t gs = 0;                                 // steps issued so far (a_ready / acc_full parity)
+  PendTile pend;                                   // tile whose scoring was deferred into the next tile
+  pend.valid = false;
   for (;;) {
     const int64_t tile = ring.take(ctl);
     if (tile >= p.n_tiles) break;
@@ -361,6 +521,16 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     const int structure = STRUCT >= 0 ? STRUCT : s.structure;
     const bool chain = structure <= GQE_CHAIN3;
     const int n_branch = s.n_anchor;
+    // TMEM: two regions of D columns, accumulator + running aggregate of the intersections.
+    // The roles alternate from tile to tile (the MMA issuer applies the same rule), so that the
+    // final accumulator of tile k can be scored while tile k+1's first contraction runs (its
+    // aggregate region, where tile k's result lives, is first written after that contraction).
+    const uint32_t region = (ring.k - 1) & 1u;
+    // chains are scored straight from TMEM (score_frag), intersections through the transposed
+    // tile in shared memory
+    const bool frag = chain;
+    const uint32_t t_acc = t_lane + region * D;
+    const uint32_t t_agg = t_lane + (region ^ 1u) * D;
 
     // rows of this tile
     const int64_t row_begin = (chain ? s.q_begin * T : s.q_begin) + (tile - s.tile_begin) * kRows;
@@ -373,7 +543,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     // diagnostics: per-tile phase stamps of worker thread 0 (tools/phase_report.py)
     int n_stamp = 0;
     unsigned long long* plog = nullptr;
-    if (p.phase_log && threadIdx.x == 0 && tile < p.phase_cap) {
+    if (threadIdx.x == 0 && ring.k == 1) cta_stamp(p, 2);
+    if (p.phase_log && threadIdx.x == 0 && tile < p.phase_cap - 256) {
       plog = p.phase_log + (size_t)tile * kPhaseSlots;
       uint32_t smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -409,6 +580,19 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       }
     }
 
+    PendTile cur;
+    cur.valid = false;
+    if (frag) {
+      cur.tile = tile; cur.row_begin = row_begin; cur.n_valid = n_valid; cur.region = region;
+      cur.valid = true;
+      cur.table = s.anc_table[0];
+#pragma unroll
+      for (int rs = 0; rs < 2; ++rs) {
+        const int r = frag_row(wid, lane, rs);
+        cur.idx[rs] = r < n_valid ? __ldg(p.anchor_rows + (row_begin + r) / T) : 0;
+      }
+    }
+
     for (int st = 0; st < pg.n; ++st, ++gs) {
       const int g = pg.gather[st];
       if (g != G_NONE) {
@@ -438,18 +622,29 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           }
         }
         // ... and the first-gather rows of the NEXT tile of this CTA, so that its only exposed
-        // gather is an L2 hit
+        // gather is an L2 hit (the index load is issued before, the prefetch after the deferred
+        // score, which hides the index latency)
         const int64_t nt = ring.peek(ctl, 0);
+        int32_t r2 = -1;
+        const float* tab2 = nullptr;
         if (nt < p.n_tiles && lane < RPW) {
           const SegDev& s2 = p.seg[seg_of_tile<STRUCT>(p, nt)];
           const bool chain2 = (STRUCT >= 0 ? STRUCT : s2.structure) <= GQE_CHAIN3;
           const int64_t rb2 = (chain2 ? s2.q_begin * T : s2.q_begin) + (nt - s2.tile_begin) * kRows;
           const int64_t re2 = chain2 ? s2.q_end * T : s2.q_end;
           if (rb2 + my_r < re2 && !(s2.remote_mask & (chain2 ? 8u : 1u))) {
-            const int32_t r2 = __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r);
-            ptx::tma_prefetch_l2((chain2 ? s2.tgt_table : s2.anc_table[0]) + (size_t)r2 * D, D * 4);
+            r2 = __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r);
+            tab2 = chain2 ? s2.tgt_table : s2.anc_table[0];
           }
         }
+        // the score of the previous tile, straight from its TMEM region
+        if (pend.valid) {
+          stamp(9);
+          score_frag<D>(p, ctl, scratch, tmem_base, pend, wid, lane);
+          pend.valid = false;
+          stamp(8);
+        }
+        if (r2 >= 0) ptx::tma_prefetch_l2(tab2 + (size_t)r2 * D, D * 4);
       }
 
       ptx::mbar_wait(bar_acc_full, gs & 1);
@@ -458,7 +653,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 
       const int epi = pg.epi[st];
       const int kind = epi & E_KIND;
-      if (kind == E_SCORE) { ++gs; break; }  // scored below, straight from the accumulator
+      if (kind == E_SCORE) { ++gs; break; }  // scored below (or during the next tile), straight from the accumulator
       const bool agg_read = kind == E_AGG && !(epi & F_FIRST);
       const float inv_nb = 1.f / (float)n_branch;
       uint32_t raw[16], araw[16] = {};
@@ -513,10 +708,21 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     }
 
     // ---- score ------------------------------------------------------------------------
-    // The accumulator row is the projected target (chains) or the query embedding
-    // (intersections).  It is transposed through shared memory (the A planes are dead by
-    // now) so that the table rows it is scored against are read warp-per-row with coalesced
-    // 128-bit loads, like the gathers.
+    // Scored straight from TMEM (score_frag) -- when this CTA has a next tile, only after that
+    // tile's first contraction has been handed to the tensor pipe.
+    if (frag) {
+      if (ring.peek(ctl, 0) < p.n_tiles) {
+        pend = cur;
+      } else {
+        score_frag<D>(p, ctl, scratch, tmem_base, cur, wid, lane);
+        stamp(6);
+      }
+      stamp(7);
+      continue;
+    }
+    // Simple intersections / the eval shape: the accumulator row (the query embedding) is
+    // transposed through shared memory (the A planes are dead by now) so that the target rows
+    // it is scored against are read warp-per-row with coalesced 128-bit loads.
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       uint32_t raw[16];
@@ -534,57 +740,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     // Rows are scored SU at a time: all table loads of a batch are issued first and the
     // warp reductions of the batch run in lockstep (one butterfly level for all values).
     double local = 0.0;
-    if (chain) {
-      constexpr int SU = 8 / NV;
-      static_assert(RPW % SU == 0 && SU % 2 == 0, "score batch");
-#pragma unroll 1
-      for (int u0 = 0; u0 < RPW; u0 += SU) {
-        float4 av[SU][NV];
-        int32_t arow[SU];
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-          arow[u] = __shfl_sync(0xffffffffu, ssrc0, u0 + u);  // -1: row past the end of the tile (warp-uniform)
-          const float4* a_src = reinterpret_cast<const float4*>(s.anc_table[0] + (size_t)(arow[u] < 0 ? 0 : arow[u]) * D);
-#pragma unroll
-          for (int j = 0; j < NV; ++j) av[u][j] = arow[u] < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(a_src + lane + 32 * j);
-        }
-        float red[SU][3];  // y.a, |y|^2, |a|^2
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-          const int r = wid * RPW + u0 + u;
-          float dot = 0.f, yy = 0.f, aa = 0.f;
-#pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            const float4 a = av[u][j];
-            const float4 y = *q_chunk<D>(qsm, r, lane + 32 * j);
-            dot = fmaf(y.x, a.x, dot); dot = fmaf(y.y, a.y, dot); dot = fmaf(y.z, a.z, dot); dot = fmaf(y.w, a.w, dot);
-            yy = fmaf(y.x, y.x, yy); yy = fmaf(y.y, y.y, yy); yy = fmaf(y.z, y.z, yy); yy = fmaf(y.w, y.w, yy);
-            aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
-          }
-          red[u][0] = dot; red[u][1] = yy; red[u][2] = aa;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int u = 0; u < SU; ++u)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) red[u][k] += __shfl_xor_sync(0xffffffffu, red[u][k], o);
-        }
-        float sc[SU];
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-          // cos(y, a_hat) with a_hat = a/|a| (unit norm): (y.a/|a|) / max(|y|, eps); a zero
-          // anchor row gives 0/0 = NaN as in the reference
-          sc[u] = __fdividef(unit_dot(red[u][0], red[u][2]), clamped_norm(red[u][1]));
-          if (lane == 0 && p.out_scores && arow[u] >= 0) p.out_scores[row_begin + wid * RPW + u0 + u] = sc[u];
-        }
-        if (lane == 0) {  // rows (2i, 2i+1) = (pos, neg) of one query (T == 2 whenever the loss is on)
-#pragma unroll
-          for (int u = 0; u < SU; u += 2)
-            if (arow[u + 1] >= 0) local += (double)hinge_(p.margin, sc[u], sc[u + 1]);
-        }
-      }
-    } else if (p.q_out) {
+    if (p.q_out) {
       // many targets per query: hand the query embedding rows to gqe_score_pairs
 #pragma unroll 1
       for (int u = 0; u < RPW; ++u) {
@@ -684,6 +840,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     }
     stamp(7);
   }
+  if (pend.valid) score_frag<D>(p, ctl, scratch, tmem_base, pend, wid, lane);  // (never: a deferred tile has a successor)
+  if (threadIdx.x == 0) cta_stamp(p, 3);
   loss_finish<D>(p, ctl, wid, lane);
 }
 
@@ -732,7 +890,7 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
   using C = Cfg<D>;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
   constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, D);
-  const uint32_t tmem_acc = ctl->tmem_base;
+  const uint32_t tmem_base = ctl->tmem_base;
   const uint32_t a_hi = ptx::smem_u32(smem + C::kOffAhi), a_lo = ptx::smem_u32(smem + C::kOffAlo);
   const uint32_t b0 = ptx::smem_u32(smem + C::kOffB);
   const uint32_t bar_a_ready = ptx::smem_u32(&ctl->a_ready), bar_acc_full = ptx::smem_u32(&ctl->acc_full);
@@ -742,8 +900,11 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
     const int64_t tile = ring.take(ctl);
     if (tile >= p.n_tiles) break;
     const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
+    const int structure = STRUCT >= 0 ? STRUCT : s.structure;
     Prog pg;
-    build_program(pg, STRUCT >= 0 ? STRUCT : s.structure, deepsets, s.composed != 0);
+    build_program(pg, structure, deepsets, s.composed != 0);
+    // the accumulator / aggregate roles of the two TMEM regions alternate per tile (see worker())
+    const uint32_t tmem_acc = tmem_base + ((ring.k - 1) & 1u) * D;
     for (int st = 0; st < pg.n; ++st, ++gs) {
       ptx::mbar_wait(bar_a_ready, gs & 1);
       ptx::tc_fence_after_sync();
@@ -795,6 +956,7 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + C::kOffCtl);
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) cta_stamp(p, 0);
 
   if (wid == C::kWorkerWarps && lane == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -816,6 +978,7 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
+  if (threadIdx.x == 0) cta_stamp(p, 1);
 
   if (wid < C::kWorkerWarps) {
     worker<D, STRUCT>(p, smem, ctl);
@@ -833,6 +996,7 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(ctl->tmem_base, C::kTmemCols);
   }
+  if (threadIdx.x == 0) cta_stamp(p, 4);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -849,11 +1013,12 @@ __global__ void __launch_bounds__(256) gqe_pack(const __grid_constant__ PackPara
   int n, kc;
   if (!e.chain_form) { n = item / (D / 8); kc = item % (D / 8); }
   else { kc = item / D; n = item % D; }
+  const int ns = e.perm ? score_col_src(n) : n;   // accumulator column n holds output column ns
   float x[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int k = kc * 8 + i;
-    x[i] = e.chain_form ? __ldg(e.src + (size_t)k * D + n) : __ldg(e.src + (size_t)n * D + k);
+    x[i] = e.chain_form ? __ldg(e.src + (size_t)k * D + ns) : __ldg(e.src + (size_t)ns * D + k);
   }
   uint4 hi, lo;
   split2(x[0], x[1], hi.x, lo.x);

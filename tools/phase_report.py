@@ -54,10 +54,24 @@ torch.cuda.synchronize()
 ctx.debug_set_phase_log(None, 0)
 print("step %.1f us" % (e0.elapsed_time(e1) * 1e3))
 raw = log.cpu().numpy().astype(np.uint64).reshape(n_tiles, 32)
+# CTA-level stamps (last 256 records, record n_tiles-1-cta): globaltimer ns / clock64 pairs
+cta = raw[::-1][:256].astype(np.int64)
+cta = cta[cta[:, 0] != 0]
+if len(cta):
+    gt = cta[:, 0:10:2].astype(np.float64)
+    t0 = gt[:, 0].min()
+    names = ["entry", "set-up done", "first tile taken", "tile loop left", "exit"]
+    print("CTA stamps (%d CTAs), us after the first CTA's entry (globaltimer): " % len(cta))
+    for i, nm in enumerate(names):
+        col = (gt[:, i] - t0) / 1e3
+        print("  %-17s min %7.1f  avg %7.1f  max %7.1f" % (nm, col.min(), col.mean(), col.max()))
+    print("  kernel span (first entry -> last exit) %.1f us; event-timed step above includes pack/compose" % ((gt[:, 4].max() - t0) / 1e3))
+raw = raw.copy()
+raw[-256:] = 0
 tags = (raw >> np.uint64(56)).astype(np.int64)
 clk = (raw & np.uint64((1 << 56) - 1)).astype(np.int64)
 MHZ = 1965.0
-NAMES = {2: "gather", 3: "wait MMA", 4: "epilogue", 5: "acc->smem transpose", 6: "score", 7: "loss reduce"}
+NAMES = {2: "gather", 3: "wait MMA", 4: "epilogue", 5: "acc->smem transpose", 6: "score", 7: "loss reduce", 8: "deferred score of the previous tile", 9: "hand-over + prefetch issue"}
 STRUCT = ["1-chain", "2-chain", "3-chain", "2-inter", "3-inter", "3-inter_chain", "3-chain_inter"]
 by_struct = {}
 for t in range(n_tiles):
@@ -88,7 +102,7 @@ for s in sorted(by_struct):
     n = v["n"]
     print("%-14s tiles=%4d  avg tile %.1f us:" % (STRUCT[s], n, v["total"] / n), end="")
     print("  first gather %.1f" % (v["first_gather"] / n), end="")
-    for k in (2, 3, 4, 5, 6, 7):
+    for k in (2, 9, 8, 3, 4, 5, 6, 7):
         if k in v:
             print(" | %s %.1f (x%.1f)" % (NAMES[k], v[k] / n, v.get("cnt%d" % k, 0) / n - (1 if k == 2 else 0)), end="")
     print()
