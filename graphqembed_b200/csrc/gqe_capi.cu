@@ -585,13 +585,15 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
         // depends on another one)
         if (deps) GQE_CUDA(c, cudaMemsetAsync(c->compose_done, 0, n_cw * sizeof(unsigned int), c->stream));
         cw.done = c->compose_done;
-        cw.target = (unsigned int)((c->d / 64) * (c->d / 64));
+        cw.target = (unsigned int)((c->d / 64) * (c->d / compose_tile_rows()));   // tiles per product
         GQE_CUDA(c, launch_compose(c->d, cw, n_cw, c->stream));
         c->launches += 1;
       }
       pp.dst = c->packed;
-      GQE_CUDA(c, launch_pack(c->d, pp, n_pack, c->stream));
+      // (the wait for the index copies sits before gqe_pack: the fused kernel is launched
+      // programmatically dependent on gqe_pack and must follow it directly in the stream)
       if (int rc = wait_for_indices()) return rc;
+      GQE_CUDA(c, launch_pack(c->d, pp, n_pack, c->stream));
       GQE_CUDA(c, launch_fused_tc(c->d, structure, lp, tiles, c->stream));
       c->launches += 2;
     } else {

@@ -8,7 +8,7 @@
 // FFMA), so it runs on the warp-level tensor-core path (wmma, bf16 operands, fp32 accumulate)
 // with the same hi/lo split as the fused kernel: c = a_hi b_hi + a_lo b_hi + a_hi b_lo,
 // ~2^-17 relative.  One CTA = one 64x64 tile of one product; the whole K extent of both
-// operands is fetched in one round of loads; a launch computes up to 64 independent products.
+// operands is fetched in one round of loads; a launch computes up to 96 products.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <mma.h>
@@ -18,10 +18,11 @@
 
 namespace gqe {
 
-template <int D>
+// tile: kComposeRows rows (of a) x 64 columns (of b)
+template <int D, int kComposeRows>
 struct ComposeSmem {
-  __nv_bfloat16 a_hi[64][D + 8], a_lo[64][D + 8];   // a[i0 .. i0+64)[0 .. D)
-  __nv_bfloat16 b_hi[D][64 + 8], b_lo[D][64 + 8];   // b[0 .. D)[j0 .. j0+64)
+  __nv_bfloat16 a_hi[kComposeRows][D + 8], a_lo[kComposeRows][D + 8];   // a[i0 .. i0+128)[0 .. D)
+  __nv_bfloat16 b_hi[D][64 + 8], b_lo[D][64 + 8];                       // b[0 .. D)[j0 .. j0+64)
 };
 
 __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* lo, const float4 v) {
@@ -36,19 +37,21 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* l
 
 constexpr int kComposeThreads = 512;
 
-template <int D>
+template <int D, int kComposeRows>
 __global__ void __launch_bounds__(kComposeThreads, 1) gqe_compose(const __grid_constant__ ComposeParams p) {
   using namespace nvcuda;
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  ComposeSmem<D>& sm = *reinterpret_cast<ComposeSmem<D>*>(smem_raw);
+  ComposeSmem<D, kComposeRows>& sm = *reinterpret_cast<ComposeSmem<D, kComposeRows>*>(smem_raw);
+  constexpr int NH = kComposeRows / 64;
   const ComposeEntry& e = p.e[blockIdx.z];
-  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int i0 = blockIdx.y * kComposeRows, j0 = blockIdx.x * 64;
   // Every load of an operand tile is issued before its first shared store (N float4 per thread
   // in registers), so the CTA pays ~one memory latency per operand.  A three-factor run names
   // the product it consumes (dep_a / dep_b): its CTAs have a LOWER blockIdx.z, were dispatched
   // before this one and cannot be starved by it; the plain operand is fetched first, then the
-  // CTA waits until all (D/64)^2 tiles of the other one are stored.
-  constexpr int N = 64 * D / 4 / kComposeThreads;   // float4 per thread per operand (8 at d = 256)
+  // CTA waits until all tiles of the other one are stored.
+  constexpr int NA = kComposeRows * D / 4 / kComposeThreads;   // float4 per thread of a (16 at d = 256)
+  constexpr int N = 64 * D / 4 / kComposeThreads;              // float4 per thread of b (8 at d = 256)
   auto wait_for = [&](int dep) {
     if (threadIdx.x == 0) {
       while ((int)(*reinterpret_cast<volatile unsigned int*>(p.done + dep) - p.target) < 0) __nanosleep(32);
@@ -56,9 +59,9 @@ __global__ void __launch_bounds__(kComposeThreads, 1) gqe_compose(const __grid_c
     }
     __syncthreads();
   };
-  auto load_a = [&](float4 (&v)[N]) {   // (__ldcg: a product of this very launch must not come from a stale L1 line)
+  auto load_a = [&](float4 (&v)[NA]) {   // (__ldcg: a product of this very launch must not come from a stale L1 line)
 #pragma unroll
-    for (int u = 0; u < N; ++u) {
+    for (int u = 0; u < NA; ++u) {
       const int idx = threadIdx.x + u * kComposeThreads;
       v[u] = __ldcg(reinterpret_cast<const float4*>(e.a + (size_t)(i0 + idx / (D / 4)) * D) + idx % (D / 4));
     }
@@ -70,63 +73,79 @@ __global__ void __launch_bounds__(kComposeThreads, 1) gqe_compose(const __grid_c
       v[u] = __ldcg(reinterpret_cast<const float4*>(e.b + (size_t)(idx / 16) * D + j0) + idx % 16);
     }
   };
-  float4 va[N], vb[N];
+  float4 va[NA], vb[N];
   if (e.dep_a < 0) load_a(va);
   if (e.dep_b < 0) load_b(vb);
   if (e.dep_a >= 0) { wait_for(e.dep_a); load_a(va); }
   if (e.dep_b >= 0) { wait_for(e.dep_b); load_b(vb); }
 #pragma unroll
-  for (int u = 0; u < N; ++u) {
+  for (int u = 0; u < NA; ++u) {
     const int idx = threadIdx.x + u * kComposeThreads;
     split_store4(&sm.a_hi[idx / (D / 4)][4 * (idx % (D / 4))], &sm.a_lo[idx / (D / 4)][4 * (idx % (D / 4))], va[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const int idx = threadIdx.x + u * kComposeThreads;
     split_store4(&sm.b_hi[idx / 16][4 * (idx % 16)], &sm.b_lo[idx / 16][4 * (idx % 16)], vb[u]);
   }
   __syncthreads();
-  // warp w (16 warps): rows 16 (w / 4) .. +16, columns 16 (w % 4) .. +16
+  // warp w (16 warps): rows 16 (w / 4) .. +16 and 64 + 16 (w / 4) .. +16, columns 16 (w % 4) .. +16
   const int w = threadIdx.x >> 5;
   const int r0 = 16 * (w >> 2), c0 = 16 * (w & 3);
-  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
-  wmma::fill_fragment(acc, 0.f);
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) wmma::fill_fragment(acc[h], 0.f);
 #pragma unroll 4
   for (int k = 0; k < D; k += 16) {
-    wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> ah, al;
     wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bh, bl;
-    wmma::load_matrix_sync(ah, &sm.a_hi[r0][k], D + 8);
-    wmma::load_matrix_sync(al, &sm.a_lo[r0][k], D + 8);
     wmma::load_matrix_sync(bh, &sm.b_hi[k][c0], 64 + 8);
     wmma::load_matrix_sync(bl, &sm.b_lo[k][c0], 64 + 8);
-    wmma::mma_sync(acc, ah, bh, acc);
-    wmma::mma_sync(acc, al, bh, acc);
-    wmma::mma_sync(acc, ah, bl, acc);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> ah, al;
+      wmma::load_matrix_sync(ah, &sm.a_hi[r0 + 64 * h][k], D + 8);
+      wmma::load_matrix_sync(al, &sm.a_lo[r0 + 64 * h][k], D + 8);
+      wmma::mma_sync(acc[h], ah, bh, acc[h]);
+      wmma::mma_sync(acc[h], al, bh, acc[h]);
+      wmma::mma_sync(acc[h], ah, bl, acc[h]);
+    }
   }
-  wmma::store_matrix_sync(e.dst + (size_t)(i0 + r0) * D + j0 + c0, acc, D, wmma::mem_row_major);
+#pragma unroll
+  for (int h = 0; h < NH; ++h)
+    wmma::store_matrix_sync(e.dst + (size_t)(i0 + r0 + 64 * h) * D + j0 + c0, acc[h], D, wmma::mem_row_major);
   // publish this tile
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) atomicAdd(p.done + blockIdx.z, 1u);
 }
 
-template <int D>
+template <int D, int ROWS>
 static cudaError_t launch_compose_t(const ComposeParams& cp, int n_entries, cudaStream_t st) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gqe_compose<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ComposeSmem<D>));
+    cudaError_t e = cudaFuncSetAttribute(gqe_compose<D, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(ComposeSmem<D, ROWS>));
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  const dim3 grid(D / 64, D / 64, (unsigned)n_entries);
-  gqe_compose<D><<<grid, kComposeThreads, sizeof(ComposeSmem<D>), st>>>(cp);
+  const dim3 grid(D / 64, D / ROWS, (unsigned)n_entries);
+  gqe_compose<D, ROWS><<<grid, kComposeThreads, sizeof(ComposeSmem<D, ROWS>), st>>>(cp);
   return cudaGetLastError();
 }
+
+// 64-row tiles: 160 CTAs for the 10 products of the benchmark mix (one CTA per SM: a second,
+// small wave).  128-row tiles (80 CTAs, one wave) were measured 8 us SLOWER per call: the time of
+// a CTA is its load -> split -> smem -> MMA chain, which grows with the tile.
+int compose_tile_rows() { return 64; }
 
 cudaError_t launch_compose(int d, const ComposeParams& cp, int n_entries, cudaStream_t st) {
   if (n_entries <= 0) return cudaSuccess;
   switch (d) {
-    case 128: return launch_compose_t<128>(cp, n_entries, st);
-    case 256: return launch_compose_t<256>(cp, n_entries, st);
+    case 128: return launch_compose_t<128, 64>(cp, n_entries, st);
+    case 256: return launch_compose_t<256, 64>(cp, n_entries, st);
     default: return cudaErrorInvalidValue;
   }
 }

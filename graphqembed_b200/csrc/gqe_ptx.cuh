@@ -57,6 +57,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// ---- programmatic dependent launch -------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the
+// kernel before it in the stream is still running (once every CTA of that kernel has executed
+// launch_dependents or exited); griddep_wait() blocks until that kernel has completed and its
+// writes are visible.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMEM allocation (one full warp executes these) -------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t n_cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(n_cols) : "memory");

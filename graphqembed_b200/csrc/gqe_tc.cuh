@@ -862,6 +862,10 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
   };
   int64_t tile = blockIdx.x;
   publish(0, tile);
+  // The packed weights come from gqe_pack, the kernel before this one in the stream; this kernel
+  // is launched programmatically dependent on it, so that the set-up and the first gathers of
+  // the workers (tables and indices only) overlap its tail.  Only this thread reads weights.
+  ptx::griddep_wait();
   for (uint32_t k = 0; tile < p.n_tiles; ++k) {
     const int64_t next = (int64_t)gridDim.x + (int64_t)atomicAdd(p.tile_counter, 1u);
     publish(k + 1, next < p.n_tiles ? next : p.n_tiles);
@@ -1006,6 +1010,7 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
 //   !chain_form : M.mm(embeds)    (decoders.py:150,289,299)
 template <int D>
 __global__ void __launch_bounds__(256) gqe_pack(const __grid_constant__ PackParams p) {
+  ptx::griddep_launch_dependents();   // the fused kernel may start its set-up and first gathers now
   const PackEntry& e = p.e[blockIdx.y];
   uint8_t* out = p.dst + (size_t)blockIdx.y * Cfg<D>::kPackedBytes;
   const int item = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 k) of one n

@@ -1,6 +1,8 @@
 // gqe_tc_inst.cuh -- instantiates the tensor-core kernels for ONE embedding
 // dimension (GQE_DIM = 128 or 256).
 #pragma once
+#include <cstdlib>
+
 #include "gqe_launch.h"
 #include "gqe_tc.cuh"
 
@@ -29,8 +31,20 @@ static cudaError_t tc_launch_one(const LaunchParams& lp, int64_t tiles, cudaStre
     configured[dev] = true;
   }
   const int64_t grid = tiles < slots[dev] ? tiles : slots[dev];
-  kern<<<(unsigned)grid, tc::Cfg<D>::kThreads, tc::Cfg<D>::kSmemBytes, st>>>(lp);
-  return cudaGetLastError();
+  // programmatic dependent launch on gqe_pack (see tc::producer); GQE_PDL=0 in the environment
+  // turns it off (diagnostics: measured 2.6 us per call on the benchmark mix)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(tc::Cfg<D>::kThreads);
+  cfg.dynamicSmemBytes = tc::Cfg<D>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int pdl = [] { const char* e = std::getenv("GQE_PDL"); return e ? std::atoi(e) : 1; }();
+  attr[0].val.programmaticStreamSerializationAllowed = pdl;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, lp);
 }
 
 template <int D>
