@@ -62,6 +62,9 @@ struct gqe_ctx {
   double* partials = nullptr;
   int64_t partials_cap = 0;
   double* loss_acc = nullptr;
+  bool loss_dirty = false;     // *loss_acc may be non-zero (a call failed between its launches)
+  float* h_loss = nullptr;     // mapped pinned word the kernels write the loss of a *_host call to
+  float* h_loss_dev = nullptr;
   unsigned int* ticket = nullptr;
   unsigned int* tile_counter = nullptr;
 
@@ -173,6 +176,7 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   cudaFree(c->ticket);
   cudaFree(c->tile_counter);
   for (void* p : c->stage) cudaFree(p);
+  if (c->h_loss) cudaFreeHost(c->h_loss);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->h2d_done) cudaEventDestroy(c->h2d_done);
   if (c->stream_idle) cudaEventDestroy(c->stream_idle);
@@ -356,7 +360,9 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
   GQE_CUDA(c, cudaSetDevice(c->device));
 
   if (out_loss) {
-    GQE_CUDA(c, cudaMemsetAsync(c->loss_acc, 0, sizeof(double), c->stream));
+    // the last launch of a call leaves the accumulator zeroed (LaunchParams::final_launch)
+    if (c->loss_dirty) GQE_CUDA(c, cudaMemsetAsync(c->loss_acc, 0, sizeof(double), c->stream));
+    c->loss_dirty = false;
     // mean over an empty batch is NaN in the reference (torch mean of an empty tensor)
     if (nq_total == 0) GQE_CUDA(c, cudaMemsetAsync(out_loss, 0xFF, sizeof(float), c->stream));
   }
@@ -432,6 +438,9 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     }
   }
 
+  int32_t last_nonempty = -1;
+  for (int32_t k = 0; k < n_segs; ++k)
+    if (segs[k].query_end > segs[k].query_begin) last_nonempty = k;
   int32_t i = 0;
   while (i < n_segs) {
     int n = 0;
@@ -563,7 +572,9 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     }
     lp.n_segs = n;
     lp.n_tiles = tiles;
+    lp.final_launch = i > last_nonempty ? 1 : 0;
     if (out_loss) {
+      c->loss_dirty = true;   // until the final launch of the call has been issued
       int rc = ensure_partials(c, tiles);
       if (rc != GQE_OK) return rc;
       lp.partials = c->partials;
@@ -601,6 +612,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       GQE_CUDA(c, launch_fused_simt(c->d, structure, lp, tiles, c->stream));
       c->launches += 1;
     }
+    if (out_loss && lp.final_launch) c->loss_dirty = false;
     if (pairs_mode) {
       PairParams qp;
       std::memset(&qp, 0, sizeof qp);
@@ -701,6 +713,16 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
   if (target_offsets && (rc = stage_reserve(c, ST_OFFSETS, sizeof(int64_t) * (size_t)(nq + 1))) != GQE_OK) return rc;
   if (out_scores && (rc = stage_reserve(c, ST_SCORES, sizeof(float) * (size_t)n_pairs)) != GQE_OK) return rc;
   if (out_loss && (rc = stage_reserve(c, ST_LOSS, sizeof(float))) != GQE_OK) return rc;
+  // The loss goes straight to a mapped pinned word (one posted write by the last CTA) instead of
+  // a device word + a D2H copy: one stream operation less on the critical path of the call.
+  float* loss_dst = out_loss ? (float*)c->stage[ST_LOSS] : nullptr;
+  if (out_loss && nq > 0) {
+    if (!c->h_loss) {
+      GQE_CUDA(c, cudaHostAlloc((void**)&c->h_loss, sizeof(float), cudaHostAllocMapped));
+      GQE_CUDA(c, cudaHostGetDevicePointer((void**)&c->h_loss_dev, c->h_loss, 0));
+    }
+    loss_dst = c->h_loss_dev;
+  }
   if (nq > 0) {
     if (!anchor_rows || !target_rows) return fail(c, GQE_ERR_INVALID, "index arrays are null");
     if (!c->copy_stream) {
@@ -723,7 +745,7 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
   }
   rc = run_fused(c, segs, n_segs, nq, (const int32_t*)c->stage[ST_ANCHOR], n_pairs, (const int32_t*)c->stage[ST_TARGET],
                  target_offsets ? (const int64_t*)c->stage[ST_OFFSETS] : nullptr, T,
-                 out_scores ? (float*)c->stage[ST_SCORES] : nullptr, margin, out_loss ? (float*)c->stage[ST_LOSS] : nullptr);
+                 out_scores ? (float*)c->stage[ST_SCORES] : nullptr, margin, loss_dst);
   if (c->wait_h2d) {   // nothing consumed the indices (empty batch / early error): keep the streams ordered
     cudaStreamWaitEvent(c->stream, c->h2d_done, 0);
     c->wait_h2d = false;
@@ -732,9 +754,11 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
   if (out_scores && n_pairs > 0)
     GQE_CUDA(c, cudaMemcpyAsync(out_scores, c->stage[ST_SCORES], sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost,
                                 c->stream));
-  if (out_loss)
+  const bool mapped_loss = out_loss && loss_dst == c->h_loss_dev;
+  if (out_loss && !mapped_loss)
     GQE_CUDA(c, cudaMemcpyAsync(out_loss, c->stage[ST_LOSS], sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (mapped_loss) *out_loss = *(volatile float*)c->h_loss;
   return GQE_OK;
 }
 

@@ -50,6 +50,7 @@ struct LaunchParams {
   double inv_q;
   double* partials;   // [gridDim.x]
   double* loss_acc;   // running sum across the launches of one call
+  int32_t final_launch;  // last launch of the call: leave *loss_acc zeroed for the next call
   unsigned int* ticket;
   // many targets per query (the eval shape): intersection tiles write their query
   // embedding rows here (fp32 [n_queries_total, D]) instead of scoring; gqe_score_pairs

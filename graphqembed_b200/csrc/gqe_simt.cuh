@@ -223,7 +223,7 @@ __device__ __forceinline__ void loss_reduce(const LaunchParams& p, TileSmem<D>& 
     s = warp_sum(s);
     if (lane == 0) {
       const double acc = *p.loss_acc + s;
-      *p.loss_acc = acc;
+      *p.loss_acc = p.final_launch ? 0.0 : acc;
       *p.out_loss = (float)(acc * p.inv_q);
       *p.ticket = 0u;
     }

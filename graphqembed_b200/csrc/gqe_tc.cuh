@@ -316,7 +316,7 @@ __device__ __forceinline__ void loss_finish(const LaunchParams& p, Ctl* ctl, int
       s = warp_sum_d(s);
       if (lane == 0) {
         const double acc = *p.loss_acc + s;
-        *p.loss_acc = acc;
+        *p.loss_acc = p.final_launch ? 0.0 : acc;
         *p.out_loss = (float)(acc * p.inv_q);
       }
     }
