@@ -416,6 +416,37 @@ def test_operator_precomposition_stays_within_tolerance(d, inter):
         assert np.abs(_np(scores) - plain).max() < 2e-5, s
 
 
+@pytest.mark.parametrize("d", [128, 256])
+@pytest.mark.parametrize("n_neg", [1, 2])
+def test_many_chain_tiles_per_cta_tc_matches_fp32(d, n_neg):
+    """Chain tiles are scored straight from TMEM, one tile late (while the CTA's next tile is on the
+    tensor pipe).  That only happens when a CTA owns several tiles: 20 000 queries x (1 + n_neg)
+    targets = 300+ tiles per structure on 148 SMs, a ragged last tile, odd and even targets per
+    query.  Every score of the tensor-core kernels against the exact-fp32 kernels, plus the fused
+    margin loss (regular (pos, neg) layout only)."""
+    nq = 20011
+    case = make_case(seed=900 + d + n_neg, d=d, decoder="bilinear", inter="mean", n_queries=nq, n_neg=n_neg,
+                     nodes_per_mode=3000, structures=("1-chain", "2-chain", "3-chain"))
+    model = build_package_model(case)
+    for compose in ("auto", "off"):
+        model.compose = compose
+        for s in case.batches:
+            b = case.batches[s]
+            targets = np.concatenate([b["target"][:, None], b["negs"]], axis=1)
+            batch = query_batch(case, s, targets)
+            model.precision = "fp32"
+            ref = _np(model.score_batch(batch))
+            model.precision = "bf16x3"
+            got = _np(model.score_batch(batch))
+            assert np.isfinite(got).all()
+            assert np.abs(got - ref).max() < 2e-5, (s, compose)
+            if n_neg == 1:
+                loss, scores = model.margin_loss_batch(batch, margin=1, return_scores=True)
+                np.testing.assert_array_equal(_np(scores).reshape(-1), got.reshape(-1))
+                sc = got.reshape(nq, 2).astype(np.float64)
+                assert abs(loss.item() - np.maximum(0.0, 1.0 - (sc[:, 0] - sc[:, 1])).mean()) < 1e-6
+
+
 def _oracle_grads(case, s, neg_nodes, margin=1.0):
     """d loss / d parameters from torch autograd over the oracle, in float64."""
     orc = case.oracle(dtype=torch.float64)

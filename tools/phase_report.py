@@ -65,6 +65,9 @@ if len(cta):
     for i, nm in enumerate(names):
         col = (gt[:, i] - t0) / 1e3
         print("  %-17s min %7.1f  avg %7.1f  max %7.1f" % (nm, col.min(), col.mean(), col.max()))
+    ck = cta[:, 1:10:2].astype(np.float64)
+    mhz = (ck[:, 3] - ck[:, 1]) / np.maximum(gt[:, 3] - gt[:, 1], 1.0) * 1e3
+    print("  SM clock inside the tile loop (clock64 / globaltimer): median %.0f MHz (tile times below assume %.0f)" % (np.median(mhz), 1965.0))
     print("  kernel span (first entry -> last exit) %.1f us; event-timed step above includes pack/compose" % ((gt[:, 4].max() - t0) / 1e3))
 raw = raw.copy()
 raw[-256:] = 0
