@@ -53,6 +53,8 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 
 // ---- fences ---------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+// one 128-byte line into L2 through the load/store path (no TMA descriptor traffic)
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -492,6 +492,23 @@ __device__ __forceinline__ void cta_stamp(const LaunchParams& p, int point) {
   rec[2 * point + 1] = (unsigned long long)clock64();
 }
 
+// L2 prefetch of the table rows a warp will need later (lane i < RPW holds the row of tile row
+// wid*RPW + i, -1: none).  One 128-byte line per lane and instruction through the load/store
+// path: the warp's RPW rows are RPW * D/32 = 64 lines = two instructions with all lanes active.
+// [The bulk-copy prefetch (cp.async.bulk.prefetch.L2, one per row) is issued lane by lane --
+// ~0.5 us of warp time per instruction -- and queues in the TMA unit in front of the weight
+// stages of the running contraction.]
+template <int D>
+__device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ table, int32_t my_row, int lane) {
+  constexpr int LINES = D / 32;   // 128-byte lines per row
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = lane + 32 * i;
+    const int32_t row = __shfl_sync(0xffffffffu, my_row, idx / LINES);
+    if (row >= 0) ptx::prefetch_l2_line(table + (size_t)row * D + (idx % LINES) * 32);
+  }
+}
+
 // ---- worker warps ---------------------------------------------------------------------
 template <int D, int STRUCT>
 __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
@@ -571,7 +588,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     if (chain) {
       if (mine) {
         gsrc0 = __ldg(p.target_rows + row_begin + my_r);
-        ssrc0 = __ldg(p.anchor_rows + (row_begin + my_r) / T);
+        ssrc0 = __ldg(p.anchor_rows + (T == 2 ? (row_begin + my_r) >> 1 : (row_begin + my_r) / T));
       }
     } else if (mine) {
       gsrc0 = __ldg(p.anchor_rows + row_begin + my_r);
@@ -592,7 +609,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 #pragma unroll
       for (int rs = 0; rs < 2; ++rs) {
         const int r = frag_row(wid, lane, rs);
-        cur.idx[rs] = r < n_valid ? __ldg(p.anchor_rows + (row_begin + r) / T) : 0;
+        cur.idx[rs] = r < n_valid ? __ldg(p.anchor_rows + (T == 2 ? (row_begin + r) >> 1 : (row_begin + r) / T)) : 0;
       }
     }
 
@@ -612,16 +629,14 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       if (st == 0) {
         // while the first contraction runs: the L2 prefetches of this tile's later rows (issued
         // only now, so that they do not queue in front of the first gather's own loads) ...
-        if (mine) {
-          if (chain) {
-            if (!(rm & 1u)) ptx::tma_prefetch_l2(s.anc_table[0] + (size_t)ssrc0 * D, D * 4);
-          } else {
-            if (!(rm & 2u)) ptx::tma_prefetch_l2(s.anc_table[1] + (size_t)gsrc1 * D, D * 4);
-            if (n_branch > 2 && !(rm & 4u)) ptx::tma_prefetch_l2(s.anc_table[2] + (size_t)gsrc2 * D, D * 4);
-            if (!(rm & 8u) && !p.q_out) {
-              ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc0 * D, D * 4);
-              if (T > 1) ptx::tma_prefetch_l2(s.tgt_table + (size_t)ssrc1 * D, D * 4);
-            }
+        if (chain) {
+          if (!(rm & 1u)) prefetch_rows_l2<D>(s.anc_table[0], ssrc0, lane);
+        } else {
+          if (!(rm & 2u)) prefetch_rows_l2<D>(s.anc_table[1], gsrc1, lane);
+          if (n_branch > 2 && !(rm & 4u)) prefetch_rows_l2<D>(s.anc_table[2], gsrc2, lane);
+          if (!(rm & 8u) && !p.q_out) {
+            prefetch_rows_l2<D>(s.tgt_table, ssrc0, lane);
+            if (T > 1) prefetch_rows_l2<D>(s.tgt_table, ssrc1, lane);
           }
         }
         // ... and the first-gather rows of the NEXT tile of this CTA, so that its only exposed
@@ -630,14 +645,14 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
         const int64_t nt = ring.peek(ctl, 0);
         int32_t r2 = -1;
         const float* tab2 = nullptr;
-        if (nt < p.n_tiles && lane < RPW) {
+        if (nt < p.n_tiles) {
           const SegDev& s2 = p.seg[seg_of_tile<STRUCT>(p, nt)];
           const bool chain2 = (STRUCT >= 0 ? STRUCT : s2.structure) <= GQE_CHAIN3;
           const int64_t rb2 = (chain2 ? s2.q_begin * T : s2.q_begin) + (nt - s2.tile_begin) * kRows;
           const int64_t re2 = chain2 ? s2.q_end * T : s2.q_end;
-          if (rb2 + my_r < re2 && !(s2.remote_mask & (chain2 ? 8u : 1u))) {
-            r2 = __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r);
+          if (!(s2.remote_mask & (chain2 ? 8u : 1u))) {
             tab2 = chain2 ? s2.tgt_table : s2.anc_table[0];
+            if (lane < RPW && rb2 + my_r < re2) r2 = __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r);
           }
         }
         // the score of the previous tile, straight from its TMEM region
@@ -647,7 +662,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           pend.valid = false;
           stamp(8);
         }
-        if (r2 >= 0) ptx::tma_prefetch_l2(tab2 + (size_t)r2 * D, D * 4);
+        if (tab2) prefetch_rows_l2<D>(tab2, r2, lane);
       }
 
       ptx::mbar_wait(bar_acc_full, gs & 1);
