@@ -82,7 +82,13 @@ static_assert(sizeof(Ctl) <= 512, "control block");
 // ---- the per-structure program --------------------------------------------------
 enum { G_NONE = 7, G_TARGET = 3 };                       // gather source: anchor 0..2, target, none
 enum { M_REL0 = 0, M_REL1 = 1, M_REL2 = 2, M_PRE = 3, M_POST = 4 };
-enum { E_TO_A = 0, E_AGG = 1, E_SCORE = 2, E_KIND = 3, F_RELU = 4, F_FIRST = 8, F_LAST = 16, F_DEST_ACC = 32 };
+// epilogue kinds (E_KIND masks them) and flags.  E_NONE: the accumulator is left in TMEM, raw,
+// for the NEXT step's epilogue (first DeepSets branch).  F_MMA_ALT: this step's MMAs write the
+// tile's second TMEM region, so that the raw first branch (F_AGG_RAW) or the running aggregate
+// in the first region survives; the epilogue then combines the two and keeps the aggregate in
+// the first region.
+enum { E_TO_A = 0, E_AGG = 1, E_SCORE = 2, E_NONE = 3, E_KIND = 3, F_RELU = 4, F_FIRST = 8, F_LAST = 16, F_DEST_ACC = 32,
+       F_AGG_RAW = 64, F_MMA_ALT = 128 };
 
 struct Prog {
   int n;
@@ -116,7 +122,11 @@ __device__ __forceinline__ void build_program(Prog& pg, int structure, bool deep
       const int pos = (b == 0 ? F_FIRST : 0) | (b == nb - 1 ? F_LAST : 0);
       const int agg_simple = E_AGG | pos | ((b == nb - 1 && structure != GQE_CHAIN_INTER3) ? F_DEST_ACC : 0);
       if (composed) {
-        push(b, b, deepsets ? (E_AGG | F_RELU | pos) : agg_simple);
+        // DeepSets: the first branch has no epilogue of its own -- its accumulator stays in TMEM
+        // and the second branch's epilogue applies relu to both (one TMEM pass and one
+        // workers <-> issuer round trip less per tile)
+        if (deepsets) push(b, b, b == 0 ? E_NONE : (E_AGG | F_RELU | F_MMA_ALT | (b == 1 ? F_AGG_RAW : 0) | (b == nb - 1 ? F_LAST : 0)));
+        else push(b, b, agg_simple);
         continue;
       }
       if (structure == GQE_INTER_CHAIN3 && b == 1) {
@@ -672,11 +682,16 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       const int epi = pg.epi[st];
       const int kind = epi & E_KIND;
       if (kind == E_SCORE) { ++gs; break; }  // scored below (or during the next tile), straight from the accumulator
+      if (kind == E_NONE) continue;          // left in TMEM for the next step's epilogue
       const bool agg_read = kind == E_AGG && !(epi & F_FIRST);
+      const bool agg_raw = (epi & F_AGG_RAW) != 0;
+      // this step's accumulator / the running aggregate (roles swapped for F_MMA_ALT steps)
+      const uint32_t t_x = (epi & F_MMA_ALT) ? t_agg : t_acc;
+      const uint32_t t_a = (epi & F_MMA_ALT) ? t_acc : t_agg;
       const float inv_nb = 1.f / (float)n_branch;
       uint32_t raw[16], araw[16] = {};
-      ptx::tmem_ld16(t_acc, raw);
-      if (agg_read) ptx::tmem_ld16(t_agg, araw);
+      ptx::tmem_ld16(t_x, raw);
+      if (agg_read) ptx::tmem_ld16(t_a, araw);
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         float x[16], a[16];
@@ -687,8 +702,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           a[i] = __uint_as_float(araw[i]);
         }
         if (ch + 1 < NCH) {  // next chunk streams out of TMEM while this one is processed
-          ptx::tmem_ld16(t_acc + 16 * (ch + 1), raw);
-          if (agg_read) ptx::tmem_ld16(t_agg + 16 * (ch + 1), araw);
+          ptx::tmem_ld16(t_x + 16 * (ch + 1), raw);
+          if (agg_read) ptx::tmem_ld16(t_a + 16 * (ch + 1), araw);
         }
         if (kind == E_AGG) {
           if (epi & F_RELU) {
@@ -696,6 +711,10 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
             for (int i = 0; i < 16; ++i) x[i] = relu_nan_(x[i]);
           }
           if (agg_read) {
+            if (agg_raw) {  // the first branch's accumulator, not yet through its relu
+#pragma unroll
+              for (int i = 0; i < 16; ++i) a[i] = relu_nan_(a[i]);
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) x[i] = use_min ? min_nan_(a[i], x[i]) : a[i] + x[i];
           }
@@ -703,7 +722,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
             uint32_t o[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(x[i]);
-            ptx::tmem_st16(t_agg + 16 * ch, o);
+            ptx::tmem_st16(t_a + 16 * ch, o);
             continue;
           }
           if (!use_min) {  // torch.mean over the stacked operands
@@ -926,8 +945,10 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
     Prog pg;
     build_program(pg, structure, deepsets, s.composed != 0);
     // the accumulator / aggregate roles of the two TMEM regions alternate per tile (see worker())
-    const uint32_t tmem_acc = tmem_base + ((ring.k - 1) & 1u) * D;
+    const uint32_t tmem_main = tmem_base + ((ring.k - 1) & 1u) * D;
+    const uint32_t tmem_alt = tmem_base + (ring.k & 1u) * D;
     for (int st = 0; st < pg.n; ++st, ++gs) {
+      const uint32_t tmem_acc = (pg.epi[st] & F_MMA_ALT) ? tmem_alt : tmem_main;
       ptx::mbar_wait(bar_a_ready, gs & 1);
       ptx::tc_fence_after_sync();
 #pragma unroll 1
