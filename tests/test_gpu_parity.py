@@ -177,7 +177,7 @@ def test_grouped_launch_matches_per_formula_calls():
     model = build_package_model(case)
     batches, per_scores, per_n = [], [], []
     rng = np.random.RandomState(3)
-    for rep in range(3):                     # 21 segments > 16: exercises the multi-launch split
+    for rep in range(6):                     # 42 segments > 32 (kMaxSegs): two launches, one loss accumulator
         for s in STRUCTURES:
             b = case.batches[s]
             n = int(rng.randint(1, 150))
@@ -192,7 +192,10 @@ def test_grouped_launch_matches_per_formula_calls():
     want_loss = np.maximum(0, 1 - (want[:, 0] - want[:, 1])).mean()
     assert abs(loss.item() - want_loss) <= 1e-6
     loss_only = model.margin_loss_grouped(batches, margin=1)
-    assert loss_only.item() == loss.item()                     # deterministic reduction
+    assert loss_only.item() == loss.item()                     # deterministic reduction, accumulator left clean
+    half = model.margin_loss_grouped(batches[:7], margin=1)    # a one-launch call after a two-launch one
+    w7 = np.concatenate(per_scores[:7])
+    assert abs(half.item() - np.maximum(0, 1 - (w7[:, 0] - w7[:, 1])).mean()) <= 1e-6
 
 
 def test_host_buffer_entry_points_match_device_ones(small):
