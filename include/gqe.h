@@ -137,10 +137,14 @@ typedef enum gqe_compose_mode { GQE_COMPOSE_OFF = 0, GQE_COMPOSE_AUTO = 1, GQE_C
 int gqe_set_compose(gqe_ctx* ctx, int32_t mode);
 /* Message of the last failure on ctx (ctx == NULL: last gqe_create failure). */
 const char* gqe_last_error(const gqe_ctx* ctx);
-/* Diagnostics: while `log` (DEVICE uint64 [n_tiles][32]) is set, thread 0 of every tile of the
- * tensor-core kernel records (tag << 56 | SM clock) stamps at its phase boundaries
- * (tags: 1+16*structure start, 2 gather done, 3 contraction done, 4 epilogue done,
- * 5 transposed, 6 scored, 7 end); tools/phase_report.py decodes them.  NULL / 0 turns it off. */
+/* Diagnostics: while `log` (DEVICE uint64 [n_records][32], zeroed by the caller) is set, thread 0
+ * of every tile < n_records - 256 of the tensor-core kernel records (tag << 56 | SM clock) stamps
+ * at its phase boundaries (tags: 1+16*structure start, 2 gather done, 9 A operand handed over and
+ * prefetches issued, 8 previous chain tile scored, 3 contraction done, 4 epilogue done,
+ * 5 transposed, 6 scored, 7 end; slot 31 = %smid), and, when n_records >= 512, CTA b writes
+ * (%globaltimer ns, clock64) pairs into record n_records-1-b at kernel entry, set-up done, first
+ * tile taken, tile loop left and exit.  tools/phase_report.py decodes both.  NULL / 0 turns it
+ * off. */
 int gqe_debug_set_phase_log(gqe_ctx* ctx, uint64_t* log, int64_t n_tiles);
 /* Number of kernels this context has launched so far (bench bookkeeping). */
 int64_t gqe_launch_count(const gqe_ctx* ctx);
