@@ -320,12 +320,41 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
     e2e_ms = tm.host_ms(step_host, args.steps)
     assert float(h_loss[0]) == loss_ref, "host entry point disagrees with the device one"
     tm.barrier()
+    fused_ms = fused_kernel_span_ms(torch, ctx, step_device, tm, device) if tables_mode != "staged" else None
     if peers is not None:
         peers.close()
     res = {"wl": wl, "nq": nq, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "loss": loss_ref, "launches": int(launches),
            "h2d": h2d, "call": call, "remote_rows": int(remote_rows), "formulas": len(wl.batches),
-           "params": (tables, rels, pre, post)}
+           "params": (tables, rels, pre, post), "fused_ms": fused_ms}
     return res
+
+
+def fused_kernel_span_ms(torch, ctx, step, tm, device, reps=8):
+    """Duration of the fused tensor-core kernel ALONE, measured by the kernel itself: with the
+    phase log on (gqe_debug_set_phase_log) thread 0 of every CTA stamps %globaltimer at entry and
+    exit; the span first entry -> last exit of one launch, averaged over `reps` untimed steps (L2
+    flushed like the timed ones).  None when the step does not run the tensor-core kernel in one
+    launch.  CUDA events cannot isolate it: the kernel is launched from inside the C call, right
+    behind gqe_pack (programmatic dependent launch)."""
+    import numpy as np
+    n_rec = 512                       # CTA records live in the last 256; tiles < 256 are stamped too
+    log = torch.zeros(n_rec * 32, dtype=torch.int64, device=device)
+    spans = []
+    try:
+        ctx.debug_set_phase_log(log.data_ptr(), n_rec)
+        for _ in range(reps):
+            log.zero_()
+            tm.flush.zero_()
+            step()
+            torch.cuda.synchronize(device)
+            rec = log.cpu().numpy().reshape(n_rec, 32)[::-1][:256]
+            rec = rec[rec[:, 0] != 0]
+            if len(rec) == 0:
+                return None
+            spans.append((rec[:, 8].max() - rec[:, 0].min()) * 1e-6)      # ns -> ms
+    finally:
+        ctx.debug_set_phase_log(None, 0)
+    return float(np.mean(spans))
 
 
 def measure_eval_shape(args, tm, local_rank, n_queries=8192, n_neg=100, d=256):
@@ -480,8 +509,10 @@ def measure_train_step(args, tm, local_rank, batch=512, d=128, steps=30, cpu_ste
             "note": "wall clock per step incl. Python; CPU = oracle port with torch autograd + torch.optim.Adam"}
 
 
-def roofline_of(wl, name, ms_per_step, pk, world=1):
-    """Roofline of the fused kernel for one step of `wl` on one GPU."""
+def roofline_of(wl, name, ms_per_step, pk, world=1, fused_ms=None):
+    """Roofline of the fused kernel for one step of `wl` on one GPU.  `frac` charges the kernel
+    with the WHOLE step (CUDA events: weight preparation kernels included); `fused_kernel` gives
+    the same figures over the kernel's own duration (in-kernel %globaltimer span)."""
     bytes_alg, flops_alg = wl.algorithmic_bytes(), wl.algorithmic_flops()
     sec = ms_per_step * 1e-3
     gbs = bytes_alg / sec / 1e9
@@ -510,6 +541,13 @@ def roofline_of(wl, name, ms_per_step, pk, world=1):
             "kernel": "gqe_fused_tc<%d,-1> (grouped tcgen05 kernel, one launch per <=32 formulas, preceded by "
                       "gqe_pack)" % wl.d,
             "kernel_ms": round(ms_per_step, 4),
+            "fused_kernel": None if not fused_ms else {
+                "ms": round(fused_ms, 4), "share_of_step": round(fused_ms / ms_per_step, 3),
+                "executed_tflops": round(passes * flops_alg / (fused_ms * 1e-3) / 1e12, 3),
+                "frac": round(passes * flops_alg / (fused_ms * 1e-3) / 1e12 / pk["bf16_tflops"], 4),
+                "hbm_gbs": round(bytes_alg / (fused_ms * 1e-3) / 1e9, 2),
+                "how": "first CTA entry -> last CTA exit, %globaltimer stamped by the kernel "
+                       "(gqe_debug_set_phase_log), mean of 8 untimed steps"},
             "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_flops_per_launch": flops_alg,
             "hbm": {"achieved_gbs": round(gbs, 2), "frac": round(gbs / pk["hbm_gbs"], 4)},
             "tensor": {"executed_tflops": round(tfl_exec, 3), "algorithmic_tflops": round(tfl, 3),
@@ -593,7 +631,7 @@ def run_native(args):
                     "ms_per_step": round(res["e2e_ms"], 5), "call": res["call"]},
             "gpu_launches": res["launches"],
             "clocks": sampler.summary(),
-            "roofline": roofline_of(wl, name, ms_per_step, pk),
+            "roofline": roofline_of(wl, name, ms_per_step, pk, fused_ms=res.get("fused_ms")),
             "loss": res["loss"],
         }
         for mode, r in extra.items():
