@@ -70,6 +70,7 @@ _SIGNATURES = {
     "gqe_last_error": (C.c_char_p, [_P]),
     "gqe_launch_count": (C.c_int64, [_P]),
     "gqe_debug_set_phase_log": (C.c_int, [_P, _P, C.c_int64]),
+    "gqe_debug_score_col_src": (C.c_int, [C.c_int]),
     "gqe_bind_tables": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64), C.c_int32]),
     "gqe_bind_relations": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.c_int32]),
     "gqe_bind_intersection": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(_P), C.c_int32, C.c_int32]),

@@ -217,6 +217,7 @@ extern "C" int gqe_debug_set_phase_log(gqe_ctx* c, uint64_t* log, int64_t n_tile
 
 extern "C" const char* gqe_last_error(const gqe_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 extern "C" int64_t gqe_launch_count(const gqe_ctx* c) { return c ? c->launches : 0; }
+extern "C" int gqe_debug_score_col_src(int n) { return n < 0 ? -1 : score_col_src_host(n); }
 
 // ---- binding ---------------------------------------------------------------
 extern "C" int gqe_bind_tables(gqe_ctx* c, int32_t n_modes, const float* const* tables, const int64_t* rows,

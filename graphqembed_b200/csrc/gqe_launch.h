@@ -44,6 +44,7 @@ cudaError_t launch_encode_bwd(int d, int64_t n, const float* table, const int32_
 // fp32 products of operator matrices (gqe_compose.cu), d = 128 / 256
 cudaError_t launch_compose(int d, const ComposeParams& cp, int n_entries, cudaStream_t st);
 int compose_tile_rows();   // rows of a gqe_compose tile (64)
+int score_col_src_host(int n);   // tc::score_col_src (gqe_tc.cuh) for the host side
 
 inline bool tc_dim_supported(int d) { return d == 128 || d == 256; }
 inline size_t tc_packed_bytes(int d) { return (size_t)4 * d * d; }

@@ -61,6 +61,10 @@ static cudaError_t tc_launch_struct(int structure, const LaunchParams& lp, int64
   }
 }
 
+#if GQE_DIM == 256
+int score_col_src_host(int n) { return tc::score_col_src(n); }
+#endif
+
 #define GQE_CAT2(a, b) a##b
 #define GQE_CAT(a, b) GQE_CAT2(a, b)
 cudaError_t GQE_CAT(launch_fused_tc_d, GQE_DIM)(int structure, const LaunchParams& lp, int64_t grid, cudaStream_t st) {

@@ -146,6 +146,11 @@ const char* gqe_last_error(const gqe_ctx* ctx);
  * tile taken, tile loop left and exit.  tools/phase_report.py decodes both.  NULL / 0 turns it
  * off. */
 int gqe_debug_set_phase_log(gqe_ctx* ctx, uint64_t* log, int64_t n_tiles);
+/* Diagnostics: the output column held by accumulator column n of a contraction whose result the
+ * tensor-core kernel scores in the TMEM fragment layout (the last hop of a chain): gqe_pack
+ * permutes the packed weights by it so that the four accumulator columns a lane owns are four
+ * contiguous output columns.  A bijection of every 16-column block (host function, no GPU). */
+int gqe_debug_score_col_src(int n);
 /* Number of kernels this context has launched so far (bench bookkeeping). */
 int64_t gqe_launch_count(const gqe_ctx* ctx);
 

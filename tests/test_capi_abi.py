@@ -44,3 +44,18 @@ def test_sass_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_scored_accumulator_column_permutation():
+    """gqe_pack permutes the output columns of a chain's last matrix so that, in the tcgen05.ld
+    16x256b fragment layout (lane t owns accumulator columns 8j + 2(t%4) + {0,1} of repeat j), the
+    four columns a lane owns in repeats (2b, 2b+1) are four CONTIGUOUS output columns -- one
+    128-bit load of the anchor row they are scored against (csrc/gqe_tc.cuh score_frag)."""
+    lib = _lib.load()
+    src = [lib.gqe_debug_score_col_src(n) for n in range(256)]
+    assert sorted(src) == list(range(256))                                   # a permutation ...
+    assert all(s // 16 == n // 16 for n, s in enumerate(src))                # ... inside 16-column blocks
+    for b in range(16):
+        for m in range(4):                                                   # lane % 4
+            owned = [16 * b + 8 * jp + 2 * m + e for jp in (0, 1) for e in (0, 1)]
+            assert [src[c] for c in owned] == [16 * b + 4 * m + i for i in range(4)]
