@@ -46,7 +46,9 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src,
                : "memory");
 }
 
-// L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address
+// L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address.
+// (Not used by the fused kernel any more: issued per lane it costs ~0.5 us of warp time per
+// instruction and queues in the TMA unit in front of the weight stages -- see prefetch_l2_line.)
 __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }

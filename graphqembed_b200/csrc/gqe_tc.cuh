@@ -19,7 +19,12 @@
 //   * the worker warps read the accumulator back with tcgen05.ld (thread == row),
 //     apply the epilogue (re-split for the next hop, ReLU + mean/min aggregation
 //     kept in a second TMEM region, or the cosine / margin loss against the gathered
-//     target rows) and never write an intermediate to global memory.
+//     target rows) and never write an intermediate to global memory;
+//   * chain tiles are scored straight from TMEM in the 16x256b fragment layout
+//     (score_frag), one tile late, in the shadow of the next tile's contraction; the two
+//     TMEM regions swap roles from tile to tile;
+//   * the kernel is launched programmatically dependent on gqe_pack (only the TMA
+//     producer waits for it).
 //
 // Warp roles: warps [0, W) workers (W = d/16: four TMEM lane quarters x d/64 column
 // groups, thread == one row x 64 columns), warp W = TMA producer, warp W+1 = MMA
