@@ -7,17 +7,29 @@
 One "step" = one pass of the hot path over one batch: every query of the batch
 is scored against its positive and one negative target and folded into the
 margin loss (what reference model.py:112-127 computes per batch).  At N=1 the
-default workload is BASELINE.json configs[3] (Bio KG full mix, d=256,
+headline workload is BASELINE.json configs[3] (Bio KG full mix, d=256,
 batch=65536) -- the metric string names no single config, so the largest
-single-GPU configuration is used; --workload selects configs[0..2].
+single-GPU configuration is used; every other config rides in `configs`.
 
-`value`    whole-job throughput with row-index arrays already resident in HBM,
-           timed with CUDA events on the launching stream, L2 flushed before
-           every step, max over ranks.
-`e2e`      same metric through the C-ABI *_host entry point: pinned HOST index
-           buffers in, HOST loss out, copies + stream sync inside the timed call.
-`roofline` algorithmic bytes / measured duration of the fused
-           kernel vs MEASURED_PEAKS.json; the tensor-core view is reported too.
+`value`    whole-job throughput with the NODE-ID arrays already resident in HBM
+           (gqe_score_grouped_nodes_device: node id -> row lookup, gather, ...,
+           loss, one kernel), CUDA events on the launching stream, L2 flushed
+           before every step, max over ranks.  The operator matrices did not change
+           between steps, so their packed images are cached (steady state of
+           eval / inference); `weights_live` is the same step with the cache off.
+`e2e`      same metric through gqe_score_grouped_nodes_host: pinned HOST node-id
+           buffers in, HOST loss out, copies + stream sync inside the timed call --
+           the span the reference arm pays (index building included).
+           `e2e.from_store` / `e2e.from_query_objects` go through the Python
+           operator surface (QueryEncoderDecoder.margin_loss) from a QueryStore
+           slice / from lists of Query objects, negative sampling included.
+`roofline` algorithmic flops (SURVEY.md 8d, x3 for the split-bf16 scheme) / the
+           fused kernel's own duration vs the MEASURED burst bf16 peak; the flops
+           the tensor pipe really issued after pre-composition beside it.
+`configs`  BASELINE.json configs[0..4] (+ min aggregator, + 66-formula mix), each
+           with device / e2e time and both roofline views.
+`hbm_bound` TransE / DistMult + SimpleSetIntersection on the 10 M-node KG: the
+           HBM-gather-bound operators against the measured copy bandwidth.
 `cpu_baseline` the oracle port of the reference path timed on this box's cores.
 """
 import argparse
@@ -53,8 +65,10 @@ def parse_args():
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded 10M-node leg at N>1")
     ap.add_argument("--no-eval-shape", action="store_true", help="skip the 1 query x 101 targets leg at N=1")
     ap.add_argument("--no-train-step", action="store_true", help="skip the configs[0] training-step leg at N=1")
-    ap.add_argument("--with-sharded", action="store_true", help="also run the 10M-node workload at N=1")
+    ap.add_argument("--with-sharded", action="store_true", help="(kept for compatibility; the 10M-node table now runs at N=1 by default)")
     ap.add_argument("--sharded-formulas", type=int, default=4, help="formulas per structure of the 10M-node leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (configs, hbm_bound) at N=1")
+    ap.add_argument("--extra-steps", type=int, default=40, help="timed steps of each secondary workload")
     return ap.parse_args()
 
 
@@ -63,9 +77,11 @@ def peaks():
     if os.path.exists(path):
         with open(path) as fh:
             p = json.load(fh)
-        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
-                "source": "measured"}
-    return {"hbm_gbs": HBM_FALLBACK_GBS, "bf16_tflops": BF16_FALLBACK_TFLOPS, "source": "fallback"}
+        # the fused kernel is a ~0.1 ms launch timed alone behind an L2 flush: the BURST figure applies
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": HBM_FALLBACK_GBS, "bf16_tflops": BF16_FALLBACK_TFLOPS, "bf16_tflops_sustained": BF16_FALLBACK_TFLOPS,
+            "source": "fallback"}
 
 
 # ---------------------------------------------------------------------------
@@ -146,7 +162,11 @@ def device_parameters(wl, torch, device, seed, owner=None, rank=0):
             tables.append(torch.randn(kg.sizes[m] + 2, d, generator=gen(i), device=device) * (1.0 / d))
     bound = math.sqrt(6.0 / (2 * d))
     uni = lambda k: (torch.rand(d, d, generator=gen(k), device=device) * 2 - 1) * bound
-    rels = [uni(1000 + i) for i in range(len(kg.rel_keys))]
+    if wl.decoder == "bilinear":
+        rels = [uni(1000 + i) for i in range(len(kg.rel_keys))]
+    else:      # relation vectors U(+-6/sqrt(d)) (decoders.py:195,224)
+        rels = [(torch.rand(d, generator=gen(1000 + i), device=device) * 2 - 1) * (6.0 / math.sqrt(d))
+                for i in range(len(kg.rel_keys))]
     pre = [uni(2000 + i) for i in range(len(kg.modes))]
     post = [uni(3000 + i) for i in range(len(kg.modes))]
     return tables, rels, pre, post
@@ -205,14 +225,18 @@ class Timed(object):
         return self.max_over_ranks(tot * 1e3)[0] / steps
 
 
-def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, formulas_per_structure=1):
+def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, formulas_per_structure=1, steps=None,
+            parity_slice=0, want_live=True):
     """One workload on this process group.  tables_mode:
-         replicated  every rank holds every table (Bio-size); pure data parallel
+         replicated  every rank holds every table; pure data parallel, no data-path collective
          p2p         tables sharded by node type, peers mapped with CUDA IPC, the fused kernel
                      gathers remote rows in place over NVLink
          staged      tables sharded by node type, rows fetched by an NCCL all-to-all exchange
                      into staging tables before the same fused kernel runs
-    """
+       The index arrays are NODE IDS (int32) -- mapped to table rows inside the kernels through the
+       bound node maps -- except on the staged path, whose indices are positions in the exchange
+       buffers.  parity_slice > 0: score that many queries of every formula a second time against
+       the full, unsharded tables held on this one GPU and require bit-equal scores."""
     import numpy as np
     import torch
 
@@ -220,54 +244,80 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
     from graphqembed_b200 import _lib, sharded
     from graphqembed_b200.workloads import make_workload
 
+    steps = steps or args.steps
     device, stream, dist = tm.device, tm.stream, tm.dist
     wl = make_workload(name, seed=rank, formulas_per_structure=formulas_per_structure)
-    n_modes = len(wl.kg.modes)
+    kg = wl.kg
+    n_modes = len(kg.modes)
     owner = None if tables_mode == "replicated" else sharded.owner_by_node_type(n_modes, world)
     tables, rels, pre, post = device_parameters(wl, torch, device, seed=1234, owner=owner, rank=rank)
-    lookup = gqe.RowLookup(wl.kg.node_ids)
-    mode_ids = {m: i for i, m in enumerate(wl.kg.modes)}
-    rel_ids = {r: i for i, r in enumerate(wl.kg.rel_keys)}
-    segs, anchor_rows, pair_rows = wl.lower(lookup, mode_ids, rel_ids)
+    lookup = gqe.RowLookup(kg.node_ids)
+    mode_ids = {m: i for i, m in enumerate(kg.modes)}
+    rel_ids = {r: i for i, r in enumerate(kg.rel_keys)}
+    segs, anchor_nodes, pair_nodes = wl.node_arrays(mode_ids, rel_ids)
     nq = wl.n_queries
-    rows = [wl.kg.sizes[m] + 2 for m in wl.kg.modes]
+    rows = [kg.sizes[m] + 2 for m in kg.modes]
+    deepsets = not wl.inter.endswith("-simple")
 
-    ctx = gqe.Context(local_rank, stream.cuda_stream)
-    ctx.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
-    ctx.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
+    def new_context(ptrs, nrows, node_maps=True):
+        c = gqe.Context(local_rank, stream.cuda_stream)
+        c.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
+        if deepsets:
+            c.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
+        else:
+            c.bind_intersection(_lib.INTER_ID[wl.inter], None, None, wl.d)
+        c.bind_tables(ptrs, nrows, wl.d)
+        if node_maps:
+            maps = lookup.device_maps(kg.modes, nrows, device)
+            c.bind_node_maps(maps[0], maps[1], maps[2])
+        return c
+
     own_ptrs = [0 if t is None else t.data_ptr() for t in tables]
     own_rows = [0 if t is None else r for t, r in zip(tables, rows)]
-
-    h_anchor = torch.from_numpy(anchor_rows).pin_memory()
-    h_pairs = torch.from_numpy(pair_rows).pin_memory()
+    h_anchor = torch.from_numpy(anchor_nodes).pin_memory()
+    h_pairs = torch.from_numpy(pair_nodes).pin_memory()
     h_loss = torch.zeros(1).pin_memory()
     d_loss = torch.zeros(1, device=device)
     remote_rows = 0
     peers = None
+    d_scores = torch.empty((nq, 2), device=device) if parity_slice else None
+    sub = None
+    if parity_slice:
+        sub = _lib.make_segments([(segs[i].plan, segs[i].query_begin,
+                                   min(segs[i].query_end, segs[i].query_begin + parity_slice)) for i in range(len(segs))])
 
     if tables_mode in ("replicated", "p2p"):
         if tables_mode == "p2p" and world > 1:
-            peers = sharded.PeerTables(ctx, owner, rows, {m: t for m, t in enumerate(tables) if t is not None})
-            ctx.bind_tables(peers.pointers(), rows, wl.d)
+            octx = new_context(own_ptrs, own_rows, node_maps=False)
+            peers = sharded.PeerTables(octx, owner, rows, {m: t for m, t in enumerate(tables) if t is not None})
+            ctx = new_context(peers.pointers(), rows)
             for c_mode, c_n, _, _, _ in sharded.chunks_of_segments(segs, nq, 2):
                 if owner[c_mode] != rank:
                     remote_rows += c_n
         else:
-            ctx.bind_tables(own_ptrs, own_rows, wl.d)
+            ctx = new_context(own_ptrs, own_rows)
         d_anchor, d_pairs = h_anchor.to(device), h_pairs.to(device)
 
         def step_device():
-            ctx.score_grouped_device(segs, nq, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, None, 1.0, d_loss.data_ptr())
+            ctx.score_grouped_device(segs, nq, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, None, 1.0, d_loss.data_ptr(),
+                                     nodes=True)
 
         def step_host():
-            ctx._check(ctx._lib.gqe_score_grouped_host(ctx._h, segs, len(segs), nq, h_anchor.data_ptr(),
-                                                       h_pairs.data_ptr(), 2, None, 1.0, h_loss.data_ptr()))
-        h2d = int(anchor_rows.nbytes + pair_rows.nbytes)
-        call = "gqe_score_grouped_host (pinned int32 row indices in, fp32 loss out)"
+            ctx._check(ctx._lib.gqe_score_grouped_nodes_host(ctx._h, segs, len(segs), nq, h_anchor.data_ptr(),
+                                                             h_pairs.data_ptr(), 2, None, 1.0, h_loss.data_ptr()))
+
+        def slice_scores():
+            ctx.score_grouped_device(sub, nq, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, d_scores.data_ptr(), 1.0, None,
+                                     nodes=True)
+        h2d = int(anchor_nodes.nbytes + pair_nodes.nbytes)
+        call = "gqe_score_grouped_nodes_host (pinned int32 NODE IDS in, fp32 loss out; lookup + scoring in one kernel)"
+        launch_ctxs = (ctx,)
     else:
+        # staged exchange: requests are table rows (the owner gathers them), lowered on the host
+        _, anchor_rows, pair_rows = wl.lower(lookup, mode_ids, rel_ids)
         info = sharded.chunks_of_segments(segs, nq, 2)
         plan = sharded.ExchangePlan(owner, world, rank, [(m, n) for m, n, _, _, _ in info])
-        ctx.bind_tables(own_ptrs, own_rows, wl.d)          # the owner-side gather reads these
+        ctx = new_context(own_ptrs, own_rows, node_maps=False)          # the owner-side gather reads these
         ex = sharded.RowExchange(plan, wl.d, sharded.device_gather(ctx), device=device)
         req, s_anchor, s_pairs = sharded.stage_grouped(plan, info, segs, anchor_rows, pair_rows, 2)
         h_req = torch.from_numpy(req).pin_memory()
@@ -279,11 +329,8 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
             if owner[c_mode] != rank:
                 remote_rows += c_n
         # a second context scores against the staging tables (the first keeps the shards bound)
-        sctx = gqe.Context(local_rank, stream.cuda_stream)
-        sctx.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
-        sctx.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
         st_ptrs, st_rows = ex.staging_tables()
-        sctx.bind_tables(st_ptrs, st_rows, wl.d)
+        sctx = new_context(st_ptrs, st_rows, node_maps=False)
 
         def step_device():
             ex.run(d_req)
@@ -299,11 +346,13 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
                                       d_loss.data_ptr())
             h_loss.copy_(d_loss, non_blocking=True)
             stream.synchronize()
+
+        def slice_scores():
+            ex.run(d_req)
+            sctx.score_grouped_device(sub, nq, d_sanchor.data_ptr(), d_spairs.data_ptr(), 2, d_scores.data_ptr(), 1.0, None)
         h2d = int(req.nbytes + s_anchor.nbytes + s_pairs.nbytes)
         call = "request H2D + NCCL all-to-all exchange + gqe_score_grouped_device + loss D2H"
         launch_ctxs = (ctx, sctx)
-    if tables_mode != "staged":
-        launch_ctxs = (ctx,)
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -312,21 +361,149 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
     tm.barrier()
     loss_ref = float(d_loss.item())
     launches0 = sum(c.launch_count() for c in launch_ctxs)
-    dev_ms = tm.device_ms(step_device, args.steps, 0, sampler)
-    launches = sum(c.launch_count() for c in launch_ctxs) - launches0
+    dev_ms = tm.device_ms(step_device, steps, 0, sampler)
+    launches = (sum(c.launch_count() for c in launch_ctxs) - launches0) / float(steps)
     assert float(d_loss.item()) == loss_ref, "non-deterministic loss"
     if sampler is not None:
         sampler.stop()      # the NVML polling thread must not compete with the host-timed loop
-    e2e_ms = tm.host_ms(step_host, args.steps)
+    e2e_ms = tm.host_ms(step_host, steps)
     assert float(h_loss[0]) == loss_ref, "host entry point disagrees with the device one"
     tm.barrier()
-    fused_ms = fused_kernel_span_ms(torch, ctx, step_device, tm, device) if tables_mode != "staged" else None
+    # the same step with the operator matrices treated as live (re-composed and re-packed every call:
+    # what a training loop that updates them every step pays)
+    live_ms = live_launches = None
+    if want_live and wl.decoder == "bilinear" and tables_mode != "staged":
+        ctx.set_weight_cache(False)
+        l0 = ctx.launch_count()
+        live_ms = tm.device_ms(step_device, max(10, steps // 2), 3)
+        live_launches = (ctx.launch_count() - l0) / float(max(10, steps // 2) + 3)
+        assert float(d_loss.item()) == loss_ref
+        ctx.set_weight_cache(True)
+    fused_ms = None
+    if wl.decoder == "bilinear" and tables_mode != "staged" and wl.d in (128, 256):
+        fused_ms = fused_kernel_span_ms(torch, ctx, step_device, tm, device)
+
+    parity = None
+    if parity_slice:
+        # this rank's queries against the FULL tables held on this one GPU: must be bit-equal
+        slice_scores()
+        torch.cuda.synchronize(device)
+        got = d_scores.clone()
+        full, _, _, _ = device_parameters(wl, torch, device, seed=1234)
+        fctx = new_context([t.data_ptr() for t in full], rows)
+        d_a2, d_p2 = h_anchor.to(device), h_pairs.to(device)
+        want = torch.empty_like(d_scores)
+        fctx.score_grouped_device(sub, nq, d_a2.data_ptr(), d_p2.data_ptr(), 2, want.data_ptr(), 1.0, None, nodes=True)
+        torch.cuda.synchronize(device)
+        err, n_cmp = 0.0, 0
+        for i in range(len(sub)):
+            qb, qe = int(sub[i].query_begin), int(sub[i].query_end)
+            err = max(err, float((got[qb:qe] - want[qb:qe]).abs().max())) if qe > qb else err
+            n_cmp += qe - qb
+        del full, fctx
+        torch.cuda.empty_cache()
+        err, = tm.max_over_ranks(err)
+        assert err == 0.0, "%s scores differ from the unsharded single-GPU scores by %g" % (tables_mode, err)
+        parity = {"queries_compared_per_rank": int(n_cmp), "parity_max_abs_err": err,
+                  "against": "the same queries scored on one GPU holding the full (unsharded) tables"}
     if peers is not None:
+        tm.barrier()
         peers.close()
-    res = {"wl": wl, "nq": nq, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "loss": loss_ref, "launches": int(launches),
-           "h2d": h2d, "call": call, "remote_rows": int(remote_rows), "formulas": len(wl.batches),
-           "params": (tables, rels, pre, post), "fused_ms": fused_ms}
-    return res
+    return {"wl": wl, "nq": nq, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "loss": loss_ref, "launches": launches,
+            "h2d": h2d, "call": call, "remote_rows": int(remote_rows), "formulas": len(wl.batches),
+            "params": (tables, rels, pre, post), "fused_ms": fused_ms, "live_ms": live_ms,
+            "live_launches": live_launches, "parity": parity, "lookup": lookup}
+
+
+def measure_python_surface(args, tm, res, steps=20):
+    """The headline mix through the Python operator surface: QueryEncoderDecoder.margin_loss(formula,
+    queries) once per formula (what replaces model.py:112-127 as the reference's train/eval loops call
+    it), negative sampling included.  (a) from StoreSlices of a QueryStore -- no per-query Python;
+    (b) from lists of Query objects, the reference's own argument type (fewer steps: it is slow)."""
+    import random
+    import numpy as np
+    import torch
+
+    import graphqembed_b200 as gqe
+    from graphqembed_b200.store import FormulaBlock
+    from graphqembed_b200.synth import SynthKG
+
+    wl, (tables, rels, pre, post) = res["wl"], res["params"]
+    kg, d, device = wl.kg, wl.d, tm.device
+
+    class G(object):
+        pass
+    graph = G()
+    graph.relations, graph.features = kg.relations, res["lookup"]
+    graph.full_lists = {m: kg.node_ids[m] for m in kg.modes}       # 1-chain negatives: any node of the mode
+    dims = {m: d for m in kg.modes}
+    feature_modules = {}
+    for m, t in zip(kg.modes, tables):
+        emb = torch.nn.Embedding(1, d)
+        emb.weight = torch.nn.Parameter(t, requires_grad=False)     # the benchmark's own table, no copy
+        feature_modules[m] = emb
+    enc = gqe.get_encoder(0, graph, dims, feature_modules)
+    dec = gqe.get_metapath_decoder(graph, dims, wl.decoder).to(device)
+    idec = gqe.get_intersection_decoder(graph, dims, wl.inter).to(device)
+    with torch.no_grad():
+        for r, t in zip(kg.rel_keys, rels):
+            dec.mats[r].copy_(t)
+        for m, a, b in zip(kg.modes, pre, post):
+            idec.pre_mats[m].copy_(a)
+            idec.post_mats[m].copy_(b)
+    model = gqe.QueryEncoderDecoder(graph, enc, dec, idec)
+    model.negative_rng = np.random.default_rng(0)
+    blocks = []
+    for b in wl.batches:       # each formula's positives; negatives: 8 stored per query, drawn per step
+        n = b.n_queries
+        pairs = b.targets.reshape(-1, 2)
+        negs = kg.sample_nodes(b.formula.target_mode, n * 8, np.random.RandomState(5)).astype(np.int32)
+        ptr = np.arange(n + 1, dtype=np.int64) * 8
+        blocks.append(FormulaBlock(b.formula, b.anchors.astype(np.int32), pairs[:, 0].astype(np.int32), ptr, negs,
+                                   np.zeros(n + 1, dtype=np.int64), np.empty(0, dtype=np.int32)))
+
+    def step_store():
+        tot = 0.0
+        with torch.no_grad():
+            losses = [model.margin_loss(blk.formula, blk.all()) for blk in blocks]
+        for blk, l in zip(blocks, losses):
+            tot += float(l) * len(blk)
+        return tot / wl.n_queries
+
+    model.check_indices = False        # errors are polled once per step below, not once per formula
+    for _ in range(3):
+        step_store()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tm.flush.zero_()
+        step_store()
+        model.context().index_error()
+    store_ms = (time.perf_counter() - t0) * 1e3 / steps
+    # lists of Query objects
+    qlists = []
+    for blk in blocks:
+        s, rl = blk.formula.query_type, blk.formula.rels
+        qlists.append([gqe.Query(SynthKG.query_graph(s, rl, int(blk.targets[i]), blk.anchors[:, i]),
+                                 [int(x) for x in blk.negs[8 * i:8 * i + 8]], None, 100) for i in range(len(blk))])
+
+    def step_objects():
+        with torch.no_grad():
+            return [float(model.margin_loss(blk.formula, qs)) for blk, qs in zip(blocks, qlists)]
+    random.seed(0)
+    step_objects()
+    t0 = time.perf_counter()
+    n_obj = max(2, steps // 8)
+    for _ in range(n_obj):
+        step_objects()
+    obj_ms = (time.perf_counter() - t0) * 1e3 / n_obj
+    return {"from_store": {"value": round(wl.n_queries / (store_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(store_ms, 4),
+                           "call": "QueryEncoderDecoder.margin_loss(formula, StoreSlice) x %d formulas: vectorised negative "
+                                   "draw + pinned H2D of node ids + fused kernel + loss read" % len(blocks)},
+            "from_query_objects": {"value": round(wl.n_queries / (obj_ms * 1e-3), 1), "unit": UNIT,
+                                   "ms_per_step": round(obj_ms, 4),
+                                   "call": "QueryEncoderDecoder.margin_loss(formula, [Query]) x %d formulas: the reference's "
+                                           "argument type (random.choice per query, attribute walks)" % len(blocks)}}
 
 
 def fused_kernel_span_ms(torch, ctx, step, tm, device, reps=8):
@@ -509,58 +686,92 @@ def measure_train_step(args, tm, local_rank, batch=512, d=128, steps=30, cpu_ste
             "note": "wall clock per step incl. Python; CPU = oracle port with torch autograd + torch.optim.Adam"}
 
 
-def roofline_of(wl, name, ms_per_step, pk, world=1, fused_ms=None):
-    """Roofline of the fused kernel for one step of `wl` on one GPU.  `frac` charges the kernel
-    with the WHOLE step (CUDA events: weight preparation kernels included); `fused_kernel` gives
-    the same figures over the kernel's own duration (in-kernel %globaltimer span)."""
+def ncu_record(name):
+    """Numbers copied from the committed ncu capture of this workload's dominant kernel
+    (profiles/traffic.json: DRAM bytes per launch, tensor-pipe activity, kernel duration under ncu)."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return {}
+    with open(tpath) as fh:
+        rec = json.load(fh).get(name)
+    if isinstance(rec, (int, float)):
+        rec = {"bytes": rec}
+    return rec or {}
+
+
+def roofline_of(wl, name, ms_per_step, pk, fused_ms=None, live_ms=None):
+    """Roofline of the dominant kernel for one step of `wl` on one GPU.
+
+    Bilinear / DeepSets workloads are bound by the tensor pipe: the d x d contractions run as three
+    bf16 tensor-core products per algorithmic one (hi*hi + lo*hi + hi*lo, fp32 accumulate), so
+    `achieved` = 3 x algorithmic flops / kernel time, against the measured BURST bf16 peak (the kernel
+    is one ~0.1 ms launch timed alone behind an L2 flush).  `frac_issued` counts only the flops the
+    tensor pipe really executed after runs of linear operators were pre-multiplied.  With the
+    weights cached the timed step IS the fused kernel (one launch between the CUDA events).
+    TransE / DistMult + element-wise intersections have no contraction: HBM-gather-bound."""
     bytes_alg, flops_alg = wl.algorithmic_bytes(), wl.algorithmic_flops()
     sec = ms_per_step * 1e-3
     gbs = bytes_alg / sec / 1e9
-    tfl = flops_alg / sec / 1e12
-    # the contractions run as three bf16 tensor-core products per algorithmic one
-    # (hi*hi + lo*hi + hi*lo, fp32 accumulate): the tensor pipe executes 3x the
-    # algorithmic flops, so the usable ceiling is the measured bf16 peak / 3
     passes = 3
-    tfl_exec = passes * tfl
+    tfl_exec = passes * flops_alg / sec / 1e12
     t_hbm = bytes_alg / (pk["hbm_gbs"] * 1e9)
     t_tc = passes * flops_alg / (pk["bf16_tflops"] * 1e12)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            traffic = json.load(fh).get(name)
-        if isinstance(traffic, dict):
-            traffic = traffic.get("bytes")
+    rec = ncu_record(name)
     bound = "hbm" if t_hbm >= t_tc else "tensor"
-    return {"bound": bound,
-            "achieved": round(gbs if bound == "hbm" else tfl_exec, 3),
-            "peak": pk["hbm_gbs"] if bound == "hbm" else pk["bf16_tflops"],
-            "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-            "frac": round((gbs / pk["hbm_gbs"]) if bound == "hbm" else (tfl_exec / pk["bf16_tflops"]), 4),
-            "traffic": traffic, "peak_source": pk["source"],
-            "kernel": "gqe_fused_tc<%d,-1> (grouped tcgen05 kernel, one launch per <=32 formulas, preceded by "
-                      "gqe_pack)" % wl.d,
-            "kernel_ms": round(ms_per_step, 4),
-            "fused_kernel": None if not fused_ms else {
-                "ms": round(fused_ms, 4), "share_of_step": round(fused_ms / ms_per_step, 3),
-                "executed_tflops": round(passes * flops_alg / (fused_ms * 1e-3) / 1e12, 3),
-                "frac": round(passes * flops_alg / (fused_ms * 1e-3) / 1e12 / pk["bf16_tflops"], 4),
-                "hbm_gbs": round(bytes_alg / (fused_ms * 1e-3) / 1e9, 2),
-                "how": "first CTA entry -> last CTA exit, %globaltimer stamped by the kernel "
-                       "(gqe_debug_set_phase_log), mean of 8 untimed steps"},
-            "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_flops_per_launch": flops_alg,
-            "hbm": {"achieved_gbs": round(gbs, 2), "frac": round(gbs / pk["hbm_gbs"], 4)},
-            "tensor": {"executed_tflops": round(tfl_exec, 3), "algorithmic_tflops": round(tfl, 3),
-                       "issued_tflops": round(passes * wl.composed_flops() / sec / 1e12, 3),
-                       "peak_tflops": pk["bf16_tflops"], "frac": round(tfl_exec / pk["bf16_tflops"], 4),
-                       "note": "d x d contractions as bf16x3 split products on tcgen05 (3 MMAs per algorithmic "
-                               "product): executed = 3 x algorithmic (SURVEY 8d: the 3-pass scheme divides the "
-                               "usable ceiling by 3); issued = what the tensor pipe really ran after runs of "
-                               "linear operators were pre-multiplied (gqe_compose); peak = measured sustained "
-                               "bf16 dense"}}
+    out = {"bound": bound,
+           "achieved": round(gbs if bound == "hbm" else tfl_exec, 3),
+           "peak": pk["hbm_gbs"] if bound == "hbm" else pk["bf16_tflops"],
+           "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+           "frac": round((gbs / pk["hbm_gbs"]) if bound == "hbm" else (tfl_exec / pk["bf16_tflops"]), 4),
+           "traffic": rec.get("bytes"), "peak_source": pk["source"],
+           "peak_kind": "measured copy bandwidth" if bound == "hbm" else "measured bf16 dense, burst (kernel timed alone)",
+           "kernel_ms": round(ms_per_step, 5),
+           "algorithmic_bytes_per_launch": bytes_alg, "algorithmic_flops_per_launch": flops_alg,
+           "hbm": {"achieved_gbs": round(gbs, 2), "frac": round(gbs / pk["hbm_gbs"], 4)}}
+    if wl.decoder == "bilinear":
+        issued = passes * wl.composed_flops(min_rows=0) / sec / 1e12
+        out["kernel"] = ("gqe_fused_tc<%d,%s> (persistent tcgen05 kernel; with the packed weights cached it is the "
+                         "only launch of the step)" % (wl.d, "-1" if len(wl.batches) > 1 else "structure"))
+        out["frac_algorithmic"] = round(tfl_exec / pk["bf16_tflops"], 4)
+        out["frac_issued"] = round(issued / pk["bf16_tflops"], 4)
+        out["tensor"] = {"executed_tflops": round(tfl_exec, 3), "algorithmic_tflops": round(flops_alg / sec / 1e12, 3),
+                         "issued_tflops": round(issued, 3), "peak_tflops": pk["bf16_tflops"],
+                         "peak_tflops_sustained": pk["bf16_tflops_sustained"],
+                         "tensor_pipe_active_pct_ncu": rec.get("tensor_pipe_active_pct"),
+                         "kernel_us_under_ncu": rec.get("kernel_us"),
+                         "note": "executed = 3 x algorithmic (split-bf16: hi*hi + lo*hi + hi*lo); issued = what the "
+                                 "tensor pipe ran after pre-composition; tensor_pipe_active_pct_ncu = "
+                                 "sm__pipe_tensor_cycles_active of the committed ncu capture (profiles/)"}
+        if fused_ms:
+            out["fused_kernel_span"] = {"ms": round(fused_ms, 5),
+                                        "how": "first CTA entry -> last CTA exit, %globaltimer stamped by the kernel itself"}
+        if live_ms:
+            out["weights_live_ms"] = round(live_ms, 5)
+    else:
+        out["kernel"] = "gqe_fused_vec<%d> (streaming warp-per-query kernel, no contraction)" % wl.d
+    return out
 
 
 NVLINK_PEER_GBS = 770.0     # /opt/skills/guides/B200_PROFILING.md: measured peer copy, per direction per GPU
+
+
+def summarize(name, r, pk, world, WORKLOADS):
+    """One secondary workload as a JSON object."""
+    wl = r["wl"]
+    sec = r["dev_ms"] * 1e-3
+    out = {"workload": WORKLOADS[name][0], "name": name, "queries_per_step_per_gpu": r["nq"], "formulas": r["formulas"],
+           "decoder": wl.decoder, "intersection": wl.inter, "d": wl.d,
+           "value": round(world * r["nq"] / sec, 1), "unit": UNIT, "ms_per_step": round(r["dev_ms"], 5),
+           "e2e": {"value": round(world * r["nq"] / (r["e2e_ms"] * 1e-3), 1), "ms_per_step": round(r["e2e_ms"], 5),
+                   "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4},
+           "gpu_launches_per_step": round(r["launches"], 2), "loss": r["loss"],
+           "roofline": roofline_of(wl, name, r["dev_ms"], pk, r.get("fused_ms"), r.get("live_ms"))}
+    if r.get("live_ms"):
+        out["weights_live"] = {"ms_per_step": round(r["live_ms"], 5), "value": round(world * r["nq"] / (r["live_ms"] * 1e-3), 1),
+                               "gpu_launches_per_step": round(r["live_launches"], 2)}
+    if r.get("parity"):
+        out["parity"] = r["parity"]
+    return out
 
 
 def run_native(args):
@@ -584,20 +795,46 @@ def run_native(args):
     tm = Timed(torch, dist, device, stream, flush)
 
     name = args.workload or DEFAULT_WORKLOAD
-    tables_mode = args.tables or ("p2p" if name == LARGE_WORKLOAD and world > 1 else "replicated")
+    tables_mode = args.tables or ("p2p" if name.startswith("synth-10m") and world > 1 else "replicated")
     sampler = ClockSampler(local_rank)
     sampler.start()
     res = measure(args, name, tables_mode, tm, rank, world, local_rank, sampler, args.formulas_per_structure)
     sampler.stop()
+    surface = None
+    if world == 1 and rank == 0 and not args.no_extras and WORKLOADS[name][4] == "bilinear":
+        surface = measure_python_surface(args, tm, res)
 
-    # BASELINE.json configs[4]: the node-type-sharded 10 M-node table, measured beside the
-    # headline whenever the job has more than one GPU (and on request at N=1)
-    extra = {}
-    if (world > 1 and args.workload is None and not args.no_sharded) or args.with_sharded:
-        for mode in (("p2p", "staged") if world > 1 else ("replicated",)):
-            r = measure(args, LARGE_WORKLOAD, mode, tm, rank, world, local_rank, None, args.sharded_formulas)
+    # BASELINE.json configs[4]: the node-type-sharded 10 M-node table, measured beside the headline
+    # whenever the job has more than one GPU; every rank checks its scores against the unsharded tables
+    sharded_res = {}
+    if world > 1 and args.workload is None and not args.no_sharded:
+        for mode in ("p2p", "staged"):
+            r = measure(args, LARGE_WORKLOAD, mode, tm, rank, world, local_rank, None, args.sharded_formulas,
+                        steps=max(10, args.steps // 2), parity_slice=4096 // (6 * args.sharded_formulas) + 1,
+                        want_live=False)
             r.pop("params")
-            extra[mode] = r
+            sharded_res[mode] = r
+            torch.cuda.empty_cache()
+
+    # every other BASELINE config + the HBM-bound operators, on one GPU
+    extras, hbm = {}, {}
+    if world == 1 and args.workload is None and not args.no_extras:
+        plan = [("configs[0]", "bio-edge-d128-b512", 1), ("configs[1]", "bio-chain-d128-b4096", 1),
+                ("configs[2]", "bio-inter-d128-b8192", 1), ("configs[2]-min", "bio-inter-d128-b8192-min", 1),
+                ("configs[3]-66-formulas", "bio-mix-d256-b65536", 11),
+                ("configs[4]-1gpu", LARGE_WORKLOAD, args.sharded_formulas)]
+        for key, wname, fps in plan:
+            r = measure(args, wname, "replicated", tm, rank, world, local_rank, None, fps, steps=args.extra_steps)
+            r.pop("params")
+            extras[key] = r
+            extras[key]["name"] = wname
+            torch.cuda.empty_cache()
+        for wname in ("synth-10m-transe-minsimple-d256-b65536", "synth-10m-distmult-meansimple-d256-b65536",
+                      "bio-transe-minsimple-d256-b65536"):
+            r = measure(args, wname, "replicated", tm, rank, world, local_rank, None, args.sharded_formulas,
+                        steps=args.extra_steps, want_live=False)
+            r.pop("params")
+            hbm[wname] = r
             torch.cuda.empty_cache()
 
     # the evaluation shape (utils.py:70-91): one query against its positive + 100 negatives
@@ -621,7 +858,10 @@ def run_native(args):
             "config": {"workload": WORKLOADS[name][0], "name": name, "queries_per_step_per_gpu": nq,
                        "targets_per_query": 2, "decoder": wl.decoder, "intersection": wl.inter, "d": wl.d,
                        "formulas": res["formulas"],
+                       "indices": "int32 NODE IDS; node id -> table row (node_maps[mode][n] + 1) inside the kernel",
                        "contractions": "bf16x3 split on tcgen05, fp32 accumulate (scores within 1e-4 of fp32)",
+                       "weights": "packed / pre-multiplied operator matrices cached across steps (parameters unchanged "
+                                  "between steps; `weights_live` = re-prepared every step)",
                        "tables": {"replicated": "replicated per GPU (Bio-size); queries sharded, no collective",
                                   "p2p": "sharded by node type; remote rows gathered in place over NVLink (CUDA IPC)",
                                   "staged": "sharded by node type; NCCL all-to-all row exchange"}[tables_mode],
@@ -629,24 +869,39 @@ def run_native(args):
             "e2e": {"value": round(world * nq / (res["e2e_ms"] * 1e-3), 1), "unit": UNIT,
                     "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": 4,
                     "ms_per_step": round(res["e2e_ms"], 5), "call": res["call"]},
-            "gpu_launches": res["launches"],
+            "gpu_launches": int(round(res["launches"] * args.steps)),
+            "gpu_launches_per_step": round(res["launches"], 2),
             "clocks": sampler.summary(),
-            "roofline": roofline_of(wl, name, ms_per_step, pk, fused_ms=res.get("fused_ms")),
+            "roofline": roofline_of(wl, name, ms_per_step, pk, res.get("fused_ms"), res.get("live_ms")),
             "loss": res["loss"],
         }
-        for mode, r in extra.items():
+        if res.get("live_ms"):
+            line["weights_live"] = {"ms_per_step": round(res["live_ms"], 5),
+                                    "value": round(world * nq / (res["live_ms"] * 1e-3), 1),
+                                    "gpu_launches_per_step": round(res["live_launches"], 2),
+                                    "note": "weight cache off: gqe_compose + gqe_pack run in front of the fused kernel "
+                                            "every step, as when an optimiser changes the matrices every step"}
+        if surface:
+            line["e2e"].update(surface)
+        for mode, r in sharded_res.items():
             sec = r["dev_ms"] * 1e-3
             nv_bytes = r["remote_rows"] * r["wl"].d * 4
             line.setdefault("sharded", {})[mode] = {
                 "workload": WORKLOADS[LARGE_WORKLOAD][0], "value": round(world * r["nq"] / sec, 1), "unit": UNIT,
+                "per_gpu": round(r["nq"] / sec, 1),
                 "ms_per_step": round(r["dev_ms"], 5), "e2e_value": round(world * r["nq"] / (r["e2e_ms"] * 1e-3), 1),
-                "gpu_launches": r["launches"], "formulas": r["formulas"], "loss_rank0": r["loss"],
+                "gpu_launches_per_step": round(r["launches"], 2), "formulas": r["formulas"], "loss_rank0": r["loss"],
+                "parity": r["parity"],
                 "hbm": {"achieved_gbs": round(r["wl"].algorithmic_bytes() / sec / 1e9, 2),
                         "frac": round(r["wl"].algorithmic_bytes() / sec / 1e9 / pk["hbm_gbs"], 4)},
                 "nvlink": {"remote_rows_per_step_rank0": r["remote_rows"], "bytes_per_step_rank0": nv_bytes,
                            "achieved_gbs_in": round(nv_bytes / sec / 1e9, 2), "peak_gbs": NVLINK_PEER_GBS,
                            "frac": round(nv_bytes / sec / 1e9 / NVLINK_PEER_GBS, 4),
                            "note": "inbound row bytes of rank 0 / step time vs the measured peer-copy bandwidth"}}
+        if extras:
+            line["configs"] = {k: summarize(r["name"], r, pk, world, WORKLOADS) for k, r in extras.items()}
+        if hbm:
+            line["hbm_bound"] = {k: summarize(k, r, pk, world, WORKLOADS) for k, r in hbm.items()}
         if eval_res is not None:
             sec = eval_res["ms"] * 1e-3
             line["eval_shape"] = {

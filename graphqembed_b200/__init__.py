@@ -9,11 +9,12 @@ Importing this package does not need a GPU; creating a context (any scoring
 call) does, and raises if the CUDA library or an sm_100 device is missing.
 """
 from . import _lib
-from ._lib import Context, GqeError, Plan, Segment, build, load, make_segments
+from ._lib import Context, GqeError, GqeIndexError, Plan, Segment, build, load, make_segments
 from .lowering import RowLookup, lower_formula, relation_order
 from .query import Formula, Query, QueryBatch, reverse_relation
+from .store import FormulaBlock, QueryStore, StoreSlice
 
-__all__ = ["Context", "GqeError", "Plan", "Segment", "build", "load", "make_segments", "RowLookup", "lower_formula",
+__all__ = ["Context", "GqeError", "GqeIndexError", "QueryStore", "StoreSlice", "FormulaBlock", "Plan", "Segment", "build", "load", "make_segments", "RowLookup", "lower_formula",
            "relation_order", "Formula", "Query", "QueryBatch", "reverse_relation", "DirectEncoder",
            "BilinearMetapathDecoder", "TransEMetapathDecoder", "BilinearDiagMetapathDecoder", "SetIntersection",
            "SimpleSetIntersection", "QueryEncoderDecoder", "get_encoder", "get_metapath_decoder",

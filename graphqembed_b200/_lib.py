@@ -35,13 +35,25 @@ DECODER_ID = {"bilinear": 0, "transe": 1, "bilinear-diag": 2}
 INTER_ID = {"mean": 0, "min": 1, "mean-simple": 2, "min-simple": 3}
 PRECISION_ID = {"bf16x3": 0, "fp32": 1}
 COMPOSE_ID = {"off": 0, "auto": 1, "always": 2}
-ABI_VERSION = 3
+ABI_VERSION = 4
+
+
+GQE_ERR_INDEX = -6
 
 
 class GqeError(RuntimeError):
     def __init__(self, code, message):
         RuntimeError.__init__(self, "gqe error %d: %s" % (code, message))
         self.code = code
+
+
+class GqeIndexError(GqeError, KeyError, IndexError):
+    """A node id that is not in the bound node map (the reference raises KeyError from its
+    node_maps dict, bio/data_utils.py:21) or a row outside its table (nn.Embedding's
+    IndexError).  Catchable as either."""
+
+    def __str__(self):
+        return RuntimeError.__str__(self)
 
 
 class Plan(C.Structure):
@@ -67,6 +79,11 @@ _SIGNATURES = {
     "gqe_set_precision": (C.c_int, [_P, C.c_int32]),
     "gqe_get_precision": (C.c_int, [_P]),
     "gqe_set_compose": (C.c_int, [_P, C.c_int32]),
+    "gqe_set_weight_cache": (C.c_int, [_P, C.c_int32]),
+    "gqe_invalidate_weights": (C.c_int, [_P]),
+    "gqe_weight_prep_count": (C.c_int64, [_P]),
+    "gqe_bind_node_maps": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gqe_index_error": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "gqe_last_error": (C.c_char_p, [_P]),
     "gqe_launch_count": (C.c_int64, [_P]),
     "gqe_debug_set_phase_log": (C.c_int, [_P, _P, C.c_int64]),
@@ -78,6 +95,14 @@ _SIGNATURES = {
     "gqe_margin_loss_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
     "gqe_score_grouped_device": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.c_int64, _P, _P, C.c_int32, _P,
                                            C.c_float, _P]),
+    "gqe_score_nodes_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, C.c_int64, _P, _P, _P]),
+    "gqe_margin_loss_nodes_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_score_grouped_nodes_device": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.c_int64, _P, _P, C.c_int32, _P,
+                                                 C.c_float, _P]),
+    "gqe_score_nodes_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, C.c_int64, _P, _P, _P]),
+    "gqe_margin_loss_nodes_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_score_grouped_nodes_host": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.c_int64, _P, _P, C.c_int32, _P,
+                                               C.c_float, _P]),
     "gqe_score_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, C.c_int64, _P, _P, _P]),
     "gqe_margin_loss_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
     "gqe_score_grouped_host": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.c_int64, _P, _P, C.c_int32, _P,
@@ -202,7 +227,8 @@ class Context(object):
 
     def _check(self, rc):
         if rc != 0:
-            raise GqeError(rc, self._lib.gqe_last_error(self._h).decode())
+            msg = self._lib.gqe_last_error(self._h).decode()
+            raise (GqeIndexError if rc == GQE_ERR_INDEX else GqeError)(rc, msg)
 
     def set_stream(self, stream):
         self._check(self._lib.gqe_set_stream(self._h, _P(stream or 0)))
@@ -221,6 +247,29 @@ class Context(object):
 
     def launch_count(self):
         return int(self._lib.gqe_launch_count(self._h))
+
+    def set_weight_cache(self, on):
+        """Cache packed / pre-multiplied operator matrices across calls (default on); with the
+        cache on, call ``invalidate_weights`` after changing a bound matrix in place."""
+        self._check(self._lib.gqe_set_weight_cache(self._h, 1 if on else 0))
+
+    def invalidate_weights(self):
+        self._check(self._lib.gqe_invalidate_weights(self._h))
+
+    def weight_prep_count(self):
+        return int(self._lib.gqe_weight_prep_count(self._h))
+
+    def bind_node_maps(self, lut_ptrs, bases, lens):
+        """Per mode: device pointer of the int32 lut (0: affine map), first node id, lut length."""
+        n = len(bases)
+        lut = _ptr_array(lut_ptrs) if lut_ptrs is not None else None
+        self._check(self._lib.gqe_bind_node_maps(self._h, n, lut, (C.c_int64 * n)(*[int(b) for b in bases]),
+                                                 (C.c_int64 * n)(*[int(x) for x in lens])))
+
+    def index_error(self):
+        """Synchronise and raise GqeIndexError if a kernel of this context saw a bad index."""
+        k, m, v = C.c_int32(), C.c_int32(), C.c_int64()
+        self._check(self._lib.gqe_index_error(self._h, C.byref(k), C.byref(m), C.byref(v)))
 
     def debug_set_phase_log(self, log_ptr, n_tiles):
         self._check(self._lib.gqe_debug_set_phase_log(self._h, _P(log_ptr or 0), int(n_tiles)))
@@ -242,40 +291,45 @@ class Context(object):
                                                     int(d if d_expand is None else d_expand)))
 
     # -- fused path, device buffers (raw device pointers as ints) -----------------
-    def score_device(self, plan, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, out_scores):
-        self._check(self._lib.gqe_score_device(self._h, C.byref(plan), n_queries, anchor_rows, n_pairs, target_rows,
-                                               target_offsets, out_scores))
+    # ``nodes=True`` selects the "_nodes" twin: the index arrays hold node ids, mapped to rows
+    # inside the kernels through the bound node maps.
+    def score_device(self, plan, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, out_scores, nodes=False):
+        fn = self._lib.gqe_score_nodes_device if nodes else self._lib.gqe_score_device
+        self._check(fn(self._h, C.byref(plan), n_queries, anchor_rows, n_pairs, target_rows, target_offsets, out_scores))
 
-    def margin_loss_device(self, plan, n_queries, anchor_rows, pair_rows, margin, out_loss, out_scores=None):
-        self._check(self._lib.gqe_margin_loss_device(self._h, C.byref(plan), n_queries, anchor_rows, pair_rows,
-                                                     float(margin), out_loss, out_scores))
+    def margin_loss_device(self, plan, n_queries, anchor_rows, pair_rows, margin, out_loss, out_scores=None, nodes=False):
+        fn = self._lib.gqe_margin_loss_nodes_device if nodes else self._lib.gqe_margin_loss_device
+        self._check(fn(self._h, C.byref(plan), n_queries, anchor_rows, pair_rows, float(margin), out_loss, out_scores))
 
     def score_grouped_device(self, segments, n_queries_total, anchor_rows, target_rows, targets_per_query,
-                             out_scores, margin=1.0, out_loss=None):
-        self._check(self._lib.gqe_score_grouped_device(self._h, segments, len(segments), n_queries_total, anchor_rows,
-                                                       target_rows, targets_per_query, out_scores, float(margin),
-                                                       out_loss))
+                             out_scores, margin=1.0, out_loss=None, nodes=False):
+        fn = self._lib.gqe_score_grouped_nodes_device if nodes else self._lib.gqe_score_grouped_device
+        self._check(fn(self._h, segments, len(segments), n_queries_total, anchor_rows, target_rows, targets_per_query,
+                       out_scores, float(margin), out_loss))
 
     # -- fused path, host buffers (numpy arrays) -----------------------------------
-    def score_host(self, plan, anchor_rows, target_rows, target_offsets, out_scores):
+    def score_host(self, plan, anchor_rows, target_rows, target_offsets, out_scores, nodes=False):
         nq = anchor_rows.shape[1]
         off = None if target_offsets is None else target_offsets.ctypes.data
-        self._check(self._lib.gqe_score_host(self._h, C.byref(plan), nq, anchor_rows.ctypes.data, target_rows.size,
-                                             target_rows.ctypes.data, off, out_scores.ctypes.data))
+        fn = self._lib.gqe_score_nodes_host if nodes else self._lib.gqe_score_host
+        self._check(fn(self._h, C.byref(plan), nq, anchor_rows.ctypes.data, target_rows.size, target_rows.ctypes.data,
+                       off, out_scores.ctypes.data))
 
-    def margin_loss_host(self, plan, anchor_rows, pair_rows, margin, out_loss, out_scores=None):
+    def margin_loss_host(self, plan, anchor_rows, pair_rows, margin, out_loss, out_scores=None, nodes=False):
         nq = anchor_rows.shape[1]
         sc = None if out_scores is None else out_scores.ctypes.data
-        self._check(self._lib.gqe_margin_loss_host(self._h, C.byref(plan), nq, anchor_rows.ctypes.data,
-                                                   pair_rows.ctypes.data, float(margin), out_loss.ctypes.data, sc))
+        fn = self._lib.gqe_margin_loss_nodes_host if nodes else self._lib.gqe_margin_loss_host
+        self._check(fn(self._h, C.byref(plan), nq, anchor_rows.ctypes.data, pair_rows.ctypes.data, float(margin),
+                       out_loss.ctypes.data, sc))
 
     def score_grouped_host(self, segments, anchor_rows, target_rows, targets_per_query, out_scores, margin=1.0,
-                           out_loss=None):
+                           out_loss=None, nodes=False):
         nq = anchor_rows.shape[1]
         sc = None if out_scores is None else out_scores.ctypes.data
         ls = None if out_loss is None else out_loss.ctypes.data
-        self._check(self._lib.gqe_score_grouped_host(self._h, segments, len(segments), nq, anchor_rows.ctypes.data,
-                                                     target_rows.ctypes.data, targets_per_query, sc, float(margin), ls))
+        fn = self._lib.gqe_score_grouped_nodes_host if nodes else self._lib.gqe_score_grouped_host
+        self._check(fn(self._h, segments, len(segments), nq, anchor_rows.ctypes.data, target_rows.ctypes.data,
+                       targets_per_query, sc, float(margin), ls))
 
     # -- operator level ---------------------------------------------------------------
     def encode_device(self, mode, n, rows, out):

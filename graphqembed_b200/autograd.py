@@ -208,10 +208,11 @@ class DifferentiablePath(object):
         comb = _Aggregate.apply(self.ctx, True, use_min, hidden[0], hidden[1], hidden[2] if len(hidden) > 2 else None)
         return _Matmul.apply(post, comb, self.ctx, False)                          # decoders.py:299
 
-    # -- model.py:70-109; ``targets`` is a list of node-id lists, scored against ONE query side ---
-    def scores(self, formula, queries, targets):
+    # -- model.py:70-109; ``anchor_nodes[k]`` holds the node ids of anchor slot k, ``targets`` is a
+    #    list of node-id sequences, each scored against the ONE query side built here ---
+    def scores(self, formula, anchor_nodes, targets):
         qt = formula.query_type
-        anchors = lambda k: [q.anchor_nodes[k] for q in queries]
+        anchors = lambda k: anchor_nodes[k]
         if qt in CHAIN_TYPES:
             a = self.encode(anchors(0), formula.anchor_modes[0])
             return [self.path_score(self.encode(t, formula.target_mode), a, formula.rels) for t in targets]
@@ -237,14 +238,21 @@ class DifferentiablePath(object):
         return [_Cosine.apply(self.encode(t, formula.target_mode), q, self.ctx, False) for t in targets]
 
 
+def anchors_of(formula, queries):
+    """Per-slot anchor node ids of a list of Query objects (model.py:75,80,83,91)."""
+    n = len(queries)
+    return [np.fromiter((q.anchor_nodes[k] for q in queries), dtype=np.int64, count=n)
+            for k in range(len(formula.anchor_modes))]
+
+
 def forward(model, formula, queries, source_nodes):
-    out = DifferentiablePath(model).scores(formula, queries, [source_nodes])
+    out = DifferentiablePath(model).scores(formula, anchors_of(formula, queries), [source_nodes])
     return None if out is None else out[0]
 
 
-def margin_loss(model, formula, queries, neg_nodes, margin=1):
+def margin_loss(model, formula, anchor_nodes, pos_nodes, neg_nodes, margin=1):
     """model.py:122-126 with the query side built once for the positive and the negative pass."""
-    pos, neg = DifferentiablePath(model).scores(formula, queries, [[q.target_node for q in queries], neg_nodes])
+    pos, neg = DifferentiablePath(model).scores(formula, anchor_nodes, [pos_nodes, neg_nodes])
     loss = margin - (pos - neg)
     loss = torch.clamp(loss, min=0)
     return loss.mean()

@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(kBwdThreads) k_dot(const float* __restrict__ x
 //   g_t = (g - x_hat (x_hat . g)) / |t|,  scattered (atomicAdd) into the dense table gradient
 __global__ void __launch_bounds__(kBwdThreads) k_encode_bwd(const float* __restrict__ table, const int32_t* __restrict__ rows,
                                                             const float* __restrict__ gout, int d, int64_t n,
-                                                            float* __restrict__ gtable) {
+                                                            float* __restrict__ gtable, int64_t table_rows,
+                                                            unsigned long long* err) {
   extern __shared__ float sm[];
   float* gs = sm;  // [d][33]
   const int64_t c0 = (int64_t)blockIdx.x * kCols;
@@ -212,7 +213,12 @@ __global__ void __launch_bounds__(kBwdThreads) k_encode_bwd(const float* __restr
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = warp; c < nv; c += kBwdThreads / 32) {
-    const size_t row = (size_t)__ldg(rows + c0 + c);
+    const int64_t row_i = (int64_t)__ldg(rows + c0 + c);
+    if (row_i < 0 || row_i >= table_rows) {   // never scatter outside the gradient table
+      if (lane == 0) report_index(err, IDX_ERR_ROW_RANGE, 0, (int32_t)row_i);
+      continue;
+    }
+    const size_t row = (size_t)row_i;
     const float* t = table + row * d;
     float ss = 0.f, tg = 0.f;
     for (int k = lane; k < d; k += 32) {
@@ -283,10 +289,10 @@ cudaError_t launch_dot(int d, int64_t n, const float* x, const float* y, float* 
   return cudaGetLastError();
 }
 cudaError_t launch_encode_bwd(int d, int64_t n, const float* table, const int32_t* rows, const float* gout, float* gtable,
-                              cudaStream_t st) {
+                              int64_t table_rows, unsigned long long* err, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const size_t smem = (size_t)d * (kCols + 1) * sizeof(float);
-  k_encode_bwd<<<(unsigned)((n + kCols - 1) / kCols), kBwdThreads, smem, st>>>(table, rows, gout, d, n, gtable);
+  k_encode_bwd<<<(unsigned)((n + kCols - 1) / kCols), kBwdThreads, smem, st>>>(table, rows, gout, d, n, gtable, table_rows, err);
   return cudaGetLastError();
 }
 

@@ -39,10 +39,31 @@ struct gqe_ctx {
 
   // arithmetic of the d x d contractions (gqe_precision)
   int precision = GQE_PREC_BF16X3;
-  // tensor-core path: packed (bf16 hi/lo, pre-swizzled) copies of the matrices one
-  // launch uses, rebuilt on every call because the parameters are live
+  // tensor-core path: packed (bf16 hi/lo, pre-swizzled) images of the operator matrices.  The
+  // buffer is a CACHE across calls: slot i holds the image described by wcache[i] (a parameter
+  // matrix or a product of up to three, one orientation, one column order) until
+  // gqe_invalidate_weights / a re-bind drops it, so a call whose matrices are all cached
+  // launches the fused kernel alone.
   uint8_t* packed = nullptr;
   size_t packed_cap = 0;
+  struct WKey {
+    const float* f[3];
+    int n, right_assoc, chain_form, perm;
+    bool operator==(const WKey& o) const {
+      return n == o.n && f[0] == o.f[0] && f[1] == o.f[1] && f[2] == o.f[2] && right_assoc == o.right_assoc &&
+             chain_form == o.chain_form && perm == o.perm;
+    }
+  };
+  std::vector<WKey> wcache;
+  bool wcache_on = true;
+  int64_t weight_preps = 0;    // matrices packed so far (bench bookkeeping)
+
+  // node id -> table row maps (gqe_bind_node_maps); rows of the bound tables are in table_rows
+  std::vector<ModeDev> node_maps;
+  // first bad index seen by a kernel: DEVICE [2] and its mapped pinned twin for the *_host calls
+  unsigned long long* d_err = nullptr;
+  unsigned long long* h_err = nullptr;
+  unsigned long long* h_err_dev = nullptr;
 
   // diagnostics: per-tile phase stamps of the tensor-core kernel
   unsigned long long* phase_log = nullptr;
@@ -52,7 +73,6 @@ struct gqe_ctx {
   int compose = GQE_COMPOSE_AUTO;
   float* compose_buf = nullptr;
   size_t compose_cap = 0;
-  unsigned int* compose_done = nullptr;   // per-product tile counters of one compose launch
 
   // query embeddings of the many-targets-per-query path (fp32 [n_queries, d], grows on demand)
   float* qbuf = nullptr;
@@ -68,13 +88,7 @@ struct gqe_ctx {
   unsigned int* ticket = nullptr;
   unsigned int* tile_counter = nullptr;
 
-  // *_host entry points: the index H2D copies run on their own stream so that they overlap the
-  // weight preparation kernels (gqe_compose / gqe_pack) of the same call; the fused kernel
-  // waits for `h2d_done`
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t h2d_done = nullptr;
-  cudaEvent_t stream_idle = nullptr;
-  bool wait_h2d = false;
+  bool err_posted = false;     // the last kernel of the call copies the index-error word to h_err itself
 
   // staging for the *_host entry points (grow on demand)
   void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -151,12 +165,17 @@ extern "C" int gqe_create(int device, void* stream, gqe_ctx** out) {
   c->device = device;
   c->stream = (cudaStream_t)stream;
   if (cudaMalloc(&c->loss_acc, sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&c->d_err, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaHostAlloc((void**)&c->h_err, 2 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&c->h_err_dev, c->h_err, 0) != cudaSuccess ||
       cudaMalloc(&c->ticket, sizeof(unsigned int)) != cudaSuccess ||
       cudaMalloc(&c->tile_counter, sizeof(unsigned int)) != cudaSuccess) {
     delete c;
     return fail(nullptr, GQE_ERR_NOMEM, "gqe_create: cudaMalloc failed");
   }
   cudaMemset(c->loss_acc, 0, sizeof(double));
+  cudaMemset(c->d_err, 0, 2 * sizeof(unsigned long long));
+  c->h_err[0] = c->h_err[1] = 0ull;
   cudaMemset(c->ticket, 0, sizeof(unsigned int));
   cudaMemset(c->tile_counter, 0, sizeof(unsigned int));
   drop_stale_error("gqe_create (end)");
@@ -171,15 +190,13 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   cudaFree(c->packed);
   cudaFree(c->qbuf);
   cudaFree(c->compose_buf);
-  cudaFree(c->compose_done);
   cudaFree(c->loss_acc);
+  cudaFree(c->d_err);
+  if (c->h_err) cudaFreeHost(c->h_err);
   cudaFree(c->ticket);
   cudaFree(c->tile_counter);
   for (void* p : c->stage) cudaFree(p);
   if (c->h_loss) cudaFreeHost(c->h_loss);
-  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-  if (c->h2d_done) cudaEventDestroy(c->h2d_done);
-  if (c->stream_idle) cudaEventDestroy(c->stream_idle);
   drop_stale_error("gqe_destroy (end)");
   delete c;
 }
@@ -204,6 +221,37 @@ extern "C" int gqe_set_compose(gqe_ctx* c, int32_t mode) {
   if (mode < GQE_COMPOSE_OFF || mode > GQE_COMPOSE_ALWAYS)
     return fail(c, GQE_ERR_INVALID, "gqe_set_compose: unknown mode %d", mode);
   c->compose = mode;
+  return GQE_OK;
+}
+
+extern "C" int gqe_set_weight_cache(gqe_ctx* c, int32_t on) {
+  if (!c) return GQE_ERR_INVALID;
+  c->wcache_on = on != 0;
+  c->wcache.clear();
+  return GQE_OK;
+}
+extern "C" int gqe_invalidate_weights(gqe_ctx* c) {
+  if (!c) return GQE_ERR_INVALID;
+  c->wcache.clear();   // slots are rewritten in stream order: kernels in flight keep reading the old images
+  return GQE_OK;
+}
+extern "C" int64_t gqe_weight_prep_count(const gqe_ctx* c) { return c ? c->weight_preps : 0; }
+
+extern "C" int gqe_bind_node_maps(gqe_ctx* c, int32_t n_modes, const int32_t* const* lut, const int64_t* base,
+                                  const int64_t* len) {
+  if (!c) return GQE_ERR_INVALID;
+  if (n_modes == 0) { c->node_maps.clear(); return GQE_OK; }
+  if (n_modes < 0 || !base || !len) return fail(c, GQE_ERR_INVALID, "gqe_bind_node_maps: bad arguments");
+  if (n_modes > kMaxModes) return fail(c, GQE_ERR_UNSUPPORTED, "gqe_bind_node_maps: more than %d node types", kMaxModes);
+  std::vector<ModeDev> maps(n_modes);
+  for (int m = 0; m < n_modes; ++m) {
+    if (len[m] < 0) return fail(c, GQE_ERR_INVALID, "gqe_bind_node_maps: mode %d has a negative length", m);
+    maps[m].lut = lut ? lut[m] : nullptr;   // null: affine map row = node - base (identity ids: base = -1)
+    maps[m].base = base[m];
+    maps[m].len = len[m];
+    maps[m].rows = 0;
+  }
+  c->node_maps.swap(maps);
   return GQE_OK;
 }
 
@@ -263,6 +311,7 @@ extern "C" int gqe_bind_relations(gqe_ctx* c, int32_t decoder, int32_t n_rels, c
   for (int r = 0; r < n_rels; ++r)
     if (!params[r]) return fail(c, GQE_ERR_INVALID, "gqe_bind_relations: relation %d has no parameter", r);
   c->rels.assign(params, params + n_rels);
+  c->wcache.clear();
   c->decoder = decoder;
   c->rel_d = d;
   return GQE_OK;
@@ -276,6 +325,7 @@ extern "C" int gqe_bind_intersection(gqe_ctx* c, int32_t inter, int32_t n_modes,
   const bool deepsets = inter <= GQE_INTER_DEEPSETS_MIN;
   c->pre.clear();
   c->post.clear();
+  c->wcache.clear();
   if (deepsets) {
     if (n_modes <= 0 || !pre || !post) return fail(c, GQE_ERR_INVALID, "gqe_bind_intersection: pre/post required");
     if (d_expand != d)
@@ -304,12 +354,14 @@ static int resolve(gqe_ctx* c, const gqe_plan& pl, SegDev* s) {
   s->structure = pl.structure;
   s->n_anchor = na;
   s->tgt_table = c->tables[pl.target_mode];
+  s->tgt_mode = (int8_t)pl.target_mode;
   if (!s->tgt_table) return fail(c, GQE_ERR_UNBOUND, "target mode %d has no table on this rank", pl.target_mode);
   if (c->table_remote[pl.target_mode]) s->remote_mask |= 8u;
   for (int k = 0; k < na; ++k) {
     if (pl.anchor_mode[k] < 0 || pl.anchor_mode[k] >= nm)
       return fail(c, GQE_ERR_INVALID, "anchor %d mode %d out of range", k, pl.anchor_mode[k]);
     s->anc_table[k] = c->tables[pl.anchor_mode[k]];
+    s->anc_mode[k] = (int8_t)pl.anchor_mode[k];
     if (!s->anc_table[k])
       return fail(c, GQE_ERR_UNBOUND, "anchor %d mode %d has no table on this rank", k, pl.anchor_mode[k]);
     if (c->table_remote[pl.anchor_mode[k]]) s->remote_mask |= 1u << k;
@@ -345,10 +397,65 @@ static int ensure_partials(gqe_ctx* c, int64_t n) {
   return GQE_OK;
 }
 
-// The one launcher behind every fused entry point.
+// ---- index errors ----------------------------------------------------------------
+// Kernels report the first bad index (unknown node id, row outside its table) in c->d_err and
+// read row 0 instead.  *_host calls fetch the word with their result and fail with
+// GQE_ERR_INDEX; *_device calls are asynchronous, the caller polls gqe_index_error().
+static int index_error_from(gqe_ctx* c, unsigned long long w0, unsigned long long w1) {
+  const int kind = (int)(w0 >> 32), mode = (int)(w0 & 0xffffffffu);
+  const long long value = (long long)w1;
+  if (kind == IDX_ERR_UNKNOWN_NODE)
+    return fail(c, GQE_ERR_INDEX, "unknown node: id %lld is not in the node map of mode %d", value, mode);
+  return fail(c, GQE_ERR_INDEX, "row index out of range: %lld is outside the table of mode %d", value, mode);
+}
+
+extern "C" int gqe_index_error(gqe_ctx* c, int32_t* kind, int32_t* mode, int64_t* value) {
+  if (!c) return GQE_ERR_INVALID;
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  unsigned long long w[2] = {0ull, 0ull};
+  GQE_CUDA(c, cudaMemcpyAsync(w, c->d_err, sizeof w, cudaMemcpyDeviceToHost, c->stream));
+  GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (kind) *kind = (int32_t)(w[0] >> 32);
+  if (mode) *mode = (int32_t)(w[0] & 0xffffffffu);
+  if (value) *value = (int64_t)w[1];
+  if (w[0] == 0ull) return GQE_OK;
+  GQE_CUDA(c, cudaMemsetAsync(c->d_err, 0, sizeof w, c->stream));
+  return index_error_from(c, w[0], w[1]);
+}
+
+// ---- packed-weight cache ------------------------------------------------------------
+constexpr int kWeightSlots = 1024;  // packed images the cache can hold (256 MiB at d = 256, 64 MiB at d = 128)
+
+static int ensure_weight_buffers(gqe_ctx* c) {
+  const size_t need = (size_t)kWeightSlots * tc_packed_bytes(c->d);
+  if (c->packed_cap < need) {
+    GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->packed);
+    c->packed = nullptr;
+    c->packed_cap = 0;
+    c->wcache.clear();
+    GQE_CUDA(c, cudaMalloc(&c->packed, need));
+    c->packed_cap = need;
+  }
+  const size_t need_c = (size_t)kMaxCompose * c->d * c->d * sizeof(float);
+  if (c->compose != GQE_COMPOSE_OFF && c->compose_cap < need_c) {
+    GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->compose_buf);
+    c->compose_buf = nullptr;
+    c->compose_cap = 0;
+    GQE_CUDA(c, cudaMalloc(&c->compose_buf, need_c));
+    c->compose_cap = need_c;
+  }
+  return GQE_OK;
+}
+
+// The one launcher behind every fused entry point.  index_kind: 0 = the index arrays hold table
+// rows, 1 = node ids (mapped through gqe_bind_node_maps inside the kernels).  err_host: mapped
+// pinned word the last CTA copies the index-error word to (the *_host calls), or null.
 static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_t nq_total,
                      const int32_t* anchor_rows, int64_t n_pairs, const int32_t* target_rows,
-                     const int64_t* target_offsets, int32_t T, float* out_scores, float margin, float* out_loss) {
+                     const int64_t* target_offsets, int32_t T, float* out_scores, float margin, float* out_loss,
+                     int index_kind, unsigned long long* err_host = nullptr) {
   if (!c) return GQE_ERR_INVALID;
   if (!segs || n_segs <= 0) return fail(c, GQE_ERR_INVALID, "no segments");
   if (nq_total < 0 || n_pairs < 0) return fail(c, GQE_ERR_INVALID, "negative size");
@@ -358,6 +465,11 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
   if (out_loss && T != 2) return fail(c, GQE_ERR_INVALID, "margin loss needs exactly 2 targets per query");
   drop_stale_error("fused entry");
   if (!target_offsets && T <= 0 && nq_total > 0) return fail(c, GQE_ERR_INVALID, "targets per query must be positive");
+  if (index_kind && c->node_maps.empty()) return fail(c, GQE_ERR_UNBOUND, "node maps are not bound (gqe_bind_node_maps)");
+  if (index_kind && c->node_maps.size() != c->tables.size())
+    return fail(c, GQE_ERR_INVALID, "node maps cover %d modes, tables %d", (int)c->node_maps.size(), (int)c->tables.size());
+  if ((int)c->tables.size() > kMaxModes)
+    return fail(c, GQE_ERR_UNSUPPORTED, "more than %d node types are not supported by the fused kernels", kMaxModes);
   GQE_CUDA(c, cudaSetDevice(c->device));
 
   if (out_loss) {
@@ -389,6 +501,14 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
   lp.tile_counter = c->tile_counter;
   lp.phase_log = c->phase_log;
   lp.phase_cap = c->phase_cap;
+  lp.index_kind = index_kind;
+  lp.err = c->d_err;
+  for (size_t m = 0; m < c->tables.size(); ++m) {
+    ModeDev& md = lp.mode[m];
+    if (index_kind) md = c->node_maps[m];
+    else { md.lut = nullptr; md.base = 0; md.len = c->table_rows[m]; }
+    md.rows = c->table_rows[m];
+  }
 
   // Bilinear d x d contractions go to the tensor cores (tcgen05, bf16x3 split) unless the
   // context asks for exact fp32; the ragged target layout stays on the fp32 kernels.
@@ -411,32 +531,18 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     }
     lp.q_out = c->qbuf;
   }
+  // TransE / DistMult with chains or the element-wise intersections have no contraction at all:
+  // they run the streaming warp-per-query kernel (gqe_vec.cu), pure HBM traffic
+  const bool use_vec = !use_tc && c->decoder != GQE_DEC_BILINEAR && !pairs_mode && !target_offsets && T <= 2 &&
+                       (c->inter >= GQE_INTER_SIMPLE_MEAN || c->inter < 0 || [&] {
+                         for (int32_t k = 0; k < n_segs; ++k)
+                           if (segs[k].plan.structure >= GQE_INTER2 && segs[k].query_end > segs[k].query_begin) return false;
+                         return true;
+                       }());
   const int64_t tile_rows = use_tc ? kTcTileRows : kTileRows;
-  if (use_tc && c->compose != GQE_COMPOSE_OFF) {
-    const size_t need = (size_t)kMaxCompose * c->d * c->d * sizeof(float);
-    if (c->compose_cap < need) {
-      GQE_CUDA(c, cudaStreamSynchronize(c->stream));
-      cudaFree(c->compose_buf);
-      c->compose_buf = nullptr;
-      c->compose_cap = 0;
-      GQE_CUDA(c, cudaMalloc(&c->compose_buf, need));
-      c->compose_cap = need;
-    }
-    if (!c->compose_done) {
-      GQE_CUDA(c, cudaMalloc(&c->compose_done, kMaxCompose * sizeof(unsigned int)));
-      GQE_CUDA(c, cudaMemsetAsync(c->compose_done, 0, kMaxCompose * sizeof(unsigned int), c->stream));
-    }
-  }
   if (use_tc) {
-    const size_t need = (size_t)kMaxPack * tc_packed_bytes(c->d);
-    if (c->packed_cap < need) {
-      GQE_CUDA(c, cudaStreamSynchronize(c->stream));
-      cudaFree(c->packed);
-      c->packed = nullptr;
-      c->packed_cap = 0;
-      GQE_CUDA(c, cudaMalloc(&c->packed, need));
-      c->packed_cap = need;
-    }
+    if (int rc = ensure_weight_buffers(c)) return rc;
+    if (!c->wcache_on) c->wcache.clear();   // parameters are treated as live: re-prepared every call
   }
 
   int32_t last_nonempty = -1;
@@ -448,39 +554,51 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     int64_t tiles = 0;
     PackParams pp;
     int n_pack = 0;
-    // packed copy of one matrix in the orientation its use needs (deduplicated per launch)
-    // `perm`: the matrix of a contraction whose accumulator is scored in the TMEM fragment
-    // layout (the last hop of a chain) has its output columns permuted at packing time
-    auto packed_of = [&](const float* src, int chain_form, int perm = 0) -> const float* {
-      int k = 0;
-      for (; k < n_pack; ++k)
-        if (pp.e[k].src == src && pp.e[k].chain_form == chain_form && pp.e[k].perm == perm) break;
-      if (k == n_pack) {
-        pp.e[k].src = src;
-        pp.e[k].chain_form = chain_form;
-        pp.e[k].perm = perm;
-        ++n_pack;
-      }
-      return reinterpret_cast<const float*>(c->packed + (size_t)k * tc_packed_bytes(c->d));
-    };
-    // fp32 products of runs of linear operators (deduplicated per launch).  A 3-factor run is
-    // two entries, the second naming the first as its operand (dep): ONE launch computes both.
-    ComposeParams cw;
-    int n_cw = 0;
-    auto product = [&](const float* a, const float* b) -> const float* {
-      for (int k = 0; k < n_cw; ++k)
-        if (cw.e[k].a == a && cw.e[k].b == b) return cw.e[k].dst;
-      ComposeEntry& e = cw.e[n_cw];
+    // fp32 products of runs of linear operators, level 0 = both operands are parameters, level 1 =
+    // one operand is a level-0 product of this call (three-factor runs): two stream-ordered launches
+    ComposeParams cw[2];
+    int n_cw[2] = {0, 0};
+    // cache full (worst case of this launch: 5 images per formula): start over
+    if (use_tc && (int)c->wcache.size() + 5 * std::min<int>(n_segs - i, kMaxSegs) > kWeightSlots) c->wcache.clear();
+    auto product = [&](const float* a, const float* b, int level) -> const float* {
+      for (int l = 0; l < 2; ++l)
+        for (int k = 0; k < n_cw[l]; ++k)
+          if (cw[l].e[k].a == a && cw[l].e[k].b == b) return cw[l].e[k].dst;
+      ComposeEntry& e = cw[level].e[n_cw[level]];
       e.a = a;
       e.b = b;
-      e.dep_a = e.dep_b = -1;
-      for (int k = 0; k < n_cw; ++k) {
-        if (cw.e[k].dst == a) e.dep_a = k;
-        if (cw.e[k].dst == b) e.dep_b = k;
-      }
-      e.dst = c->compose_buf + (size_t)n_cw * c->d * c->d;
-      ++n_cw;
+      e.dst = c->compose_buf + (size_t)(n_cw[0] + n_cw[1]) * c->d * c->d;
+      ++n_cw[level];
       return e.dst;
+    };
+    // Packed image of a matrix or of a product of up to three (f0 f1 f2; right_assoc: f0 (f1 f2))
+    // in the orientation its use needs.  `perm`: the matrix of a contraction whose accumulator is
+    // scored in the TMEM fragment layout (the last hop of a chain) has its output columns
+    // permuted at packing time.  Served from the context's cache when present.
+    auto packed_of = [&](const float* f0, const float* f1, const float* f2, int right_assoc, int chain_form,
+                         int perm) -> const float* {
+      gqe_ctx::WKey key;
+      key.f[0] = f0; key.f[1] = f1; key.f[2] = f2;
+      key.n = f2 ? 3 : (f1 ? 2 : 1);
+      key.right_assoc = key.n == 3 ? right_assoc : 0;
+      key.chain_form = chain_form;
+      key.perm = perm;
+      size_t slot = 0;
+      for (; slot < c->wcache.size(); ++slot)
+        if (c->wcache[slot] == key) break;
+      uint8_t* dst = c->packed + slot * tc_packed_bytes(c->d);
+      if (slot == c->wcache.size()) {
+        c->wcache.push_back(key);
+        const float* src = f0;
+        if (key.n == 2) src = product(f0, f1, 0);
+        else if (key.n == 3) src = right_assoc ? product(f0, product(f1, f2, 0), 1) : product(product(f0, f1, 0), f2, 1);
+        pp.e[n_pack].src = src;
+        pp.e[n_pack].dst = dst;
+        pp.e[n_pack].chain_form = chain_form;
+        pp.e[n_pack].perm = perm;
+        ++n_pack;
+      }
+      return reinterpret_cast<const float*>(dst);
     };
     int first_structure = -1;
     bool uniform = true;
@@ -502,48 +620,45 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
       if (use_tc) {
         const int st = g.plan.structure;
         const int chain_form = st <= GQE_CHAIN3 ? 1 : 0;
-        // composing pays off once a few tiles share the product (d^3 fp32 FMAs per product)
-        const bool compose = c->compose == GQE_COMPOSE_ALWAYS || (c->compose == GQE_COMPOSE_AUTO && rows >= 8 * kTcTileRows);
+        // composing pays off once a few tiles share the product (d^3 FMAs per product); with the
+        // cache on, the product is reused by later calls as well
+        const bool compose = c->compose == GQE_COMPOSE_ALWAYS ||
+                             (c->compose == GQE_COMPOSE_AUTO && (rows >= 8 * kTcTileRows || c->wcache_on));
         const bool ds = s->pre != nullptr;
-        // the contraction whose accumulator the kernel scores in the TMEM fragment layout
-        // (tc::score_frag: the last hop of a chain) is packed with permuted output columns;
-        // the intersections are scored through the transposed tile (fp = 0)
-        const int fp = 0;
+        auto one = [&](const float* m, int cf, int perm = 0) { return packed_of(m, nullptr, nullptr, 0, cf, perm); };
         if (!compose || st == GQE_CHAIN1 || (st >= GQE_INTER2 && !ds && st != GQE_INTER_CHAIN3)) {
-          // nothing to merge: one contraction per operator, as written in the reference
+          // nothing to merge: one contraction per operator, as written in the reference; the
+          // accumulator of a chain's last hop is scored in the TMEM fragment layout (perm)
           for (int k = 0; k < n_rels_of(st); ++k) {
             const bool last = k == n_rels_of(st) - 1;
-            s->rel[k] = packed_of(s->rel[k], chain_form, last && (st <= GQE_CHAIN3 || (st == GQE_CHAIN_INTER3 && fp)));
+            s->rel[k] = one(s->rel[k], chain_form, last && st <= GQE_CHAIN3);
           }
-          if (s->pre) s->pre = packed_of(s->pre, 0);
-          if (s->post) s->post = packed_of(s->post, 0, st != GQE_CHAIN_INTER3 && fp);
+          if (s->pre) s->pre = one(s->pre, 0);
+          if (s->post) s->post = one(s->post, 0);
         } else {
           s->composed = 1;
           const float *r0 = s->rel[0], *r1 = s->rel[1], *r2 = s->rel[2], *pre = s->pre, *post = s->post;
           s->rel[0] = s->rel[1] = s->rel[2] = s->pre = s->post = nullptr;
           if (st <= GQE_CHAIN3) {                       // act.mm(M1).mm(M2)[.mm(M3)]  (decoders.py:143-145)
-            const float* w = product(r0, r1);
-            if (st == GQE_CHAIN3) w = product(w, r2);
-            s->rel[0] = packed_of(w, 1, 1);
+            s->rel[0] = packed_of(r0, r1, st == GQE_CHAIN3 ? r2 : nullptr, 0, 1, 1);
           } else if (st == GQE_INTER2 || st == GQE_INTER3) {   // relu(pre.mm(R_b.mm(e)))  (decoders.py:289-292)
-            s->rel[0] = packed_of(product(pre, r0), 0);
-            s->rel[1] = packed_of(product(pre, r1), 0);
-            if (st == GQE_INTER3) s->rel[2] = packed_of(product(pre, r2), 0);
-            s->post = packed_of(post, 0, fp);
+            s->rel[0] = packed_of(pre, r0, nullptr, 0, 0, 0);
+            s->rel[1] = packed_of(pre, r1, nullptr, 0, 0, 0);
+            if (st == GQE_INTER3) s->rel[2] = packed_of(pre, r2, nullptr, 0, 0, 0);
+            s->post = one(post, 0);
           } else if (st == GQE_INTER_CHAIN3) {          // branch 1: R2a.mm(R2b.mm(e))  (model.py:84-86)
-            const float* t = product(r2, r1);
             if (ds) {
-              s->rel[0] = packed_of(product(pre, r0), 0);
-              s->rel[1] = packed_of(product(pre, t), 0);
-              s->post = packed_of(post, 0, fp);
+              s->rel[0] = packed_of(pre, r0, nullptr, 0, 0, 0);
+              s->rel[1] = packed_of(pre, r2, r1, 1, 0, 0);
+              s->post = one(post, 0);
             } else {
-              s->rel[0] = packed_of(r0, 0);
-              s->rel[1] = packed_of(t, 0);
+              s->rel[0] = one(r0, 0);
+              s->rel[1] = packed_of(r2, r1, nullptr, 0, 0, 0);
             }
           } else {                                      // 3-chain_inter (DeepSets): R1.mm(post.mm(.))  (model.py:106-107)
-            s->rel[0] = packed_of(product(pre, r0), 0);
-            s->rel[1] = packed_of(product(pre, r1), 0);
-            s->post = packed_of(product(r2, post), 0, fp);
+            s->rel[0] = packed_of(pre, r0, nullptr, 0, 0, 0);
+            s->rel[1] = packed_of(pre, r1, nullptr, 0, 0, 0);
+            s->post = packed_of(r2, post, nullptr, 0, 0, 0);
           }
         }
       }
@@ -574,6 +689,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     lp.n_segs = n;
     lp.n_tiles = tiles;
     lp.final_launch = i > last_nonempty ? 1 : 0;
+    lp.err_host = lp.final_launch ? err_host : nullptr;
     if (out_loss) {
       c->loss_dirty = true;   // until the final launch of the call has been issued
       int rc = ensure_partials(c, tiles);
@@ -582,34 +698,24 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
     }
     // single formula -> that structure's own kernel; otherwise the grouped kernel
     const int structure = (n == 1 && uniform) ? first_structure : -1;
-    auto wait_for_indices = [&]() -> int {
-      if (c->wait_h2d) {
-        GQE_CUDA(c, cudaStreamWaitEvent(c->stream, c->h2d_done, 0));
-        c->wait_h2d = false;
-      }
-      return GQE_OK;
-    };
     if (use_tc) {
-      if (n_cw > 0) {
-        bool deps = false;
-        for (int k = 0; k < n_cw; ++k) deps = deps || cw.e[k].dep_a >= 0 || cw.e[k].dep_b >= 0;
-        // tile counters of this launch's products start at zero (only read when a product
-        // depends on another one)
-        if (deps) GQE_CUDA(c, cudaMemsetAsync(c->compose_done, 0, n_cw * sizeof(unsigned int), c->stream));
-        cw.done = c->compose_done;
-        cw.target = (unsigned int)((c->d / 64) * (c->d / compose_tile_rows()));   // tiles per product
-        GQE_CUDA(c, launch_compose(c->d, cw, n_cw, c->stream));
+      for (int l = 0; l < 2; ++l)
+        if (n_cw[l] > 0) {
+          GQE_CUDA(c, launch_compose(c->d, cw[l], n_cw[l], c->stream));
+          c->launches += 1;
+        }
+      if (n_pack > 0) {
+        GQE_CUDA(c, launch_pack(c->d, pp, n_pack, c->stream));
         c->launches += 1;
+        c->weight_preps += n_pack;
       }
-      pp.dst = c->packed;
-      // (the wait for the index copies sits before gqe_pack: the fused kernel is launched
-      // programmatically dependent on gqe_pack and must follow it directly in the stream)
-      if (int rc = wait_for_indices()) return rc;
-      GQE_CUDA(c, launch_pack(c->d, pp, n_pack, c->stream));
       GQE_CUDA(c, launch_fused_tc(c->d, structure, lp, tiles, c->stream));
-      c->launches += 2;
+      c->launches += 1;
+      if (lp.err_host) c->err_posted = true;
+    } else if (use_vec) {
+      GQE_CUDA(c, launch_fused_vec(c->d, lp, c->stream));
+      c->launches += 1;
     } else {
-      if (int rc = wait_for_indices()) return rc;
       GQE_CUDA(c, launch_fused_simt(c->d, structure, lp, tiles, c->stream));
       c->launches += 1;
     }
@@ -624,6 +730,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
         ps.tgt_table = lp.seg[k].tgt_table;
         ps.q_begin = lp.seg[k].q_begin;
         ps.q_end = lp.seg[k].q_end;
+        ps.mode = lp.mode[lp.seg[k].tgt_mode];
         n_p += target_offsets ? n_pairs : (ps.q_end - ps.q_begin) * T;
       }
       if (qp.n_segs > 0) {
@@ -633,6 +740,8 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
         qp.target_offsets = target_offsets;
         qp.n_pairs = n_pairs;
         qp.out_scores = out_scores;
+        qp.index_kind = index_kind;
+        qp.err = c->d_err;
         GQE_CUDA(c, launch_score_pairs(c->d, qp, n_p, c->stream));
         c->launches += 1;
       }
@@ -652,24 +761,46 @@ static int regular_T(gqe_ctx* c, int64_t nq, int64_t n_pairs, const int64_t* off
   return GQE_OK;
 }
 
-extern "C" int gqe_score_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
-                                int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets,
-                                float* out_scores) {
+static int score_device_impl(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                             int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets,
+                             float* out_scores, int index_kind) {
   if (!c) return GQE_ERR_INVALID;
   if (!plan || (!out_scores && n_pairs > 0)) return fail(c, GQE_ERR_INVALID, "gqe_score_device: null argument");
   int32_t T;
   int rc = regular_T(c, n_queries, n_pairs, target_offsets, &T);
   if (rc != GQE_OK) return rc;
   gqe_segment seg{*plan, 0, n_queries};
-  return run_fused(c, &seg, 1, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, T, out_scores, 0.f, nullptr);
+  return run_fused(c, &seg, 1, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, T, out_scores, 0.f, nullptr,
+                   index_kind);
+}
+extern "C" int gqe_score_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                                int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets,
+                                float* out_scores) {
+  return score_device_impl(c, plan, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, out_scores, 0);
+}
+extern "C" int gqe_score_nodes_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_nodes,
+                                      int64_t n_pairs, const int32_t* target_nodes, const int64_t* target_offsets,
+                                      float* out_scores) {
+  return score_device_impl(c, plan, n_queries, anchor_nodes, n_pairs, target_nodes, target_offsets, out_scores, 1);
 }
 
-extern "C" int gqe_margin_loss_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
-                                      const int32_t* pair_rows, float margin, float* out_loss, float* out_scores) {
+static int margin_loss_device_impl(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                                   const int32_t* pair_rows, float margin, float* out_loss, float* out_scores,
+                                   int index_kind) {
   if (!c) return GQE_ERR_INVALID;
   if (!plan || !out_loss) return fail(c, GQE_ERR_INVALID, "gqe_margin_loss_device: null argument");
   gqe_segment seg{*plan, 0, n_queries};
-  return run_fused(c, &seg, 1, n_queries, anchor_rows, 2 * n_queries, pair_rows, nullptr, 2, out_scores, margin, out_loss);
+  return run_fused(c, &seg, 1, n_queries, anchor_rows, 2 * n_queries, pair_rows, nullptr, 2, out_scores, margin, out_loss,
+                   index_kind);
+}
+extern "C" int gqe_margin_loss_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                                      const int32_t* pair_rows, float margin, float* out_loss, float* out_scores) {
+  return margin_loss_device_impl(c, plan, n_queries, anchor_rows, pair_rows, margin, out_loss, out_scores, 0);
+}
+extern "C" int gqe_margin_loss_nodes_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries,
+                                            const int32_t* anchor_nodes, const int32_t* pair_nodes, float margin,
+                                            float* out_loss, float* out_scores) {
+  return margin_loss_device_impl(c, plan, n_queries, anchor_nodes, pair_nodes, margin, out_loss, out_scores, 1);
 }
 
 extern "C" int gqe_score_grouped_device(gqe_ctx* c, const gqe_segment* segments, int32_t n_segments,
@@ -677,7 +808,15 @@ extern "C" int gqe_score_grouped_device(gqe_ctx* c, const gqe_segment* segments,
                                         int32_t targets_per_query, float* out_scores, float margin, float* out_loss) {
   if (!c) return GQE_ERR_INVALID;
   return run_fused(c, segments, n_segments, n_queries_total, anchor_rows, n_queries_total * targets_per_query,
-                   target_rows, nullptr, targets_per_query, out_scores, margin, out_loss);
+                   target_rows, nullptr, targets_per_query, out_scores, margin, out_loss, 0);
+}
+extern "C" int gqe_score_grouped_nodes_device(gqe_ctx* c, const gqe_segment* segments, int32_t n_segments,
+                                              int64_t n_queries_total, const int32_t* anchor_nodes,
+                                              const int32_t* target_nodes, int32_t targets_per_query, float* out_scores,
+                                              float margin, float* out_loss) {
+  if (!c) return GQE_ERR_INVALID;
+  return run_fused(c, segments, n_segments, n_queries_total, anchor_nodes, n_queries_total * targets_per_query,
+                   target_nodes, nullptr, targets_per_query, out_scores, margin, out_loss, 1);
 }
 
 // ---- host-buffer variants ------------------------------------------------------
@@ -702,7 +841,7 @@ static int max_anchors(const gqe_segment* segs, int n) {
 
 static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_t nq, const int32_t* anchor_rows,
                           int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets, int32_t T,
-                          float* out_scores, float margin, float* out_loss) {
+                          float* out_scores, float margin, float* out_loss, int index_kind) {
   if (!c) return GQE_ERR_INVALID;
   if (!segs || n_segs <= 0) return fail(c, GQE_ERR_INVALID, "no segments");
   GQE_CUDA(c, cudaSetDevice(c->device));
@@ -726,31 +865,21 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
   }
   if (nq > 0) {
     if (!anchor_rows || !target_rows) return fail(c, GQE_ERR_INVALID, "index arrays are null");
-    if (!c->copy_stream) {
-      GQE_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-      GQE_CUDA(c, cudaEventCreateWithFlags(&c->h2d_done, cudaEventDisableTiming));
-      GQE_CUDA(c, cudaEventCreateWithFlags(&c->stream_idle, cudaEventDisableTiming));
-    }
-    // the staging buffers may still be read by work queued earlier on the compute stream
-    GQE_CUDA(c, cudaEventRecord(c->stream_idle, c->stream));
-    GQE_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->stream_idle, 0));
+    // in stream order, in front of the kernels: with the packed weights cached there is nothing
+    // to overlap the copies with, and a second stream would only add event traffic to the call
     GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_ANCHOR], anchor_rows, sizeof(int32_t) * (size_t)na * nq,
-                                cudaMemcpyHostToDevice, c->copy_stream));
+                                cudaMemcpyHostToDevice, c->stream));
     GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_TARGET], target_rows, sizeof(int32_t) * (size_t)n_pairs,
-                                cudaMemcpyHostToDevice, c->copy_stream));
+                                cudaMemcpyHostToDevice, c->stream));
     if (target_offsets)
       GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_OFFSETS], target_offsets, sizeof(int64_t) * (size_t)(nq + 1),
-                                  cudaMemcpyHostToDevice, c->copy_stream));
-    GQE_CUDA(c, cudaEventRecord(c->h2d_done, c->copy_stream));
-    c->wait_h2d = true;   // consumed by the first kernel of run_fused that reads the indices
+                                  cudaMemcpyHostToDevice, c->stream));
   }
+  c->h_err[0] = 0ull;
+  c->err_posted = false;
   rc = run_fused(c, segs, n_segs, nq, (const int32_t*)c->stage[ST_ANCHOR], n_pairs, (const int32_t*)c->stage[ST_TARGET],
                  target_offsets ? (const int64_t*)c->stage[ST_OFFSETS] : nullptr, T,
-                 out_scores ? (float*)c->stage[ST_SCORES] : nullptr, margin, loss_dst);
-  if (c->wait_h2d) {   // nothing consumed the indices (empty batch / early error): keep the streams ordered
-    cudaStreamWaitEvent(c->stream, c->h2d_done, 0);
-    c->wait_h2d = false;
-  }
+                 out_scores ? (float*)c->stage[ST_SCORES] : nullptr, margin, loss_dst, index_kind, c->h_err_dev);
   if (rc != GQE_OK) return rc;
   if (out_scores && n_pairs > 0)
     GQE_CUDA(c, cudaMemcpyAsync(out_scores, c->stage[ST_SCORES], sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost,
@@ -758,42 +887,55 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
   const bool mapped_loss = out_loss && loss_dst == c->h_loss_dev;
   if (out_loss && !mapped_loss)
     GQE_CUDA(c, cudaMemcpyAsync(out_loss, c->stage[ST_LOSS], sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  // the index-error word: posted by the last CTA of the tensor-core kernel, fetched otherwise
+  if (!c->err_posted && nq > 0)
+    GQE_CUDA(c, cudaMemcpyAsync(c->h_err, c->d_err, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   GQE_CUDA(c, cudaStreamSynchronize(c->stream));
   if (mapped_loss) *out_loss = *(volatile float*)c->h_loss;
+  const unsigned long long w0 = *(volatile unsigned long long*)&c->h_err[0];
+  if (w0 != 0ull) {
+    const unsigned long long w1 = *(volatile unsigned long long*)&c->h_err[1];
+    cudaMemsetAsync(c->d_err, 0, 2 * sizeof(unsigned long long), c->stream);
+    return index_error_from(c, w0, w1);
+  }
   return GQE_OK;
 }
 
-extern "C" int gqe_score_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
-                              int64_t n_pairs, const int32_t* target_rows, const int64_t* target_offsets,
-                              float* out_scores) {
-  if (!c) return GQE_ERR_INVALID;
-  if (!plan || (!out_scores && n_pairs > 0)) return fail(c, GQE_ERR_INVALID, "gqe_score_host: null argument");
-  int32_t T;
-  int rc = regular_T(c, n_queries, n_pairs, target_offsets, &T);
-  if (rc != GQE_OK) return rc;
-  gqe_segment seg{*plan, 0, n_queries};
-  return run_fused_host(c, &seg, 1, n_queries, anchor_rows, n_pairs, target_rows, target_offsets, T, out_scores, 0.f,
-                        nullptr);
-}
-
-extern "C" int gqe_margin_loss_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
-                                    const int32_t* pair_rows, float margin, float* out_loss, float* out_scores) {
-  if (!c) return GQE_ERR_INVALID;
-  if (!plan || !out_loss) return fail(c, GQE_ERR_INVALID, "gqe_margin_loss_host: null argument");
-  gqe_segment seg{*plan, 0, n_queries};
-  return run_fused_host(c, &seg, 1, n_queries, anchor_rows, 2 * n_queries, pair_rows, nullptr, 2, out_scores, margin,
-                        out_loss);
-}
-
-extern "C" int gqe_score_grouped_host(gqe_ctx* c, const gqe_segment* segments, int32_t n_segments,
-                                      int64_t n_queries_total, const int32_t* anchor_rows, const int32_t* target_rows,
-                                      int32_t targets_per_query, float* out_scores, float margin, float* out_loss) {
-  if (!c) return GQE_ERR_INVALID;
-  // grouped anchors are always laid out with GQE_MAX_ANCHORS slots
-  if (!segments || n_segments <= 0) return fail(c, GQE_ERR_INVALID, "no segments");
-  return run_fused_host(c, segments, n_segments, n_queries_total, anchor_rows, n_queries_total * targets_per_query,
-                        target_rows, nullptr, targets_per_query, out_scores, margin, out_loss);
-}
+#define GQE_HOST_ENTRY_POINTS(SUFFIX, KIND)                                                                           \
+  extern "C" int gqe_score##SUFFIX##_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchors, \
+                                          int64_t n_pairs, const int32_t* targets, const int64_t* target_offsets,     \
+                                          float* out_scores) {                                                        \
+    if (!c) return GQE_ERR_INVALID;                                                                                   \
+    if (!plan || (!out_scores && n_pairs > 0)) return fail(c, GQE_ERR_INVALID, "gqe_score_host: null argument");      \
+    int32_t T;                                                                                                        \
+    int rc = regular_T(c, n_queries, n_pairs, target_offsets, &T);                                                    \
+    if (rc != GQE_OK) return rc;                                                                                      \
+    gqe_segment seg{*plan, 0, n_queries};                                                                             \
+    return run_fused_host(c, &seg, 1, n_queries, anchors, n_pairs, targets, target_offsets, T, out_scores, 0.f,      \
+                          nullptr, KIND);                                                                             \
+  }                                                                                                                   \
+  extern "C" int gqe_margin_loss##SUFFIX##_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries,                 \
+                                                const int32_t* anchors, const int32_t* pairs, float margin,          \
+                                                float* out_loss, float* out_scores) {                                \
+    if (!c) return GQE_ERR_INVALID;                                                                                   \
+    if (!plan || !out_loss) return fail(c, GQE_ERR_INVALID, "gqe_margin_loss_host: null argument");                   \
+    gqe_segment seg{*plan, 0, n_queries};                                                                             \
+    return run_fused_host(c, &seg, 1, n_queries, anchors, 2 * n_queries, pairs, nullptr, 2, out_scores, margin,      \
+                          out_loss, KIND);                                                                            \
+  }                                                                                                                   \
+  extern "C" int gqe_score_grouped##SUFFIX##_host(gqe_ctx* c, const gqe_segment* segments, int32_t n_segments,       \
+                                                  int64_t n_queries_total, const int32_t* anchors,                   \
+                                                  const int32_t* targets, int32_t targets_per_query,                 \
+                                                  float* out_scores, float margin, float* out_loss) {                \
+    if (!c) return GQE_ERR_INVALID;                                                                                   \
+    if (!segments || n_segments <= 0) return fail(c, GQE_ERR_INVALID, "no segments");                                 \
+    /* grouped anchors are always laid out with GQE_MAX_ANCHORS slots */                                              \
+    return run_fused_host(c, segments, n_segments, n_queries_total, anchors, n_queries_total * targets_per_query,     \
+                          targets, nullptr, targets_per_query, out_scores, margin, out_loss, KIND);                   \
+  }
+GQE_HOST_ENTRY_POINTS(, 0)
+GQE_HOST_ENTRY_POINTS(_nodes, 1)
+#undef GQE_HOST_ENTRY_POINTS
 
 // ---- operator-level entry points -------------------------------------------------
 static int launch_op(gqe_ctx* c, int d, const OpParams& op) {
@@ -819,6 +961,8 @@ extern "C" int gqe_encode_device(gqe_ctx* c, int32_t mode, int64_t n, const int3
   op.op = OP_ENCODE;
   op.n = n;
   op.table = c->tables[mode];
+  op.table_rows = c->table_rows[mode];
+  op.err = c->d_err;
   op.rows = rows;
   op.out = out;
   return launch_op(c, c->d, op);
@@ -985,7 +1129,7 @@ extern "C" int gqe_encode_bwd_device(gqe_ctx* c, int32_t mode, int64_t n, const 
   int rc = bwd_common(c, c->d, n, "gqe_encode_bwd_device");
   if (rc != GQE_OK || n == 0) return rc;
   if (!rows || !gout || !gtable) return fail(c, GQE_ERR_INVALID, "gqe_encode_bwd_device: null argument");
-  GQE_BWD_LAUNCH(c, launch_encode_bwd(c->d, n, c->tables[mode], rows, gout, gtable, c->stream));
+  GQE_BWD_LAUNCH(c, launch_encode_bwd(c->d, n, c->tables[mode], rows, gout, gtable, c->table_rows[mode], c->d_err, c->stream));
   return GQE_OK;
 }
 
@@ -1107,7 +1251,7 @@ extern "C" int gqe_gather_rows_device(gqe_ctx* c, int32_t mode, int64_t n, const
   if (n == 0) return GQE_OK;
   if (!rows || !out) return fail(c, GQE_ERR_INVALID, "gqe_gather_rows_device: null argument");
   GQE_CUDA(c, cudaSetDevice(c->device));
-  GQE_CUDA(c, launch_gather_rows(c->tables[mode], rows, n, c->d, out, c->stream));
+  GQE_CUDA(c, launch_gather_rows(c->tables[mode], rows, n, c->d, out, c->table_rows[mode], c->d_err, c->stream));
   c->launches += 1;
   return GQE_OK;
 }

@@ -7,8 +7,10 @@
 // the fused kernel to pay off, and latency-bound on the CUDA cores (17 us per 64x64 tile with
 // FFMA), so it runs on the warp-level tensor-core path (wmma, bf16 operands, fp32 accumulate)
 // with the same hi/lo split as the fused kernel: c = a_hi b_hi + a_lo b_hi + a_hi b_lo,
-// ~2^-17 relative.  One CTA = one 64x64 tile of one product; the whole K extent of both
-// operands is fetched in one round of loads; a launch computes up to 96 products.
+// ~2^-17 relative (NOT exact fp32).  One CTA = one 64x64 tile of one product; the whole K extent
+// of both operands is fetched in one round of loads; a launch computes up to 96 products.  A
+// three-factor run is two stream-ordered launches (the inner product first).  The results are
+// packed into the context's weight cache, so this kernel only runs when a parameter changed.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <mma.h>
@@ -46,38 +48,20 @@ __global__ void __launch_bounds__(kComposeThreads, 1) gqe_compose(const __grid_c
   const ComposeEntry& e = p.e[blockIdx.z];
   const int i0 = blockIdx.y * kComposeRows, j0 = blockIdx.x * 64;
   // Every load of an operand tile is issued before its first shared store (N float4 per thread
-  // in registers), so the CTA pays ~one memory latency per operand.  A three-factor run names
-  // the product it consumes (dep_a / dep_b): its CTAs have a LOWER blockIdx.z, were dispatched
-  // before this one and cannot be starved by it; the plain operand is fetched first, then the
-  // CTA waits until all tiles of the other one are stored.
+  // in registers), so the CTA pays ~one memory latency per operand.
   constexpr int NA = kComposeRows * D / 4 / kComposeThreads;   // float4 per thread of a (16 at d = 256)
   constexpr int N = 64 * D / 4 / kComposeThreads;              // float4 per thread of b (8 at d = 256)
-  auto wait_for = [&](int dep) {
-    if (threadIdx.x == 0) {
-      while ((int)(*reinterpret_cast<volatile unsigned int*>(p.done + dep) - p.target) < 0) __nanosleep(32);
-      __threadfence();
-    }
-    __syncthreads();
-  };
-  auto load_a = [&](float4 (&v)[NA]) {   // (__ldcg: a product of this very launch must not come from a stale L1 line)
-#pragma unroll
-    for (int u = 0; u < NA; ++u) {
-      const int idx = threadIdx.x + u * kComposeThreads;
-      v[u] = __ldcg(reinterpret_cast<const float4*>(e.a + (size_t)(i0 + idx / (D / 4)) * D) + idx % (D / 4));
-    }
-  };
-  auto load_b = [&](float4 (&v)[N]) {
-#pragma unroll
-    for (int u = 0; u < N; ++u) {
-      const int idx = threadIdx.x + u * kComposeThreads;
-      v[u] = __ldcg(reinterpret_cast<const float4*>(e.b + (size_t)(idx / 16) * D + j0) + idx % 16);
-    }
-  };
   float4 va[NA], vb[N];
-  if (e.dep_a < 0) load_a(va);
-  if (e.dep_b < 0) load_b(vb);
-  if (e.dep_a >= 0) { wait_for(e.dep_a); load_a(va); }
-  if (e.dep_b >= 0) { wait_for(e.dep_b); load_b(vb); }
+#pragma unroll
+  for (int u = 0; u < NA; ++u) {
+    const int idx = threadIdx.x + u * kComposeThreads;
+    va[u] = __ldcg(reinterpret_cast<const float4*>(e.a + (size_t)(i0 + idx / (D / 4)) * D) + idx % (D / 4));
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const int idx = threadIdx.x + u * kComposeThreads;
+    vb[u] = __ldcg(reinterpret_cast<const float4*>(e.b + (size_t)(idx / 16) * D + j0) + idx % 16);
+  }
 #pragma unroll
   for (int u = 0; u < NA; ++u) {
     const int idx = threadIdx.x + u * kComposeThreads;
@@ -113,10 +97,6 @@ __global__ void __launch_bounds__(kComposeThreads, 1) gqe_compose(const __grid_c
 #pragma unroll
   for (int h = 0; h < NH; ++h)
     wmma::store_matrix_sync(e.dst + (size_t)(i0 + r0 + 64 * h) * D + j0 + c0, acc[h], D, wmma::mem_row_major);
-  // publish this tile
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(p.done + blockIdx.z, 1u);
 }
 
 template <int D, int ROWS>
@@ -136,11 +116,9 @@ static cudaError_t launch_compose_t(const ComposeParams& cp, int n_entries, cuda
   return cudaGetLastError();
 }
 
-// 64-row tiles: 160 CTAs for the 10 products of the benchmark mix (one CTA per SM: a second,
-// small wave).  128-row tiles (80 CTAs, one wave) were measured 8 us SLOWER per call: the time of
-// a CTA is its load -> split -> smem -> MMA chain, which grows with the tile.
-int compose_tile_rows() { return 64; }
-
+// 64-row tiles: 160 CTAs for the 10 products of the benchmark mix.  128-row tiles (80 CTAs, one
+// wave) were measured 8 us SLOWER per call: the time of a CTA is its load -> split -> smem -> MMA
+// chain, which grows with the tile.
 cudaError_t launch_compose(int d, const ComposeParams& cp, int n_entries, cudaStream_t st) {
   if (n_entries <= 0) return cudaSuccess;
   switch (d) {

@@ -23,7 +23,8 @@ GQE_DECLARE_TC_DIM(256)
 #undef GQE_DECLARE_TC_DIM
 
 // raw row gather (gqe_rows.cu): out[i] = table[rows[i]], any d % 4 == 0
-cudaError_t launch_gather_rows(const float* table, const int32_t* rows, int64_t n, int d, float* out, cudaStream_t st);
+cudaError_t launch_gather_rows(const float* table, const int32_t* rows, int64_t n, int d, float* out, int64_t table_rows,
+                               unsigned long long* err, cudaStream_t st);
 
 // (query, target) pair scoring against stored query embeddings (gqe_pairs.cu)
 cudaError_t launch_score_pairs(int d, const PairParams& pp, int64_t n_pairs_total, cudaStream_t st);
@@ -39,11 +40,14 @@ cudaError_t launch_cosine_bwd(int d, int64_t n, const float* x, const float* y, 
                               float* gy, cudaStream_t st);
 cudaError_t launch_dot(int d, int64_t n, const float* x, const float* y, float* out, cudaStream_t st);
 cudaError_t launch_encode_bwd(int d, int64_t n, const float* table, const int32_t* rows, const float* gout, float* gtable,
-                              cudaStream_t st);
+                              int64_t table_rows, unsigned long long* err, cudaStream_t st);
 
-// fp32 products of operator matrices (gqe_compose.cu), d = 128 / 256
+// streaming kernel of the contraction-free decoders (gqe_vec.cu): TransE / DistMult chains and
+// element-wise intersections, any supported d, regular layout with T <= 2
+cudaError_t launch_fused_vec(int d, const LaunchParams& lp, cudaStream_t st);
+
+// products of operator matrices (gqe_compose.cu), d = 128 / 256
 cudaError_t launch_compose(int d, const ComposeParams& cp, int n_entries, cudaStream_t st);
-int compose_tile_rows();   // rows of a gqe_compose tile (64)
 int score_col_src_host(int n);   // tc::score_col_src (gqe_tc.cuh) for the host side
 
 inline bool tc_dim_supported(int d) { return d == 128 || d == 256; }

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) gqe_score_pairs(const __grid_constant__ P
         q = lo;
       }
       int64_t q_last = ragged ? __ldg(p.target_offsets + q + 1) : (q + 1) * p.T;  // first pair of the next query
-      const int32_t my_row = (p0 + lane < p1) ? __ldg(p.target_rows + p0 + lane) : 0;
+      const int32_t my_row = (p0 + lane < p1) ? resolve_index(sg.mode, 0, __ldg(p.target_rows + p0 + lane), p.index_kind, p.err) : 0;
       float4 qv[NV];
       float nq = 1.f;
       int64_t q_loaded = -1;

@@ -14,8 +14,24 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kRowsPerWarp = kTileRows / kWarps;  // 8
 constexpr int kPanelK = 16;
 constexpr int kRowStride = kTileRows + 4;  // 68 floats: 16B-aligned rows, 4-bank skew
-constexpr int kMaxSegs = 32;
+constexpr int kMaxSegs = 96;     // formulas per launch (the launch parameter block stays < 16 KB)
+constexpr int kMaxModes = 32;     // node types a launch can address (Bio: 5, configs[4]: 8)
 constexpr float kCosEps = 1e-8f;  // nn.CosineSimilarity default eps (model.py:68)
+
+// One node type as the kernels see it: how an index of the caller becomes a row of the mode's
+// table, and how many rows that table has.  The index arrays of a call hold either table rows
+// (index_kind == 0) or NODE IDS (index_kind == 1, the *_nodes entry points), which are mapped as
+//     row = lut ? lut[node - base] : node - base          (gqe_bind_node_maps)
+// i.e. the node_maps[mode][n] + 1 of reference netquery/bio/data_utils.py:20-21 as a dense
+// per-mode table.  Every resolved row is checked against `rows`; a miss (unknown node, row out of
+// range) is reported through LaunchParams::err and reads row 0 instead of out of bounds.
+struct ModeDev {
+  const int32_t* lut;   // DEVICE int32 [len]: table row of node (base + i), -1 = not a node of this mode
+  int64_t base;
+  int64_t len;
+  int64_t rows;         // rows of the bound table
+};
+enum { IDX_ERR_NONE = 0, IDX_ERR_UNKNOWN_NODE = 1, IDX_ERR_ROW_RANGE = 2 };
 
 // One formula's slice of a launch, fully resolved to device pointers.
 struct SegDev {
@@ -23,6 +39,8 @@ struct SegDev {
   int32_t n_anchor;
   uint32_t remote_mask;  // bit k: anchor table k lives in a PEER GPU's HBM; bit 3: the target table
   int32_t composed;      // tensor-core path: runs of linear operators were pre-multiplied (gqe_compose)
+  int8_t tgt_mode;       // index into LaunchParams::mode
+  int8_t anc_mode[GQE_MAX_ANCHORS];
   const float* tgt_table;
   const float* anc_table[GQE_MAX_ANCHORS];
   const float* rel[GQE_MAX_RELS];  // relation parameters in application order
@@ -62,6 +80,11 @@ struct LaunchParams {
   // diagnostics (gqe_debug_set_phase_log): kPhaseSlots (tag << 56 | clock64) stamps per tile
   unsigned long long* phase_log;
   int64_t phase_cap;  // tiles the log has room for
+  // index resolution (see ModeDev)
+  int32_t index_kind;           // 0: the index arrays hold table rows, 1: node ids
+  unsigned long long* err;      // DEVICE [2]: (kind << 32 | mode, offending value) of the first bad index
+  unsigned long long* err_host; // mapped pinned copy written by the last CTA of a *_host call, or null
+  ModeDev mode[kMaxModes];
 };
 constexpr int kPhaseSlots = 32;
 
@@ -73,6 +96,8 @@ struct OpParams {
   int32_t mutate;   // TransE path score: write the translated embeds1 back
   int64_t n;
   const float* table;
+  int64_t table_rows;        // OP_ENCODE: rows of `table` (bounds check)
+  unsigned long long* err;   // see LaunchParams::err
   const int32_t* rows;
   const float* rel[GQE_MAX_RELS];
   const float* pre;
@@ -87,6 +112,7 @@ struct OpParams {
 constexpr int kTcTileRows = 128;
 struct PackEntry {
   const float* src;
+  uint8_t* dst;        // packed image of this entry (a slot of the context's weight cache)
   int32_t chain_form;  // 1: B[n][k] = M[k][n] (act.mm(M)); 0: B[n][k] = M[n][k] (M.mm(embeds))
   int32_t perm;        // 1: output columns permuted inside 16-column blocks for the fragment-layout
                        //    scoring of the accumulator (tc::score_col_src)
@@ -94,27 +120,23 @@ struct PackEntry {
 constexpr int kMaxPack = 5 * kMaxSegs;
 struct PackParams {
   PackEntry e[kMaxPack];
-  uint8_t* dst;
 };
-// gqe_compose: dst = a . b (fp32 [d,d] row-major), one product per blockIdx.z.  A product
-// whose operand is itself a product of the same launch (three-factor runs) names it in
-// dep_a / dep_b (index into e[], always a LOWER index) and waits for its tiles.
+// gqe_compose: dst = a . b ([d,d] row-major, bf16x3 products accumulated in fp32), one product
+// per blockIdx.z.
 struct ComposeEntry {
   const float* a;
   const float* b;
   float* dst;
-  int32_t dep_a, dep_b;  // -1: operand is a plain parameter matrix
 };
 constexpr int kMaxCompose = 3 * kMaxSegs;  // a structure needs at most three products
 struct ComposeParams {
   ComposeEntry e[kMaxCompose];
-  unsigned int* done;     // per-product counters of stored tiles (zeroed before the launch)
-  unsigned int target;    // tiles per product
 };
 // gqe_score_pairs: one formula segment's (query, target) pairs against stored query embeddings
 struct PairSeg {
   const float* tgt_table;
   int64_t q_begin, q_end;
+  ModeDev mode;                   // the target mode (index resolution)
 };
 struct PairParams {
   PairSeg seg[kMaxSegs];
@@ -125,7 +147,30 @@ struct PairParams {
   const int64_t* target_offsets;  // ragged layout (single segment) or null
   int64_t n_pairs;                // ragged: total pairs
   float* out_scores;
+  int32_t index_kind;
+  unsigned long long* err;
 };
+
+// ---- index resolution (device side) ----------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void report_index(unsigned long long* err, int kind, int mode, int32_t value) {
+  if (err && atomicCAS(err, 0ull, ((unsigned long long)kind << 32) | (unsigned int)mode) == 0ull)
+    err[1] = (unsigned long long)(long long)value;
+}
+// caller index (row or node id) -> checked table row of `m`
+__device__ __forceinline__ int32_t resolve_index(const ModeDev& m, int mode, int32_t v, int index_kind,
+                                                 unsigned long long* err) {
+  int64_t r = v;
+  if (index_kind) {
+    const int64_t k = (int64_t)v - m.base;
+    if (k < 0 || k >= m.len) { report_index(err, IDX_ERR_UNKNOWN_NODE, mode, v); return 0; }
+    r = m.lut ? (int64_t)__ldg(m.lut + k) : k;
+    if (r < 0) { report_index(err, IDX_ERR_UNKNOWN_NODE, mode, v); return 0; }
+  }
+  if (r < 0 || r >= m.rows) { report_index(err, IDX_ERR_ROW_RANGE, mode, v); return 0; }
+  return (int32_t)r;
+}
+#endif
 
 enum { OP_ENCODE = 0, OP_PROJECT = 1, OP_PATH_SCORE = 2, OP_INTERSECT = 3, OP_COSINE = 4, OP_MATMUL = 5 };
 

@@ -54,7 +54,8 @@ __device__ __forceinline__ float min_nan(float a, float b) { return (a < b || a 
 // A warp reads one row per instruction group, fully coalesced.
 template <int D>
 __device__ __forceinline__ void gather_normalise(float (*X)[kRowStride], const float* __restrict__ table,
-                                                 const int32_t* __restrict__ rows, int n_valid) {
+                                                 const int32_t* __restrict__ rows, int n_valid, const ModeDev& md,
+                                                 int mode, int index_kind, unsigned long long* err) {
   constexpr int TC = D / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -64,7 +65,7 @@ __device__ __forceinline__ void gather_normalise(float (*X)[kRowStride], const f
     for (int u = 0; u < 4; ++u) {
       const int r = warp * kRowsPerWarp + rr + u;
       const bool ok = r < n_valid;
-      const size_t row = ok ? (size_t)__ldg(rows + r) : 0;
+      const size_t row = ok ? (size_t)resolve_index(md, mode, __ldg(rows + r), index_kind, err) : 0;
       const float* src = table + row * D + lane;
 #pragma unroll
       for (int j = 0; j < TC; ++j) v[u][j] = ok ? __ldg(src + 32 * j) : 0.f;
@@ -244,7 +245,7 @@ __device__ __forceinline__ void chain_tile(const LaunchParams& p, const SegDev& 
   const int64_t base = pair_begin + tile_in_seg * kTileRows;
   const int n_valid = (int)min((int64_t)kTileRows, pair_end - base);
 
-  gather_normalise<D>(sm.X, s.tgt_table, p.target_rows + base, n_valid);
+  gather_normalise<D>(sm.X, s.tgt_table, p.target_rows + base, n_valid, p.mode[s.tgt_mode], s.tgt_mode, p.index_kind, p.err);
   __syncthreads();
   for (int h = 0; h < n_hops; ++h) {
     if (p.decoder == GQE_DEC_BILINEAR) tile_matmul<D, false, EPI_NONE>(sm.X, sm.P, s.rel[h]);
@@ -258,7 +259,7 @@ __device__ __forceinline__ void chain_tile(const LaunchParams& p, const SegDev& 
     if (r >= n_valid) break;
     const int64_t pair = base + r;
     const int64_t q = s.q_begin + query_of_pair(p, pair - pair_begin, s.q_end - s.q_begin);
-    const size_t arow = (size_t)__ldg(p.anchor_rows + q);
+    const size_t arow = (size_t)resolve_index(p.mode[s.anc_mode[0]], s.anc_mode[0], __ldg(p.anchor_rows + q), p.index_kind, p.err);
     const float* src = s.anc_table[0] + arow * D + lane;
     float a[TC], y[TC];
     float sa = 0.f;
@@ -313,7 +314,8 @@ __device__ __forceinline__ void inter_tile(const LaunchParams& p, const SegDev& 
   const int n_branch = s.n_anchor;
 
   for (int b = 0; b < n_branch; ++b) {
-    gather_normalise<D>(sm.X, s.anc_table[b], p.anchor_rows + (int64_t)b * p.anchor_stride + q0, n_valid);
+    gather_normalise<D>(sm.X, s.anc_table[b], p.anchor_rows + (int64_t)b * p.anchor_stride + q0, n_valid,
+                        p.mode[s.anc_mode[b]], s.anc_mode[b], p.index_kind, p.err);
     __syncthreads();
     if (structure == GQE_INTER_CHAIN3 && b == 1) {
       tile_project<D>(sm.X, sm.P, s.rel[1], p.decoder);  // reverse(r2b) first (model.py:85)
@@ -361,7 +363,7 @@ __device__ __forceinline__ void inter_tile(const LaunchParams& p, const SegDev& 
     else { t0 = q * p.T; t1 = t0 + p.T; }
     float s0 = 0.f, s1 = 0.f;
     for (int64_t t = t0; t < t1; ++t) {
-      const size_t trow = (size_t)__ldg(p.target_rows + t);
+      const size_t trow = (size_t)resolve_index(p.mode[s.tgt_mode], s.tgt_mode, __ldg(p.target_rows + t), p.index_kind, p.err);
       const float* src = s.tgt_table + trow * D + lane;
       float st = 0.f, dq = 0.f;
 #pragma unroll
@@ -452,7 +454,11 @@ __global__ void __launch_bounds__(kThreads, (D <= 128 ? 2 : 1)) gqe_op_simt(cons
   const int n_valid = (int)min((int64_t)kTileRows, p.n - c0);
   switch (p.op) {
     case OP_ENCODE:
-      gather_normalise<D>(sm.X, p.table, p.rows + c0, n_valid);
+      {
+        ModeDev md;
+        md.lut = nullptr; md.base = 0; md.len = p.table_rows; md.rows = p.table_rows;
+        gather_normalise<D>(sm.X, p.table, p.rows + c0, n_valid, md, 0, 0, p.err);
+      }
       __syncthreads();
       store_fm<D>(p.out, sm.X, p.n, c0, n_valid);
       break;

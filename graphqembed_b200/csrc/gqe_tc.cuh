@@ -320,6 +320,9 @@ struct TileRing {  // consumer side of the tile-id ring
 template <int D>
 __device__ __forceinline__ void loss_finish(const LaunchParams& p, Ctl* ctl, int wid, int lane) {
   using C = Cfg<D>;
+  // (launched programmatically dependent on the previous kernel in the stream -- with the weights
+  // cached that is the previous call's fused kernel, whose last CTA reset the words read here)
+  if (wid == 0) ptx::griddep_wait();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int t = atomicAdd(p.ticket, 1u);
@@ -341,6 +344,10 @@ __device__ __forceinline__ void loss_finish(const LaunchParams& p, Ctl* ctl, int
     if (lane == 0) {  // leave the scheduler state ready for the next launch
       *p.ticket = 0u;
       *p.tile_counter = 0u;
+      if (p.err_host) {   // *_host calls: the first bad index (if any) travels with the result
+        p.err_host[1] = __ldcg(p.err + 1);
+        p.err_host[0] = __ldcg(p.err);
+      }
     }
   }
 }
@@ -549,6 +556,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
   uint32_t gs = 0;                                 // steps issued so far (a_ready / acc_full parity)
   PendTile pend;                                   // tile whose scoring was deferred into the next tile
   pend.valid = false;
+  int32_t carry_tile = -1;                         // tile whose first-gather row of this lane is in carry_row
+  int32_t carry_row = -1;
   for (;;) {
     const int64_t tile = ring.take(ctl);
     if (tile >= p.n_tiles) break;
@@ -598,20 +607,27 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     // ~100x slower than the NVLink loads it would hide -- profiles/r01_peer_gather_micro.md)
     const bool mine = lane < RPW && my_r < n_valid;
     const uint32_t rm = s.remote_mask;
+    const int ik = p.index_kind;
+    // caller index (table row, or node id through the mode's node map) -> checked table row
+    auto tgt_row = [&](const int32_t* src) { return resolve_index(p.mode[s.tgt_mode], s.tgt_mode, __ldg(src), ik, p.err); };
+    auto anc_row = [&](int k, const int32_t* src) {
+      return resolve_index(p.mode[s.anc_mode[k]], s.anc_mode[k], __ldg(src), ik, p.err);
+    };
     int32_t gsrc0 = -1, gsrc1 = -1, gsrc2 = -1;      // gather sources: anchors 0..2 or (chains) the targets
     int32_t ssrc0 = -1, ssrc1 = -1;                  // scoring rows: the anchor (chains) or targets 0, 1
+    const bool carried = carry_tile == (int32_t)tile;         // first-gather rows resolved while the previous tile ran
     if (chain) {
       if (mine) {
-        gsrc0 = __ldg(p.target_rows + row_begin + my_r);
-        ssrc0 = __ldg(p.anchor_rows + (T == 2 ? (row_begin + my_r) >> 1 : (row_begin + my_r) / T));
+        gsrc0 = carried ? carry_row : tgt_row(p.target_rows + row_begin + my_r);
+        ssrc0 = anc_row(0, p.anchor_rows + (T == 2 ? (row_begin + my_r) >> 1 : (row_begin + my_r) / T));
       }
     } else if (mine) {
-      gsrc0 = __ldg(p.anchor_rows + row_begin + my_r);
-      gsrc1 = __ldg(p.anchor_rows + p.anchor_stride + row_begin + my_r);
-      if (n_branch > 2) gsrc2 = __ldg(p.anchor_rows + 2 * p.anchor_stride + row_begin + my_r);
+      gsrc0 = carried ? carry_row : anc_row(0, p.anchor_rows + row_begin + my_r);
+      gsrc1 = anc_row(1, p.anchor_rows + p.anchor_stride + row_begin + my_r);
+      if (n_branch > 2) gsrc2 = anc_row(2, p.anchor_rows + 2 * p.anchor_stride + row_begin + my_r);
       if (!p.q_out) {
-        ssrc0 = __ldg(p.target_rows + (row_begin + my_r) * T);
-        if (T > 1) ssrc1 = __ldg(p.target_rows + (row_begin + my_r) * T + 1);
+        ssrc0 = tgt_row(p.target_rows + (row_begin + my_r) * T);
+        if (T > 1) ssrc1 = tgt_row(p.target_rows + (row_begin + my_r) * T + 1);
       }
     }
 
@@ -624,7 +640,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 #pragma unroll
       for (int rs = 0; rs < 2; ++rs) {
         const int r = frag_row(wid, lane, rs);
-        cur.idx[rs] = r < n_valid ? __ldg(p.anchor_rows + (T == 2 ? (row_begin + r) >> 1 : (row_begin + r) / T)) : 0;
+        cur.idx[rs] = r < n_valid ? anc_row(0, p.anchor_rows + (T == 2 ? (row_begin + r) >> 1 : (row_begin + r) / T)) : 0;
       }
     }
 
@@ -660,15 +676,20 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
         const int64_t nt = ring.peek(ctl, 0);
         int32_t r2 = -1;
         const float* tab2 = nullptr;
+        bool remote2 = true;
         if (nt < p.n_tiles) {
           const SegDev& s2 = p.seg[seg_of_tile<STRUCT>(p, nt)];
           const bool chain2 = (STRUCT >= 0 ? STRUCT : s2.structure) <= GQE_CHAIN3;
           const int64_t rb2 = (chain2 ? s2.q_begin * T : s2.q_begin) + (nt - s2.tile_begin) * kRows;
           const int64_t re2 = chain2 ? s2.q_end * T : s2.q_end;
-          if (!(s2.remote_mask & (chain2 ? 8u : 1u))) {
-            tab2 = chain2 ? s2.tgt_table : s2.anc_table[0];
-            if (lane < RPW && rb2 + my_r < re2) r2 = __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r);
-          }
+          remote2 = (s2.remote_mask & (chain2 ? 8u : 1u)) != 0;
+          tab2 = chain2 ? s2.tgt_table : s2.anc_table[0];
+          const int m2 = chain2 ? s2.tgt_mode : s2.anc_mode[0];
+          // resolved here (index + node map) and carried into the next tile in a register
+          if (lane < RPW && rb2 + my_r < re2)
+            r2 = resolve_index(p.mode[m2], m2, __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r), ik, p.err);
+          carry_tile = (int32_t)nt;
+          carry_row = r2;
         }
         // the score of the previous tile, straight from its TMEM region
         if (pend.valid) {
@@ -677,7 +698,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           pend.valid = false;
           stamp(8);
         }
-        if (tab2) prefetch_rows_l2<D>(tab2, r2, lane);
+        if (tab2 && !remote2) prefetch_rows_l2<D>(tab2, r2, lane);
       }
 
       ptx::mbar_wait(bar_acc_full, gs & 1);
@@ -855,7 +876,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           }
           // more than one (pos, neg) pair per query (the eval shape): the remaining targets
           for (int t0 = 2; t0 < T; ++t0) {
-            const float4* c_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)__ldg(p.target_rows + q * T + t0) * D);
+            const float4* c_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)tgt_row(p.target_rows + q * T + t0) * D);
             float d2 = 0.f, n2 = 0.f;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
@@ -1056,7 +1077,7 @@ template <int D>
 __global__ void __launch_bounds__(256) gqe_pack(const __grid_constant__ PackParams p) {
   ptx::griddep_launch_dependents();   // the fused kernel may start its set-up and first gathers now
   const PackEntry& e = p.e[blockIdx.y];
-  uint8_t* out = p.dst + (size_t)blockIdx.y * Cfg<D>::kPackedBytes;
+  uint8_t* out = e.dst;
   const int item = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 k) of one n
   if (item >= D * D / 8) return;
   int n, kc;

@@ -23,11 +23,22 @@ class RowLookup(object):
     the reference's ``{mode: {node: position}}`` dicts, ``{mode: id_array}``
     (position i holds the node id, as stored in graph_data.pkl), or None for
     identity (node id == position, reference utils.py:18-20).
+
+    Each mode is held as a dense table ``lut[node - base] = row`` (-1: not a node
+    of the mode): an O(1) lookup on the host (``rows``) and, uploaded once per
+    device (``device_maps``), the table the CUDA kernels index themselves when
+    they are handed node ids (``gqe_bind_node_maps``).  A mode whose ids are too
+    sparse for a dense table (range > 16 x nodes + 2^20) falls back to a sorted
+    search on the host only.
     """
 
+    DENSE_SLACK = 16
+    DENSE_FLOOR = 1 << 20
+
     def __init__(self, node_maps=None):
-        self._keys = {}
-        self._vals = {}
+        self._lut = {}       # mode -> (base, int32 lut)
+        self._sorted = {}    # mode -> (keys, vals)  (sparse ids only)
+        self._device = {}    # device -> (modes, [lut tensors])
         self.identity = node_maps is None
         if node_maps is None:
             return
@@ -38,24 +49,68 @@ class RowLookup(object):
             else:
                 keys = np.asarray(m, dtype=np.int64)
                 vals = np.arange(len(keys), dtype=np.int64)
-            order = np.argsort(keys, kind="stable")
-            self._keys[mode] = keys[order]
-            self._vals[mode] = vals[order]
+            if len(keys) == 0:
+                self._lut[mode] = (0, np.full(1, -1, dtype=np.int32))
+                continue
+            lo, hi = int(keys.min()), int(keys.max())
+            if hi - lo + 1 <= self.DENSE_SLACK * len(keys) + self.DENSE_FLOOR and vals.max() + 1 < 2 ** 31:
+                lut = np.full(hi - lo + 1, -1, dtype=np.int32)
+                lut[keys - lo] = (vals + 1).astype(np.int32)
+                self._lut[mode] = (lo, lut)
+            else:
+                order = np.argsort(keys, kind="stable")
+                self._sorted[mode] = (keys[order], vals[order])
+
+    @property
+    def modes(self):
+        return list(self._lut) + list(self._sorted)
 
     def rows(self, nodes, mode):
-        """int32 table rows for ``nodes`` (any int sequence / array) of ``mode``."""
+        """int32 table rows for ``nodes`` (any int sequence / array) of ``mode``.
+        KeyError on an unknown mode or node, like the reference's dict lookups."""
         nodes = np.asarray(nodes, dtype=np.int64)
         if self.identity:
             return (nodes + 1).astype(np.int32)
-        keys = self._keys[mode]          # KeyError on an unknown mode, like the reference
+        if mode in self._lut:
+            base, lut = self._lut[mode]
+            k = nodes - base
+            inside = (k >= 0) & (k < len(lut))
+            r = lut[np.where(inside, k, 0)]
+            bad = ~inside | (r < 0)
+            if bad.any():
+                raise KeyError(int(nodes.reshape(-1)[np.flatnonzero(bad.reshape(-1))[0]]))
+            return r
+        keys, vals = self._sorted[mode]          # KeyError on an unknown mode, like the reference
         pos = np.searchsorted(keys, nodes)
         pos_c = np.minimum(pos, len(keys) - 1)
         bad = keys[pos_c] != nodes
         if bad.any():
             raise KeyError(int(nodes.reshape(-1)[np.flatnonzero(bad.reshape(-1))[0]]))
-        return (self._vals[mode][pos_c] + 1).astype(np.int32)
+        return (vals[pos_c] + 1).astype(np.int32)
 
     __call__ = rows
+
+    def device_maps(self, modes, table_rows, device):
+        """-> (lut device pointers, bases, lens, keep-alive tensors) for ``gqe_bind_node_maps``
+        in the order of ``modes``, or None when some mode has no dense table (sparse ids: the
+        host lookup is used instead).  Identity maps are affine: row = node + 1."""
+        if self.identity:
+            return [0] * len(modes), [-1] * len(modes), [int(r) for r in table_rows], []
+        if any(m not in self._lut for m in modes):
+            return None
+        import torch
+        key = (str(device), tuple(modes))
+        held = self._device.get(key)
+        if held is None:
+            held = [torch.from_numpy(self._lut[m][1]).to(device) for m in modes]
+            self._device[key] = held
+        return ([t.data_ptr() for t in held], [self._lut[m][0] for m in modes], [self._lut[m][1].size for m in modes],
+                held)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_device"] = {}     # device copies are rebuilt on demand
+        return state
 
 
 def relation_order(formula):

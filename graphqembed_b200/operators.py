@@ -1,5 +1,11 @@
 """The reference's operator surface, backed by the sm_100a CUDA library.
 
+NOTE (scope): the standalone operator calls here (``enc.forward``, ``path_dec.forward`` /
+``.project``, ``inter_dec.forward``) are INFERENCE calls: they detach their inputs and
+return tensors without ``grad_fn``.  Training goes through
+``graphqembed_b200.QueryEncoderDecoder.margin_loss``, whose differentiable chain
+(``autograd.py``) runs the same kernels with hand-written backward passes.
+
 Classes here keep the constructor signatures, method names, attribute dicts
 and ``state_dict`` key names of reference ``netquery/encoders.py`` and
 ``netquery/decoders.py`` so that they can be handed to the reference's own
@@ -79,6 +85,13 @@ class _CudaOperator(nn.Module):
 
     def _bind(self, ctx):
         raise NotImplementedError
+
+    def __getstate__(self):
+        # the native context (a ctypes handle) is per process: recreated lazily after
+        # copy.deepcopy / pickle / torch.save(module)
+        state = dict(self.__dict__)
+        state.pop("_gqe_state", None)
+        return state
 
 
 class DirectEncoder(_CudaOperator):
@@ -181,6 +194,9 @@ class _MetapathDecoder(_CudaOperator):
         """Score of a metapath between two embedding batches -> [B]."""
         ctx = self._ctx()
         ids = [self.rel_ids[r] for r in rels]          # KeyError like self.mats[i_rel]
+        _require_cuda(embeds1, "embeds1")
+        if embeds1.dim() != 2 or embeds1.size(0) != self.dim:
+            raise ValueError("expected a [%d, n] feature-major tensor, got %s" % (self.dim, tuple(embeds1.shape)))
         mutate = self.kind == "transe" and embeds1.is_contiguous() and embeds1.dtype == torch.float32
         e1 = embeds1.detach() if mutate else _fm(embeds1, self.dim)
         e2 = _fm(embeds2, self.dim)
@@ -291,6 +307,11 @@ class SimpleSetIntersection(nn.Module):
     def kind(self):
         return self.agg + "-simple"
 
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_gqe_state", None)
+        return state
+
     def forward(self, embeds1, embeds2, mode, embeds3=[]):
         d = embeds1.size(0)
         e1, e2 = _fm(embeds1, d), _fm(embeds2, d)
@@ -315,12 +336,16 @@ def cosine_similarity_dim0(x, y):
     d = x.size(0)
     x, y = _fm(x, d), _fm(y, d)
     dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
-    ctx = _lib.Context(dev)
+    ctx = _SHARED_CTX.get(dev)
+    if ctx is None:
+        ctx = _SHARED_CTX[dev] = _lib.Context(dev)     # parameter-free calls share one context per device
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     out = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
     ctx.cosine_device(d, x.size(1), x.data_ptr(), y.data_ptr(), out.data_ptr())
-    torch.cuda.current_stream(dev).synchronize()   # ctx is dropped on return
     return out
+
+
+_SHARED_CTX = {}
 
 
 # ---- factories with the reference's names (netquery/utils.py:93-150) -------------

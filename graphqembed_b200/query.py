@@ -79,28 +79,33 @@ def _cap(samples, limit, strict):
     return random.sample(list(samples), limit)
 
 
+def parse_query_graph(query_graph):
+    """The index content of one stored query graph (graph.py:40-54):
+    -> (query_type, rels, target_node, anchor_nodes).  An edge is
+    ``(node_u, (mode_u, rel, mode_v), node_v)``; nested structures hold their
+    second branch as a pair of edges."""
+    query_type, edges = query_graph[0], query_graph[1:]
+    if query_type in CHAIN_TYPES:
+        rels = tuple(edge[1] for edge in edges)
+        anchors = (edges[-1][-1],)
+    elif query_type in FLAT_INTER_TYPES:
+        rels = tuple(edge[1] for edge in edges)
+        anchors = tuple(edge[-1] for edge in edges)
+    elif query_type in NESTED_TYPES:
+        first, (second_a, second_b) = edges[0], edges[1]
+        rels = (first[1], (second_a[1], second_b[1]))
+        anchors = (first[-1], second_b[-1]) if query_type == "3-inter_chain" else (second_a[-1], second_b[-1])
+    else:
+        raise ValueError("unknown query type %r" % (query_type,))
+    return query_type, rels, edges[0][0], anchors
+
+
 class Query(object):
     """One sampled query graph with its negative samples."""
 
     def __init__(self, query_graph, neg_samples, hard_neg_samples, neg_sample_max=100, keep_graph=False):
-        query_type, edges = query_graph[0], query_graph[1:]
-        if query_type in CHAIN_TYPES:
-            rels = tuple(edge[1] for edge in edges)
-            self.anchor_nodes = (edges[-1][-1],)
-        elif query_type in FLAT_INTER_TYPES:
-            rels = tuple(edge[1] for edge in edges)
-            self.anchor_nodes = tuple(edge[-1] for edge in edges)
-        elif query_type in NESTED_TYPES:
-            first, (second_a, second_b) = edges[0], edges[1]
-            rels = (first[1], (second_a[1], second_b[1]))
-            if query_type == "3-inter_chain":
-                self.anchor_nodes = (first[-1], second_b[-1])
-            else:
-                self.anchor_nodes = (second_a[-1], second_b[-1])
-        else:
-            raise ValueError("unknown query type %r" % (query_type,))
+        query_type, rels, self.target_node, self.anchor_nodes = parse_query_graph(query_graph)
         self.formula = Formula(query_type, rels)
-        self.target_node = edges[0][0]
         self.query_graph = query_graph if keep_graph else None
         self.neg_samples = _cap(neg_samples, neg_sample_max, strict=True)
         self.hard_neg_samples = _cap(hard_neg_samples, neg_sample_max, strict=False)
@@ -135,8 +140,12 @@ class QueryBatch(object):
 
     def __init__(self, formula, anchors, targets, offsets=None):
         self.formula = formula
-        self.anchors = np.ascontiguousarray(anchors, dtype=np.int64)
-        self.targets = np.ascontiguousarray(targets, dtype=np.int64).reshape(-1)
+        # node ids are kept as given when they already are int32 (the flat QueryStore's native
+        # type and what the node-id entry points of the C ABI take), else widened to int64
+        keep32 = getattr(anchors, "dtype", None) == np.int32 and getattr(targets, "dtype", None) == np.int32
+        dt = np.int32 if keep32 else np.int64
+        self.anchors = np.ascontiguousarray(anchors, dtype=dt)
+        self.targets = np.ascontiguousarray(targets, dtype=dt).reshape(-1)
         self.offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
         if self.anchors.ndim != 2 or self.anchors.shape[0] != len(formula.anchor_modes):
             raise ValueError("anchors must be [n_anchors, n_queries]")
@@ -146,6 +155,22 @@ class QueryBatch(object):
                 raise ValueError("regular layout needs len(targets) to be a multiple of n_queries")
         elif self.offsets.shape != (nq + 1,) or (nq + 1 and (self.offsets[0] != 0 or self.offsets[-1] != self.targets.size)):
             raise ValueError("offsets must be [n_queries+1], start at 0 and end at len(targets)")
+
+    def int32_ids(self):
+        """(anchors int32 [A,Q], targets int32 [P]) -- the form the node-id entry points of the C
+        ABI take -- or None when an id does not fit 32 bits.  Cached."""
+        ids = self.__dict__.get("_ids32")
+        if ids is None and self.anchors.dtype == np.int32:
+            ids = self.__dict__["_ids32"] = (self.anchors, self.targets)
+        if ids is None:
+            lim = 2 ** 31
+            ok = True
+            for arr in (self.anchors, self.targets):
+                if arr.size and (arr.min() < -lim or arr.max() >= lim):
+                    ok = False
+            ids = (self.anchors.astype(np.int32), self.targets.astype(np.int32)) if ok else False
+            self.__dict__["_ids32"] = ids
+        return ids or None
 
     @property
     def n_queries(self):

@@ -26,6 +26,7 @@ from . import _lib
 from .lowering import lower_formula
 from .operators import DirectEncoder, SetIntersection, SimpleSetIntersection, _MetapathDecoder, _require_cuda
 from .query import QUERY_TYPES, QueryBatch
+from .store import StoreSlice
 
 
 class QueryEncoderDecoder(nn.Module):
@@ -53,35 +54,77 @@ class QueryEncoderDecoder(nn.Module):
         # tensor-core path only: pre-multiply runs of linear operators once per call
         # ("auto": when >= 1024 rows of a formula share the product; "off"; "always")
         self.compose = "auto"
+        # raise KeyError / IndexError for a bad node id inside the call, like the reference (one
+        # stream synchronisation per call); off = asynchronous, poll context().index_error()
+        self.check_indices = True
+        # negatives of StoreSlice batches: a numpy Generator (None: a process-wide default), or
+        # the reference's own global-``random`` draws when reference_negatives is set
+        self.negative_rng = None
+        self.reference_negatives = False
+        self._pinned = {}
+        self._pinned_used = []
 
     # ---- context / binding ---------------------------------------------------
     def _signature(self):
         return tuple(p.data_ptr() for p in self.parameters())
+
+    def _weight_version(self):
+        """Sum of the autograd version counters of every operator matrix / vector: changes
+        whenever one of them is modified in place (optimizer.step(), copy_, load_state_dict)."""
+        v = 0
+        for p in self.path_dec.parameters():
+            v += p._version
+        for p in self.inter_dec.parameters():
+            v += p._version
+        return v
 
     def context(self):
         p = _require_cuda(next(self.enc.parameters()), "QueryEncoderDecoder parameters")
         dev = p.device.index if p.device.index is not None else torch.cuda.current_device()
         st = self._state
         if st is None or st[1] != dev:
-            st = [_lib.Context(dev), dev, None]
+            st = [_lib.Context(dev), dev, None, None, False, None]   # ctx, device, pointers, weight version, node maps?, keep-alive
             self._state = st
+        ctx = st[0]
         sig = self._signature()
         if st[2] != sig:
-            self.enc._bind(st[0])
-            self.path_dec._bind(st[0])
+            self.enc._bind(ctx)
+            self.path_dec._bind(ctx)
             if isinstance(self.inter_dec, SetIntersection):
                 modes = self.enc.modes
                 pre = [_require_cuda(self.inter_dec.pre_mats[m], "pre matrix").data_ptr() for m in modes]
                 post = [_require_cuda(self.inter_dec.post_mats[m], "post matrix").data_ptr() for m in modes]
-                st[0].bind_intersection(_lib.INTER_ID[self.inter_dec.kind], pre, post, self.inter_dec.dim,
-                                        self.inter_dec.expand_dim)
+                ctx.bind_intersection(_lib.INTER_ID[self.inter_dec.kind], pre, post, self.inter_dec.dim,
+                                      self.inter_dec.expand_dim)
             else:
-                st[0].bind_intersection(_lib.INTER_ID[self.inter_dec.kind], None, None, self.enc.dim)
+                ctx.bind_intersection(_lib.INTER_ID[self.inter_dec.kind], None, None, self.enc.dim)
+            # the node id -> row tables of the modes, uploaded once: the kernels then take node ids
+            maps = self.enc.features.device_maps(self.enc.modes, [self.enc.table(m).size(0) for m in self.enc.modes],
+                                                 p.device)
+            st[4] = maps is not None
+            if maps is not None:
+                ctx.bind_node_maps(maps[0], maps[1], maps[2])
+                st[5] = maps[3]
             st[2] = sig
-        st[0].set_stream(torch.cuda.current_stream(dev).cuda_stream)
-        st[0].set_precision(self.precision)
-        st[0].set_compose(self.compose)
-        return st[0]
+            st[3] = None
+        # packed / pre-multiplied operator matrices are cached inside the context; an in-place
+        # update of any of them (autograd version counter) drops the cache
+        ver = self._weight_version()
+        if st[3] != ver:
+            ctx.invalidate_weights()
+            st[3] = ver
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        ctx.set_precision(self.precision)
+        ctx.set_compose(self.compose)
+        return ctx
+
+    def __getstate__(self):
+        # the native context (a ctypes handle) is per process: recreated lazily after
+        # copy.deepcopy / pickle / torch.save(model)
+        state = dict(self.__dict__)
+        state["_state"] = None
+        state["_pinned"] = {}
+        return state
 
     @property
     def device(self):
@@ -97,7 +140,8 @@ class QueryEncoderDecoder(nn.Module):
 
     # ---- index lowering --------------------------------------------------------
     def lower_batch(self, batch):
-        """QueryBatch (node ids) -> (anchor_rows [A,Q] int32, target_rows [P] int32)."""
+        """QueryBatch (node ids) -> (anchor_rows [A,Q] int32, target_rows [P] int32) on the host
+        (an O(1) table lookup per node; KeyError on an unknown node)."""
         f = batch.formula
         nq = batch.n_queries
         anchor_rows = np.empty((len(f.anchor_modes), nq), dtype=np.int32)
@@ -106,27 +150,70 @@ class QueryEncoderDecoder(nn.Module):
         target_rows = self.enc.rows(batch.targets, f.target_mode)
         return anchor_rows, target_rows
 
+    def _indices(self, batch):
+        """-> (anchors int32 [A,Q], targets int32 [P], nodes): the node ids themselves when the
+        context holds the node maps (the kernels do the lookup of bio/data_utils.py:20-21), else
+        rows lowered on the host."""
+        if self._state is not None and self._state[4]:
+            ids = batch.int32_ids()
+            if ids is not None:
+                return ids[0], ids[1], True
+        a, t = self.lower_batch(batch)
+        return a, t, False
+
     def _to_dev(self, arr):
-        return torch.from_numpy(np.ascontiguousarray(arr)).to(self.device, non_blocking=True)
+        """numpy -> device tensor through a reusable pinned staging buffer (a true async copy;
+        torch's own pageable path is a synchronous staging copy inside the driver)."""
+        arr = np.ascontiguousarray(arr)
+        n = arr.nbytes
+        if n == 0:
+            return torch.empty(arr.shape, dtype=torch.from_numpy(arr).dtype, device=self.device)
+        key = len(self._pinned_used)
+        slot = self._pinned.get(key)
+        if slot is None or slot[0].numel() < n:
+            slot = [torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory(), None]
+            self._pinned[key] = slot
+        if slot[1] is not None:
+            slot[1].synchronize()            # the previous copy out of this buffer has landed
+        host = slot[0][:n].view(torch.from_numpy(arr).dtype).view(arr.shape)
+        host.numpy()[...] = arr
+        out = host.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        slot[1] = ev
+        self._pinned_used.append(key)
+        return out
+
+    def _check_indices(self, ctx, nodes):
+        """The reference raises KeyError inside forward() for a node that is not in node_maps;
+        with the lookup on the device the kernels report it asynchronously.  ``check_indices``
+        (default on) synchronises and raises here, like the reference; turn it off to keep the
+        call asynchronous and poll ``context().index_error()`` yourself."""
+        self._pinned_used = []
+        if self.check_indices:
+            ctx.index_error()
 
     # ---- scoring -----------------------------------------------------------------
     def score_batch(self, batch):
         """Scores of a QueryBatch, in the batch's own pair order -> FloatTensor[n_pairs]."""
         ctx = self.context()
         plan = self.plan(batch.formula)
-        anchor_rows, target_rows = self.lower_batch(batch)
-        a = self._to_dev(anchor_rows)
-        t = self._to_dev(target_rows)
+        anchors, targets, nodes = self._indices(batch)
+        a = self._to_dev(anchors)
+        t = self._to_dev(targets)
         off = None if batch.offsets is None else self._to_dev(batch.offsets)
         out = torch.empty(batch.n_pairs, dtype=torch.float32, device=self.device)
         ctx.score_device(plan, batch.n_queries, a.data_ptr(), batch.n_pairs, t.data_ptr(),
-                         None if off is None else off.data_ptr(), out.data_ptr())
+                         None if off is None else off.data_ptr(), out.data_ptr(), nodes=nodes)
+        self._check_indices(ctx, nodes)
         return out
 
     def forward(self, formula, queries, source_nodes):
         """model.py:70-109.  Unknown query types return None like the reference."""
         if formula.query_type not in QUERY_TYPES:
             return None
+        if isinstance(queries, StoreSlice):      # pair i = queries[i] against source_nodes[i]
+            return self.score_batch(QueryBatch(formula, queries.anchors, np.asarray(source_nodes, dtype=np.int32)))
         batch, order = QueryBatch.from_queries(formula, queries, source_nodes)
         scores = self.score_batch(batch)
         if order is None:
@@ -145,22 +232,47 @@ class QueryEncoderDecoder(nn.Module):
             return [random.choice(self.graph.full_lists[formula.target_mode]) for _ in queries]
         return [random.choice(query.neg_samples) for query in queries]
 
+    def _full_array(self, mode):
+        g = self.graph
+        if hasattr(g, "full_array"):
+            return g.full_array(mode)
+        cache = self.__dict__.setdefault("_full_arrays", {})
+        arr = cache.get(mode)
+        if arr is None:
+            arr = cache[mode] = np.asarray(g.full_lists[mode], dtype=np.int32)
+        return arr
+
     def margin_loss(self, formula, queries, hard_negatives=False, margin=1):
         """model.py:112-127 in one launch: the query side is built once and
-        scored against the positive and the negative; hinge + mean are fused."""
-        neg_nodes = self.pick_negatives(formula, queries, hard_negatives)
+        scored against the positive and the negative; hinge + mean are fused.
+
+        ``queries``: a list of ``Query`` objects (the reference's argument), or a
+        ``StoreSlice`` of a ``QueryStore`` -- then nothing here is per-query Python: the
+        anchors / targets are array views, the negatives one vectorised draw
+        (``self.negative_rng``; ``self.reference_negatives = True`` draws with the global
+        ``random`` module in the reference's order instead)."""
+        if isinstance(queries, StoreSlice):
+            if "inter" not in formula.query_type and hard_negatives:
+                raise Exception("Hard negative examples can only be used with intersection queries")
+            full = self._full_array(formula.target_mode) if formula.query_type == "1-chain" else None
+            neg_nodes = queries.draw_negatives(hard_negatives, full, self.negative_rng, self.reference_negatives)
+            anchors, pos_nodes = queries.anchors, queries.targets
+        else:
+            neg_nodes = self.pick_negatives(formula, queries, hard_negatives)
+            n = len(queries)
+            anchors = np.empty((len(formula.anchor_modes), n), dtype=np.int64)
+            for k in range(anchors.shape[0]):
+                anchors[k] = np.fromiter((q.anchor_nodes[k] for q in queries), dtype=np.int64, count=n)
+            pos_nodes = np.fromiter((q.target_node for q in queries), dtype=np.int64, count=n)
+            neg_nodes = np.fromiter(neg_nodes, dtype=np.int64, count=n)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training: the differentiable operator chain (autograd.py); its backward runs the
-            # hand-written VJP kernels and leaves dense .grad tensors for any torch optimiser
+            # hand-written VJP kernels and leaves .grad tensors for the optimiser
             from . import autograd
-            return autograd.margin_loss(self, formula, queries, neg_nodes, margin)
-        n = len(queries)
-        anchors = np.empty((len(formula.anchor_modes), n), dtype=np.int64)
-        for k in range(anchors.shape[0]):
-            anchors[k] = np.fromiter((q.anchor_nodes[k] for q in queries), dtype=np.int64, count=n)
-        pairs = np.empty((n, 2), dtype=np.int64)
-        pairs[:, 0] = np.fromiter((q.target_node for q in queries), dtype=np.int64, count=n)
-        pairs[:, 1] = np.fromiter(neg_nodes, dtype=np.int64, count=n)
+            return autograd.margin_loss(self, formula, list(anchors), pos_nodes, neg_nodes, margin)
+        pairs = np.empty((len(pos_nodes), 2), dtype=anchors.dtype)
+        pairs[:, 0] = pos_nodes
+        pairs[:, 1] = neg_nodes
         return self.margin_loss_batch(QueryBatch(formula, anchors, pairs.reshape(-1)), margin)
 
     def margin_loss_batch(self, batch, margin=1, return_scores=False):
@@ -169,13 +281,14 @@ class QueryEncoderDecoder(nn.Module):
             raise ValueError("margin loss needs exactly (positive, negative) per query")
         ctx = self.context()
         plan = self.plan(batch.formula)
-        anchor_rows, pair_rows = self.lower_batch(batch)
-        a = self._to_dev(anchor_rows)
-        t = self._to_dev(pair_rows)
+        anchors, pairs, nodes = self._indices(batch)
+        a = self._to_dev(anchors)
+        t = self._to_dev(pairs)
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         scores = torch.empty((batch.n_queries, 2), dtype=torch.float32, device=self.device) if return_scores else None
         ctx.margin_loss_device(plan, batch.n_queries, a.data_ptr(), t.data_ptr(), margin, loss.data_ptr(),
-                               None if scores is None else scores.data_ptr())
+                               None if scores is None else scores.data_ptr(), nodes=nodes)
+        self._check_indices(ctx, nodes)
         return (loss, scores) if return_scores else loss
 
     def margin_loss_grouped(self, batches, margin=1, return_scores=False):
@@ -183,22 +296,26 @@ class QueryEncoderDecoder(nn.Module):
         ALL queries of all batches.  Each batch holds (positive, negative) pairs."""
         ctx = self.context()
         total = sum(b.n_queries for b in batches)
-        anchor_rows = np.zeros((_lib.GQE_MAX_ANCHORS, total), dtype=np.int32)
-        pair_rows = np.empty((total, 2), dtype=np.int32)
+        anchor_idx = np.zeros((_lib.GQE_MAX_ANCHORS, total), dtype=np.int32)
+        pair_idx = np.empty((total, 2), dtype=np.int32)
+        lowered = [self._indices(b) for b in batches]
+        nodes = all(x[2] for x in lowered)
         items, q0 = [], 0
-        for b in batches:
+        for b, (a, t, was_nodes) in zip(batches, lowered):
             if b.offsets is not None or b.n_pairs != 2 * b.n_queries:
                 raise ValueError("margin loss needs exactly (positive, negative) per query")
-            a, t = self.lower_batch(b)
-            anchor_rows[:a.shape[0], q0:q0 + b.n_queries] = a
-            pair_rows[q0:q0 + b.n_queries] = t.reshape(-1, 2)
+            if was_nodes and not nodes:          # mixed: fall back to host-lowered rows for all
+                a, t = self.lower_batch(b)
+            anchor_idx[:a.shape[0], q0:q0 + b.n_queries] = a
+            pair_idx[q0:q0 + b.n_queries] = t.reshape(-1, 2)
             items.append((self.plan(b.formula), q0, q0 + b.n_queries))
             q0 += b.n_queries
         segs = _lib.make_segments(items)
-        a = self._to_dev(anchor_rows)
-        t = self._to_dev(pair_rows)
+        a = self._to_dev(anchor_idx)
+        t = self._to_dev(pair_idx)
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         scores = torch.empty((total, 2), dtype=torch.float32, device=self.device) if return_scores else None
         ctx.score_grouped_device(segs, total, a.data_ptr(), t.data_ptr(), 2,
-                                 None if scores is None else scores.data_ptr(), margin, loss.data_ptr())
+                                 None if scores is None else scores.data_ptr(), margin, loss.data_ptr(), nodes=nodes)
+        self._check_indices(ctx, nodes)
         return (loss, scores) if return_scores else loss

@@ -24,6 +24,9 @@ WORKLOADS = {
     # BASELINE.json configs[3] -- the largest single-GPU configuration: the bench default
     "bio-mix-d256-b65536": ("Bio KG full mix (1/2/3-chain + 2/3-inter + 3-inter_chain), d=256, batch=65536", 256,
                             65536, STRUCTURES[:6], "bilinear", "mean"),
+    # configs[2] with the element-wise-min aggregator the north star names (utils.py:144-145)
+    "bio-inter-d128-b8192-min": ("Bio KG 2-inter + 3-inter DeepSets intersection (agg = min), d=128, batch=8192", 128,
+                                 8192, ("2-inter", "3-inter"), "bilinear", "min"),
     # BASELINE.json configs[0] (the reference's own CPU-runnable case)
     "bio-edge-d128-b512": ("Bio KG 1-chain (edge) queries, Bilinear decoder, d=128, batch=512", 128, 512,
                            ("1-chain",), "bilinear", "mean"),
@@ -31,6 +34,17 @@ WORKLOADS = {
     # is sharded by node type over the GPUs of one box (1.28 GB per GPU at 8 GPUs)
     "synth-10m-d256-b65536": ("Synthetic KG 10M nodes / 100 relations, full query mix, d=256, batch=65536 per GPU",
                               256, 65536, STRUCTURES[:6], "bilinear", "mean"),
+    # the contraction-free operators (TransE / DistMult decoder, SimpleSetIntersection): pure HBM gather.
+    # On the 10 M-node KG the table (10.24 GB) is far beyond L2, so every row comes from DRAM.
+    "synth-10m-transe-minsimple-d256-b65536": ("Synthetic KG 10M nodes, full query mix, TransE decoder + "
+                                               "SimpleSetIntersection(min), d=256, batch=65536", 256, 65536,
+                                               STRUCTURES[:6], "transe", "min-simple"),
+    "synth-10m-distmult-meansimple-d256-b65536": ("Synthetic KG 10M nodes, full query mix, DistMult decoder + "
+                                                  "SimpleSetIntersection(mean), d=256, batch=65536", 256, 65536,
+                                                  STRUCTURES[:6], "bilinear-diag", "mean-simple"),
+    "bio-transe-minsimple-d256-b65536": ("Bio KG full query mix, TransE decoder + SimpleSetIntersection(min), d=256, "
+                                         "batch=65536 (tables L2-resident)", 256, 65536, STRUCTURES[:6], "transe",
+                                         "min-simple"),
 }
 DEFAULT_WORKLOAD = "bio-mix-d256-b65536"
 LARGE_WORKLOAD = "synth-10m-d256-b65536"
@@ -56,6 +70,20 @@ class Workload(object):
             items.append((lower_formula(f, mode_ids, rel_ids), q0, q0 + b.n_queries))
             q0 += b.n_queries
         return _lib.make_segments(items), anchor_rows, pair_rows
+
+    def node_arrays(self, mode_ids, rel_ids):
+        """-> (segments, anchor_nodes int32 [3, Q], pair_nodes int32 [Q, 2]): the reference's NODE IDS
+        in the layout of the grouped *_nodes entry points (no lookup done here)."""
+        total = self.n_queries
+        anchor_nodes = np.zeros((_lib.GQE_MAX_ANCHORS, total), dtype=np.int32)
+        pair_nodes = np.empty((total, 2), dtype=np.int32)
+        items, q0 = [], 0
+        for b in self.batches:
+            anchor_nodes[:b.anchors.shape[0], q0:q0 + b.n_queries] = b.anchors
+            pair_nodes[q0:q0 + b.n_queries] = b.targets.reshape(-1, 2)
+            items.append((lower_formula(b.formula, mode_ids, rel_ids), q0, q0 + b.n_queries))
+            q0 += b.n_queries
+        return _lib.make_segments(items), anchor_nodes, pair_nodes
 
     # SURVEY.md section 8d, per query, fp32 rows + int32 indices + fp32 scores, T = 2
     def algorithmic_bytes(self):
@@ -104,12 +132,22 @@ class Workload(object):
         return total
 
 
+_KG_CACHE = {}
+
+
+def _kg_cached(kind):
+    kg = _KG_CACHE.get(kind)
+    if kg is None:
+        kg = _KG_CACHE[kind] = synthetic_large(seed=0) if kind == "large" else bio_shaped(seed=0)
+    return kg
+
+
 def make_workload(name=DEFAULT_WORKLOAD, seed=0, kg=None, formulas_per_structure=1, total=None):
     desc, d, n_total, structures, decoder, inter = WORKLOADS[name]
     if total is not None:
         n_total = int(total)
     if kg is None:
-        kg = synthetic_large(seed=0) if name.startswith("synth-10m") else bio_shaped(seed=0)
+        kg = _kg_cached("large" if name.startswith("synth-10m") else "bio")
     rng = np.random.RandomState(1000 + seed)
     n_slices = len(structures) * formulas_per_structure
     sizes = [n_total // n_slices + (1 if i < n_total % n_slices else 0) for i in range(n_slices)]

@@ -23,6 +23,14 @@
  *     reference netquery/decoders.py:135-137.
  *   - embeddings exchanged by the operator-level calls are FEATURE-MAJOR
  *     [d, n] fp32 (reference layout: encoders.py:41, decoders.py:150).
+ *   - index arrays hold table ROWS (the entry points without "_nodes") or NODE IDS (the
+ *     "_nodes" twins, mapped to rows on the device through gqe_bind_node_maps).  Every index is
+ *     bounds-checked inside the kernels: a bad one reads row 0 and is reported -- the *_host
+ *     calls return GQE_ERR_INDEX, the asynchronous *_device calls leave it for gqe_index_error.
+ *   - packed / pre-multiplied images of the relation and DeepSets matrices are CACHED across
+ *     calls on the tensor-core path: after changing a bound matrix in place (an optimiser
+ *     step) call gqe_invalidate_weights, or turn the cache off with gqe_set_weight_cache.
+ *     Embedding tables are always read in place.
  *   - there is no CPU fallback anywhere behind this header.
  */
 #ifndef GQE_H_
@@ -34,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GQE_ABI_VERSION 3
+#define GQE_ABI_VERSION 4
 #define GQE_MAX_ANCHORS 3
 #define GQE_MAX_RELS 3
 
@@ -44,7 +52,10 @@ typedef enum gqe_status {
   GQE_ERR_UNBOUND = -2,      /* tables / relations / intersection not bound yet */
   GQE_ERR_UNSUPPORTED = -3,  /* dimension or combination this build has no kernel for */
   GQE_ERR_CUDA = -4,         /* a CUDA runtime call failed; see gqe_last_error */
-  GQE_ERR_NOMEM = -5
+  GQE_ERR_NOMEM = -5,
+  GQE_ERR_INDEX = -6         /* a node id is not in the bound node map (the reference's KeyError,
+                                bio/data_utils.py:21) or a row index is outside its table (nn.Embedding's
+                                IndexError); the offending value is in gqe_last_error */
 } gqe_status;
 
 /* Query structures of reference netquery/model.py:70-109. */
@@ -129,12 +140,26 @@ int gqe_set_precision(gqe_ctx* ctx, int32_t precision);
 int gqe_get_precision(const gqe_ctx* ctx);
 /* Operator pre-composition on the tensor-core path.  Runs of consecutive linear operators of
  * a formula (chained relation matrices; DeepSets pre x relation; relation x post) are
- * multiplied together in fp32 once per call, so the fused kernel runs one contraction per run:
- * a 3-chain costs one contraction per (query, target) pair instead of three.  Same algebra
- * as reference netquery/decoders.py:143-150,289-299, different fp32 rounding (~1e-7 relative).
- * AUTO (default) composes when at least 8 tiles (1024 rows) of a formula share the product. */
+ * multiplied together once (split-bf16 products accumulated in fp32, ~2^-17 relative -- the
+ * same arithmetic as the contractions themselves, NOT exact fp32) and cached, so the fused
+ * kernel runs one contraction per run: a 3-chain costs one contraction per (query, target) pair
+ * instead of three.  Same algebra as reference netquery/decoders.py:143-150,289-299, different
+ * rounding: scores stay within ~4e-6 of the exact-fp32 kernels (tests/test_gpu_parity.py).
+ * AUTO (default) composes whenever the weight cache is on, else when at least 8 tiles
+ * (1024 rows) of a formula share the product. */
 typedef enum gqe_compose_mode { GQE_COMPOSE_OFF = 0, GQE_COMPOSE_AUTO = 1, GQE_COMPOSE_ALWAYS = 2 } gqe_compose_mode;
 int gqe_set_compose(gqe_ctx* ctx, int32_t mode);
+/* Weight cache of the tensor-core path.  The d x d operator matrices a formula uses are split
+ * into bf16 planes, swizzled and (with pre-composition) multiplied together before the fused
+ * kernel can stream them; the context keeps those images keyed by the source pointers, so only
+ * the first call that needs a matrix pays for it (two small kernels) and every later call is the
+ * fused kernel alone.  The cache cannot see in-place updates of the parameters:
+ *   gqe_invalidate_weights  drop every image (call after optimizer.step(); re-binding does it too)
+ *   gqe_set_weight_cache    on (default) / off = re-prepare on every call, parameters fully live
+ *   gqe_weight_prep_count   matrices packed so far on this context (bookkeeping) */
+int gqe_set_weight_cache(gqe_ctx* ctx, int32_t on);
+int gqe_invalidate_weights(gqe_ctx* ctx);
+int64_t gqe_weight_prep_count(const gqe_ctx* ctx);
 /* Message of the last failure on ctx (ctx == NULL: last gqe_create failure). */
 const char* gqe_last_error(const gqe_ctx* ctx);
 /* Diagnostics: while `log` (DEVICE uint64 [n_records][32], zeroed by the caller) is set, thread 0
@@ -160,6 +185,22 @@ int64_t gqe_launch_count(const gqe_ctx* ctx);
  * netquery/bio/data_utils.py:16-21 (one [rows, d] fp32 table per mode). */
 int gqe_bind_tables(gqe_ctx* ctx, int32_t n_modes, const float* const* tables /*HOST array of DEVICE ptrs*/,
                     const int64_t* rows /*HOST [n_modes]*/, int32_t d);
+/* rows[m] is also the bound every row index of mode m is checked against inside the kernels. */
+/* Node id -> table row maps, one per mode, in the order of gqe_bind_tables.  Replaces the
+ * node_maps dict lookup of the `features` closure (reference netquery/bio/data_utils.py:20-21,
+ * CUDA variant utils.py:17-24): the "_nodes" entry points take the reference's node ids and
+ * every kernel computes
+ *     row = lut[m] ? lut[m][node - base[m]] : node - base[m]
+ * in its index prologue.  lut[m]: DEVICE int32 [len[m]], entry = node_maps[mode][node] + 1, or -1
+ * for an id that is not a node of the mode (reported as GQE_ERR_INDEX: the reference's KeyError).
+ * lut == NULL (or lut[m] == NULL) selects the affine form; identity ids (utils.py:18-20:
+ * row = node + 1) are base = -1.  n_modes == 0 unbinds.  The arrays are not copied. */
+int gqe_bind_node_maps(gqe_ctx* ctx, int32_t n_modes, const int32_t* const* lut /*HOST array of DEVICE ptrs*/,
+                       const int64_t* base /*HOST [n_modes]*/, const int64_t* len /*HOST [n_modes]*/);
+/* First index error a kernel of this context has seen since the last call (synchronises the
+ * stream): GQE_OK and *kind = 0 when there is none, else GQE_ERR_INDEX with *kind = 1 (unknown
+ * node) or 2 (row out of range), the mode and the offending value; the record is cleared. */
+int gqe_index_error(gqe_ctx* ctx, int32_t* kind, int32_t* mode, int64_t* value);
 /* A table pointer may be a PEER pointer obtained from gqe_ipc_open (another
  * GPU's shard of the node-type-sharded table): the fused kernels then read
  * those rows in place over NVLink.  tables[m] == NULL with rows[m] == 0 marks
@@ -219,6 +260,20 @@ int gqe_score_grouped_device(gqe_ctx* ctx, const gqe_segment* segments, int32_t 
                              const int32_t* target_rows, int32_t targets_per_query,
                              float* out_scores, float margin, float* out_loss);
 
+/* Node-id variants: identical to the three calls above except that the index arrays hold the
+ * reference's NODE IDS (int32) instead of table rows; the lookup of
+ * netquery/bio/data_utils.py:20-21 happens inside the kernel (gqe_bind_node_maps). */
+int gqe_score_nodes_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries,
+                           const int32_t* anchor_nodes, int64_t n_pairs, const int32_t* target_nodes,
+                           const int64_t* target_offsets, float* out_scores);
+int gqe_margin_loss_nodes_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries,
+                                 const int32_t* anchor_nodes, const int32_t* pair_nodes,
+                                 float margin, float* out_loss, float* out_scores);
+int gqe_score_grouped_nodes_device(gqe_ctx* ctx, const gqe_segment* segments, int32_t n_segments,
+                                   int64_t n_queries_total, const int32_t* anchor_nodes,
+                                   const int32_t* target_nodes, int32_t targets_per_query,
+                                   float* out_scores, float margin, float* out_loss);
+
 /* Host-buffer variants: same semantics, HOST index arrays in, HOST results
  * out; the H2D / D2H copies and a stream synchronise happen inside the call.
  * This is the call a non-torch host (the reference's own CPU pipeline) makes. */
@@ -232,6 +287,19 @@ int gqe_score_grouped_host(gqe_ctx* ctx, const gqe_segment* segments, int32_t n_
                            int64_t n_queries_total, const int32_t* anchor_rows,
                            const int32_t* target_rows, int32_t targets_per_query,
                            float* out_scores, float margin, float* out_loss);
+
+/* ... and from HOST node-id arrays: what replaces model.py:75-92 + bio/data_utils.py:20-21 +
+ * the scoring itself for a host that holds the reference's query data as flat int32 arrays. */
+int gqe_score_nodes_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries,
+                         const int32_t* anchor_nodes, int64_t n_pairs, const int32_t* target_nodes,
+                         const int64_t* target_offsets, float* out_scores);
+int gqe_margin_loss_nodes_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries,
+                               const int32_t* anchor_nodes, const int32_t* pair_nodes,
+                               float margin, float* out_loss, float* out_scores);
+int gqe_score_grouped_nodes_host(gqe_ctx* ctx, const gqe_segment* segments, int32_t n_segments,
+                                 int64_t n_queries_total, const int32_t* anchor_nodes,
+                                 const int32_t* target_nodes, int32_t targets_per_query,
+                                 float* out_scores, float margin, float* out_loss);
 
 /* ---- operator-level entry points (the un-fused reference surface) -------
  * All embeddings are DEVICE fp32 feature-major [d, n]. */
