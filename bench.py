@@ -626,30 +626,34 @@ def measure_train_step(args, tm, local_rank, batch=512, d=128, steps=30, cpu_ste
     dec = gqe.get_metapath_decoder(graph, dims, "bilinear")
     idec = gqe.get_intersection_decoder(graph, dims, "mean")
     model = gqe.QueryEncoderDecoder(graph, enc, dec, idec).to(device)
-    opt = torch.optim.Adam(model.parameters(), lr=0.01)
     f = gqe.Formula("1-chain", rels)
     qs = [gqe.Query(SynthKG.query_graph("1-chain", rels, b["target"][i], b["anchors"][:, i]), None, None)
           for i in range(batch)]
 
-    def step():
-        opt.zero_grad()
-        loss = model.margin_loss(f, qs)
-        loss.backward()
-        opt.step()
-        return loss
+    def timed(model, opt):
+        def step():
+            opt.zero_grad()
+            loss = model.margin_loss(f, qs)
+            loss.backward()
+            opt.step()
+            return loss
+        random.seed(0)
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize(device)
+        l0 = model.context().launch_count()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = step()
+        last = float(loss.item())
+        torch.cuda.synchronize(device)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        return ms, (model.context().launch_count() - l0) / steps, last
 
-    random.seed(0)
-    for _ in range(5):
-        step()
-    torch.cuda.synchronize(device)
-    l0 = model.context().launch_count()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        loss = step()
-    last = float(loss.item())
-    torch.cuda.synchronize(device)
-    gpu_ms = (time.perf_counter() - t0) * 1e3 / steps
-    launches = (model.context().launch_count() - l0) / steps
+    import copy
+    sparse_model = copy.deepcopy(model)
+    gpu_ms, launches, last = timed(model, torch.optim.Adam(model.parameters(), lr=0.01))
+    sp_ms, sp_launches, sp_last = timed(sparse_model, gqe.SparseRowAdam(sparse_model, lr=0.01))
 
     # the reference's path on the host: same shapes, dense Adam over every tensor
     cores = os.cpu_count() or 1
@@ -682,6 +686,10 @@ def measure_train_step(args, tm, local_rank, batch=512, d=128, steps=30, cpu_ste
                         "(dense table gradients)" % (d, batch),
             "gpu_ms_per_step": round(gpu_ms, 3), "gpu_queries_per_s": round(batch / gpu_ms * 1e3, 1),
             "gpu_kernels_per_step": round(launches, 1), "loss_after": last,
+            "sparse": {"what": "same step with SparseRowAdam: table gradients as (row, gradient) pairs, row-wise Adam "
+                               "with exact catch-up of the zero-gradient steps (dense-Adam trajectory)",
+                       "gpu_ms_per_step": round(sp_ms, 3), "gpu_queries_per_s": round(batch / sp_ms * 1e3, 1),
+                       "gpu_kernels_per_step": round(sp_launches, 1), "loss_after": sp_last},
             "cpu_ms_per_step": round(cpu_ms, 3), "cpu_queries_per_s": round(batch / cpu_ms * 1e3, 1), "cpu_cores": cores,
             "note": "wall clock per step incl. Python; CPU = oracle port with torch autograd + torch.optim.Adam"}
 

@@ -12,7 +12,7 @@ import sys
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_NAME = "libgqe_b200.so"
-LIB_PATH = os.path.join(_PKG, LIB_NAME)
+LIB_PATH = os.environ.get("GQE_LIB_PATH") or os.path.join(_PKG, LIB_NAME)   # (override: kernel A/B experiments)
 CSRC = os.path.join(_PKG, "csrc")
 BUILD_DIR = os.path.join(_PKG, "build")
 
@@ -120,6 +120,9 @@ _SIGNATURES = {
     "gqe_dot_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "gqe_cosine_bwd_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, C.c_int32, _P, _P]),
     "gqe_encode_bwd_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+    "gqe_encode_bwd_rows_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+    "gqe_adam_rows_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int32, C.c_float,
+                                       C.c_float, C.c_float, C.c_float]),
     "gqe_ipc_export": (C.c_int, [_P, _P, C.c_char_p, C.POINTER(C.c_int64)]),
     "gqe_ipc_open": (C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(_P)]),
     "gqe_ipc_close": (C.c_int, [_P, _P]),
@@ -372,6 +375,15 @@ class Context(object):
 
     def encode_bwd_device(self, mode, n, rows, gout, gtable):
         self._check(self._lib.gqe_encode_bwd_device(self._h, int(mode), n, rows, gout, gtable))
+
+    def encode_bwd_rows_device(self, mode, n, rows, gout, grad_rows):
+        self._check(self._lib.gqe_encode_bwd_rows_device(self._h, int(mode), n, rows, gout, grad_rows))
+
+    def adam_rows_device(self, table, exp_avg, exp_avg_sq, last_step, table_rows, d, n, rows, grad_rows, step, lr,
+                         beta1, beta2, eps):
+        self._check(self._lib.gqe_adam_rows_device(self._h, table, exp_avg, exp_avg_sq, last_step, int(table_rows), int(d),
+                                                   int(n), rows, grad_rows, int(step), float(lr), float(beta1),
+                                                   float(beta2), float(eps)))
 
     # -- node-type-sharded tables ---------------------------------------------------------
     def ipc_export(self, dev_ptr):

@@ -39,21 +39,29 @@ def _c(t):
 
 
 class _Encode(Function):
+    """DirectEncoder.forward (encoders.py:41-43).  Backward: the dense [rows, d] table gradient
+    nn.Embedding produces (``sparse`` False), or the same gradient as a sparse COO tensor of
+    (gathered row, gradient row) pairs -- no dense tensor, no atomics -- for SparseRowAdam."""
+
     @staticmethod
-    def forward(fctx, weight, ctx, mode_id, rows):
+    def forward(fctx, weight, ctx, mode_id, rows, sparse):
         d, n = weight.size(1), rows.numel()
         out = torch.empty((d, n), dtype=torch.float32, device=weight.device)
         ctx.encode_device(mode_id, n, rows.data_ptr(), out.data_ptr())
-        fctx.gqe = (ctx, mode_id, rows, tuple(weight.shape))
+        fctx.gqe = (ctx, mode_id, rows, tuple(weight.shape), sparse)
         return out
 
     @staticmethod
     def backward(fctx, g):
-        ctx, mode_id, rows, shape = fctx.gqe
+        ctx, mode_id, rows, shape, sparse = fctx.gqe
         g = _c(g)
+        if sparse:
+            vals = torch.empty((rows.numel(), shape[1]), dtype=torch.float32, device=g.device)
+            ctx.encode_bwd_rows_device(mode_id, rows.numel(), rows.data_ptr(), g.data_ptr(), vals.data_ptr())
+            return torch.sparse_coo_tensor(rows.to(torch.int64).unsqueeze(0), vals, shape), None, None, None, None
         gtable = torch.zeros(shape, dtype=torch.float32, device=g.device)
         ctx.encode_bwd_device(mode_id, rows.numel(), rows.data_ptr(), g.data_ptr(), gtable.data_ptr())
-        return gtable, None, None, None
+        return gtable, None, None, None, None
 
 
 class _Matmul(Function):
@@ -179,7 +187,10 @@ class DifferentiablePath(object):
     def encode(self, nodes, mode):
         enc = self.m.enc
         rows = torch.from_numpy(np.ascontiguousarray(enc.rows(nodes, mode))).to(self.m.device)
-        return _Encode.apply(enc.table(mode), self.ctx, enc.mode_ids[mode], rows)
+        hook = getattr(self.m, "row_hook", None)
+        if hook is not None:
+            hook(mode, rows)          # SparseRowAdam: bring these rows up to date before they are read
+        return _Encode.apply(enc.table(mode), self.ctx, enc.mode_ids[mode], rows, bool(getattr(self.m, "sparse_table_grads", False)))
 
     def project(self, embeds, rel):
         dec = self.m.path_dec

@@ -245,11 +245,13 @@ extern "C" int gqe_bind_node_maps(gqe_ctx* c, int32_t n_modes, const int32_t* co
   if (n_modes > kMaxModes) return fail(c, GQE_ERR_UNSUPPORTED, "gqe_bind_node_maps: more than %d node types", kMaxModes);
   std::vector<ModeDev> maps(n_modes);
   for (int m = 0; m < n_modes; ++m) {
-    if (len[m] < 0) return fail(c, GQE_ERR_INVALID, "gqe_bind_node_maps: mode %d has a negative length", m);
+    if (len[m] < 0 || len[m] > 0x7fffffffLL || base[m] < -0x80000000LL || base[m] > 0x7fffffffLL)
+      return fail(c, GQE_ERR_INVALID, "gqe_bind_node_maps: mode %d: node ids and map lengths must fit 32 bits", m);
     maps[m].lut = lut ? lut[m] : nullptr;   // null: affine map row = node - base (identity ids: base = -1)
-    maps[m].base = base[m];
-    maps[m].len = len[m];
+    maps[m].base = (int32_t)base[m];
+    maps[m].len = (uint32_t)len[m];
     maps[m].rows = 0;
+    maps[m].pad_ = 0;
   }
   c->node_maps.swap(maps);
   return GQE_OK;
@@ -506,8 +508,8 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
   for (size_t m = 0; m < c->tables.size(); ++m) {
     ModeDev& md = lp.mode[m];
     if (index_kind) md = c->node_maps[m];
-    else { md.lut = nullptr; md.base = 0; md.len = c->table_rows[m]; }
-    md.rows = c->table_rows[m];
+    else { md.lut = nullptr; md.base = 0; md.len = 0; }
+    md.rows = (uint32_t)std::min<int64_t>(c->table_rows[m], 0x7fffffffLL);
   }
 
   // Bilinear d x d contractions go to the tensor cores (tcgen05, bf16x3 split) unless the
@@ -1130,6 +1132,36 @@ extern "C" int gqe_encode_bwd_device(gqe_ctx* c, int32_t mode, int64_t n, const 
   if (rc != GQE_OK || n == 0) return rc;
   if (!rows || !gout || !gtable) return fail(c, GQE_ERR_INVALID, "gqe_encode_bwd_device: null argument");
   GQE_BWD_LAUNCH(c, launch_encode_bwd(c->d, n, c->tables[mode], rows, gout, gtable, c->table_rows[mode], c->d_err, c->stream));
+  return GQE_OK;
+}
+
+extern "C" int gqe_encode_bwd_rows_device(gqe_ctx* c, int32_t mode, int64_t n, const int32_t* rows, const float* gout,
+                                          float* grad_rows) {
+  if (!c) return GQE_ERR_INVALID;
+  if (c->tables.empty()) return fail(c, GQE_ERR_UNBOUND, "embedding tables are not bound");
+  if (mode < 0 || mode >= (int)c->tables.size()) return fail(c, GQE_ERR_INVALID, "mode %d out of range", mode);
+  if (!c->tables[mode]) return fail(c, GQE_ERR_UNBOUND, "mode %d has no table on this rank", mode);
+  int rc = bwd_common(c, c->d, n, "gqe_encode_bwd_rows_device");
+  if (rc != GQE_OK || n == 0) return rc;
+  if (!rows || !gout || !grad_rows) return fail(c, GQE_ERR_INVALID, "gqe_encode_bwd_rows_device: null argument");
+  GQE_BWD_LAUNCH(c, launch_encode_bwd_rows(c->d, n, c->tables[mode], rows, gout, grad_rows, c->table_rows[mode], c->d_err,
+                                           c->stream));
+  return GQE_OK;
+}
+
+extern "C" int gqe_adam_rows_device(gqe_ctx* c, float* table, float* exp_avg, float* exp_avg_sq, int32_t* last_step,
+                                    int64_t table_rows, int32_t d, int64_t n, const int64_t* rows, const float* grad_rows,
+                                    int32_t step, float lr, float beta1, float beta2, float eps) {
+  if (!c) return GQE_ERR_INVALID;
+  if (n < 0 || table_rows <= 0 || d <= 0 || step < 0) return fail(c, GQE_ERR_INVALID, "gqe_adam_rows_device: bad size");
+  if (n == 0) return GQE_OK;
+  if (!table || !exp_avg || !exp_avg_sq || !last_step) return fail(c, GQE_ERR_INVALID, "gqe_adam_rows_device: null argument");
+  if (grad_rows && !rows) return fail(c, GQE_ERR_INVALID, "gqe_adam_rows_device: gradient rows need their row indices");
+  if (grad_rows && step < 1) return fail(c, GQE_ERR_INVALID, "gqe_adam_rows_device: Adam steps are numbered from 1");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  drop_stale_error("gqe_adam_rows_device");
+  GQE_BWD_LAUNCH(c, launch_adam_rows(table, exp_avg, exp_avg_sq, last_step, table_rows, d, n, rows, grad_rows, step, lr,
+                                     beta1, beta2, eps, c->stream));
   return GQE_OK;
 }
 

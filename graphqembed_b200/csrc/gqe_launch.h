@@ -42,6 +42,13 @@ cudaError_t launch_dot(int d, int64_t n, const float* x, const float* y, float* 
 cudaError_t launch_encode_bwd(int d, int64_t n, const float* table, const int32_t* rows, const float* gout, float* gtable,
                               int64_t table_rows, unsigned long long* err, cudaStream_t st);
 
+// sparse training step (gqe_opt.cu): per-row encoder gradients and the row-wise Adam
+cudaError_t launch_encode_bwd_rows(int d, int64_t n, const float* table, const int32_t* rows, const float* gout, float* out,
+                                   int64_t table_rows, unsigned long long* err, cudaStream_t st);
+cudaError_t launch_adam_rows(float* table, float* m, float* v, int32_t* last, int64_t table_rows, int d, int64_t n,
+                             const int64_t* rows, const float* grads, int step, float lr, float beta1, float beta2,
+                             float eps, cudaStream_t st);
+
 // streaming kernel of the contraction-free decoders (gqe_vec.cu): TransE / DistMult chains and
 // element-wise intersections, any supported d, regular layout with T <= 2
 cudaError_t launch_fused_vec(int d, const LaunchParams& lp, cudaStream_t st);

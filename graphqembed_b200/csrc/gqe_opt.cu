@@ -1,0 +1,169 @@
+// gqe_opt.cu -- sparse side of the training step: row gradients of the embedding tables and a
+// row-wise Adam that reproduces DENSE torch.optim.Adam.
+//
+// The reference's step is loss.backward(); optimizer.step() with nn.Embedding tables and dense
+// Adam (netquery/bio/train.py:59-62, train_helpers.py:78-79): every step materialises an
+// [N_mode + 2, d] gradient per touched table and updates all of its rows, although a batch of 512
+// queries touches ~1500 of them.  Here
+//   * k_encode_bwd_rows emits the gradient of the DirectEncoder (encoders.py:41-43) PER GATHERED
+//     ROW -- (rows[c], g_c) pairs, no scatter, no atomics: the table gradient as a sparse tensor;
+//   * k_adam_rows applies Adam to exactly those rows, and first CATCHES UP each row with the
+//     zero-gradient steps dense Adam would have applied since the row was last touched (the
+//     moments decay, the row keeps moving): m <- b1 m, v <- b2 v,
+//     p <- p - lr/(1 - b1^t) * m / (sqrt(v)/sqrt(1 - b2^t) + eps) for every skipped step t of the
+//     table.  So the trajectory is dense Adam's, at the cost of the touched rows.  Rows that
+//     were never touched have m = v = 0 and never move: nothing to catch up.
+// A catch-up longer than kExactSteps applies the first kExactSteps steps one by one and folds
+// the rest into the moments (b1^512 ~ 4e-24: the skipped parameter movement is below fp32
+// resolution).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gqe_launch.h"
+
+namespace gqe {
+namespace {
+
+constexpr int kExactSteps = 512;
+
+__device__ __forceinline__ float osum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[c, :] = (g_c - x_hat (x_hat . g_c)) / |t|,  t = table[rows[c]], g_c = gout[:, c]   (one warp per column)
+__global__ void __launch_bounds__(256) k_encode_bwd_rows(const float* __restrict__ table, const int32_t* __restrict__ rows,
+                                                         const float* __restrict__ gout, int d, int64_t n,
+                                                         float* __restrict__ out, int64_t table_rows,
+                                                         unsigned long long* err) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp0; c < n; c += n_warps) {
+    int64_t row = (int64_t)__ldg(rows + c);
+    const bool bad = row < 0 || row >= table_rows;
+    if (bad) {
+      if (lane == 0) report_index(err, IDX_ERR_ROW_RANGE, 0, (int32_t)row);
+      row = 0;
+    }
+    const float* t = table + row * d;
+    float ss = 0.f, tg = 0.f;
+    for (int k = lane; k < d; k += 32) {
+      const float v = __ldg(t + k);
+      ss = fmaf(v, v, ss);
+      tg = fmaf(v, gout[(size_t)k * n + c], tg);
+    }
+    ss = osum(ss); tg = osum(tg);
+    const float nrm = sqrtf(ss);
+    const float inv = 1.f / nrm, proj = tg / (nrm * nrm * nrm);   // x_hat (x_hat.g) / |t| = t (t.g) / |t|^3
+    for (int k = lane; k < d; k += 32)
+      out[(size_t)c * d + k] = bad ? 0.f : gout[(size_t)k * n + c] * inv - __ldg(t + k) * proj;
+  }
+}
+
+struct AdamHyper {
+  float lr, beta1, beta2, eps;
+};
+
+// zero-gradient Adam steps (from, to] of one row (lane-strided over d)
+__device__ __forceinline__ void adam_catch_up(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int d,
+                                              int lane, int from, int to, const AdamHyper h) {
+  if (to <= from) return;
+  const int exact = min(to - from, kExactSteps);
+  for (int k = lane; k < d; k += 32) {
+    float pm = m[k], pv = v[k], pp = p[k];
+    if (pm != 0.f || pv != 0.f) {
+      double b1p = pow((double)h.beta1, (double)from), b2p = pow((double)h.beta2, (double)from);
+      for (int s = 0; s < exact; ++s) {
+        b1p *= (double)h.beta1;
+        b2p *= (double)h.beta2;
+        pm *= h.beta1;
+        pv *= h.beta2;
+        const float step = h.lr / (float)(1.0 - b1p);
+        const float denom = sqrtf(pv) / sqrtf((float)(1.0 - b2p)) + h.eps;
+        pp -= step * (pm / denom);
+      }
+      const int rest = to - from - exact;
+      if (rest > 0) {
+        pm *= powf(h.beta1, (float)rest);
+        pv *= powf(h.beta2, (float)rest);
+      }
+      m[k] = pm; v[k] = pv; p[k] = pp;
+    }
+  }
+}
+
+// grads == nullptr: catch the listed rows (or, rows == nullptr, ALL rows) up to `step`;
+//                   duplicate rows in the list are fine (one claimant per row).
+// grads != nullptr: `rows` are UNIQUE; catch each up to step - 1, then apply Adam step `step`
+//                   with its gradient row.
+__global__ void __launch_bounds__(256) k_adam_rows(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v,
+                                                   int32_t* __restrict__ last, int64_t table_rows, int d, int64_t n,
+                                                   const int64_t* __restrict__ rows, const float* __restrict__ grads,
+                                                   int step, const AdamHyper h) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < n; i += n_warps) {
+    const int64_t row = rows ? rows[i] : i;
+    if (row < 0 || row >= table_rows) continue;
+    float* p = table + row * d;
+    float* pm = m + row * d;
+    float* pv = v + row * d;
+    const int target = grads ? step - 1 : step;
+    int from = 0;
+    bool mine = false;
+    if (lane == 0) {
+      from = last[row];
+      if (from < target) mine = atomicCAS(last + row, from, target) == from;
+      else mine = grads != nullptr && from == target;
+    }
+    from = __shfl_sync(0xffffffffu, from, 0);
+    mine = __shfl_sync(0xffffffffu, mine ? 1 : 0, 0) != 0;
+    if (!mine) continue;                       // another warp of this launch owns the row
+    if (from < target && from > 0) adam_catch_up(p, pm, pv, d, lane, from, target, h);
+    if (grads) {
+      const float bc1 = (float)(1.0 - pow((double)h.beta1, (double)step));
+      const float bc2s = sqrtf((float)(1.0 - pow((double)h.beta2, (double)step)));
+      const float* g = grads + (size_t)i * d;
+      for (int k = lane; k < d; k += 32) {
+        const float gk = g[k];
+        const float mk = pm[k] + (gk - pm[k]) * (1.f - h.beta1);     // exp_avg.lerp_(grad, 1 - beta1)
+        const float vk = pv[k] * h.beta2 + (1.f - h.beta2) * gk * gk;
+        pm[k] = mk;
+        pv[k] = vk;
+        p[k] -= (h.lr / bc1) * (mk / (sqrtf(vk) / bc2s + h.eps));
+      }
+      if (lane == 0) last[row] = step;
+    }
+  }
+}
+
+int opt_grid(int64_t warps_wanted) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (warps_wanted + 7) / 8;
+  return (int)(want < (int64_t)sms * 8 ? (want > 0 ? want : 1) : (int64_t)sms * 8);
+}
+
+}  // namespace
+
+cudaError_t launch_encode_bwd_rows(int d, int64_t n, const float* table, const int32_t* rows, const float* gout, float* out,
+                                   int64_t table_rows, unsigned long long* err, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_encode_bwd_rows<<<opt_grid(n), 256, 0, st>>>(table, rows, gout, d, n, out, table_rows, err);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam_rows(float* table, float* m, float* v, int32_t* last, int64_t table_rows, int d, int64_t n,
+                             const int64_t* rows, const float* grads, int step, float lr, float beta1, float beta2,
+                             float eps, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  AdamHyper h{lr, beta1, beta2, eps};
+  k_adam_rows<<<opt_grid(n), 256, 0, st>>>(table, m, v, last, table_rows, d, n, rows, grads, step, h);
+  return cudaGetLastError();
+}
+
+}  // namespace gqe

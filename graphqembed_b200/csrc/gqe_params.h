@@ -14,8 +14,14 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kRowsPerWarp = kTileRows / kWarps;  // 8
 constexpr int kPanelK = 16;
 constexpr int kRowStride = kTileRows + 4;  // 68 floats: 16B-aligned rows, 4-bank skew
-constexpr int kMaxSegs = 96;     // formulas per launch (the launch parameter block stays < 16 KB)
-constexpr int kMaxModes = 32;     // node types a launch can address (Bio: 5, configs[4]: 8)
+#ifndef GQE_MAX_SEGS
+#define GQE_MAX_SEGS 32
+#endif
+#ifndef GQE_MAX_MODES
+#define GQE_MAX_MODES 16
+#endif
+constexpr int kMaxSegs = GQE_MAX_SEGS;     // formulas per launch
+constexpr int kMaxModes = GQE_MAX_MODES;   // node types a launch can address (Bio: 5, configs[4]: 8)
 constexpr float kCosEps = 1e-8f;  // nn.CosineSimilarity default eps (model.py:68)
 
 // One node type as the kernels see it: how an index of the caller becomes a row of the mode's
@@ -27,9 +33,10 @@ constexpr float kCosEps = 1e-8f;  // nn.CosineSimilarity default eps (model.py:6
 // range) is reported through LaunchParams::err and reads row 0 instead of out of bounds.
 struct ModeDev {
   const int32_t* lut;   // DEVICE int32 [len]: table row of node (base + i), -1 = not a node of this mode
-  int64_t base;
-  int64_t len;
-  int64_t rows;         // rows of the bound table
+  int32_t base;
+  uint32_t len;
+  uint32_t rows;        // rows of the bound table
+  uint32_t pad_;
 };
 enum { IDX_ERR_NONE = 0, IDX_ERR_UNKNOWN_NODE = 1, IDX_ERR_ROW_RANGE = 2 };
 
@@ -152,23 +159,34 @@ struct PairParams {
 };
 
 // ---- index resolution (device side) ----------------------------------------------------
+// All 32-bit: node ids, rows and map lengths are < 2^31, so "inside the map" and "inside the
+// table" are ONE unsigned compare each (a negative value wraps to >= 2^31).
 #ifdef __CUDACC__
-__device__ __forceinline__ void report_index(unsigned long long* err, int kind, int mode, int32_t value) {
+static __device__ __noinline__ void report_index(unsigned long long* err, int kind, int mode, int32_t value) {
   if (err && atomicCAS(err, 0ull, ((unsigned long long)kind << 32) | (unsigned int)mode) == 0ull)
     err[1] = (unsigned long long)(long long)value;
 }
-// caller index (row or node id) -> checked table row of `m`
+// raw index (a table row, or a node id when index_kind != 0) -> row candidate; issues the node-map
+// load and does not branch on loaded data.  -1: the id is outside the map.
+__device__ __forceinline__ int32_t index_lookup(const ModeDev& m, int32_t v, int index_kind) {
+  if (!index_kind) return v;
+  const uint32_t k = (uint32_t)v - (uint32_t)m.base;
+  const bool inside = k < m.len;
+  return inside ? (m.lut ? __ldg(m.lut + k) : (int32_t)k) : -1;
+}
+// candidate -> checked row: a miss is reported (with the caller's raw index `v`) and reads row 0
+__device__ __forceinline__ int32_t index_check(const ModeDev& m, int mode, int32_t cand, int32_t v, int index_kind,
+                                               unsigned long long* err) {
+  if ((uint32_t)cand >= m.rows) {
+    report_index(err, (index_kind && cand < 0) ? IDX_ERR_UNKNOWN_NODE : IDX_ERR_ROW_RANGE, mode, v);
+    return 0;
+  }
+  return cand;
+}
+// both halves back to back (callers that have nothing to put between the dependent loads)
 __device__ __forceinline__ int32_t resolve_index(const ModeDev& m, int mode, int32_t v, int index_kind,
                                                  unsigned long long* err) {
-  int64_t r = v;
-  if (index_kind) {
-    const int64_t k = (int64_t)v - m.base;
-    if (k < 0 || k >= m.len) { report_index(err, IDX_ERR_UNKNOWN_NODE, mode, v); return 0; }
-    r = m.lut ? (int64_t)__ldg(m.lut + k) : k;
-    if (r < 0) { report_index(err, IDX_ERR_UNKNOWN_NODE, mode, v); return 0; }
-  }
-  if (r < 0 || r >= m.rows) { report_index(err, IDX_ERR_ROW_RANGE, mode, v); return 0; }
-  return (int32_t)r;
+  return index_check(m, mode, index_lookup(m, v, index_kind), v, index_kind, err);
 }
 #endif
 

@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 128 ? 2 : 1)) gqe_op_simt(cons
     case OP_ENCODE:
       {
         ModeDev md;
-        md.lut = nullptr; md.base = 0; md.len = p.table_rows; md.rows = p.table_rows;
+        md.lut = nullptr; md.base = 0; md.len = 0; md.rows = (uint32_t)p.table_rows; md.pad_ = 0;
         gather_normalise<D>(sm.X, p.table, p.rows + c0, n_valid, md, 0, 0, p.err);
       }
       __syncthreads();

@@ -81,6 +81,7 @@ struct Ctl {
   int64_t tile_id[2];
   uint32_t tmem_base;
   int last;
+  uint8_t bad[32];          // per worker warp: bit 0 = a lane saw a bad index in this tile, bit 1 = in the carried row
 };
 static_assert(sizeof(Ctl) <= 512, "control block");
 
@@ -531,6 +532,29 @@ __device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ table
   }
 }
 
+// Cold path of the index checks.  The hot path only notes THAT a lane saw an index outside its
+// table / node map (and substitutes row 0); this re-resolves every index of the tile rows of one
+// warp, slowly, to report which one it was (LaunchParams::err).
+template <int D>
+__device__ __noinline__ void diagnose_indices(const LaunchParams& p, const SegDev& s, bool chain, int64_t row_begin,
+                                              int n_valid, int wid, int lane) {
+  constexpr int RPW = kRows / Cfg<D>::kWorkerWarps;
+  const int T = p.T, ik = p.index_kind;
+  const int r = wid * RPW + lane;
+  if (lane >= RPW || r >= n_valid) return;
+  const int64_t row = row_begin + r;
+  if (chain) {
+    resolve_index(p.mode[s.tgt_mode], s.tgt_mode, __ldg(p.target_rows + row), ik, p.err);
+    resolve_index(p.mode[s.anc_mode[0]], s.anc_mode[0], __ldg(p.anchor_rows + (T == 2 ? row >> 1 : row / T)), ik, p.err);
+  } else {
+    for (int k = 0; k < s.n_anchor; ++k)
+      resolve_index(p.mode[s.anc_mode[k]], s.anc_mode[k], __ldg(p.anchor_rows + k * p.anchor_stride + row), ik, p.err);
+    if (!p.q_out)
+      for (int t = 0; t < T; ++t)
+        resolve_index(p.mode[s.tgt_mode], s.tgt_mode, __ldg(p.target_rows + row * T + t), ik, p.err);
+  }
+}
+
 // ---- worker warps ---------------------------------------------------------------------
 template <int D, int STRUCT>
 __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
@@ -556,8 +580,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
   uint32_t gs = 0;                                 // steps issued so far (a_ready / acc_full parity)
   PendTile pend;                                   // tile whose scoring was deferred into the next tile
   pend.valid = false;
-  int32_t carry_tile = -1;                         // tile whose first-gather row of this lane is in carry_row
-  int32_t carry_row = -1;
+  int32_t carry_row = -1;                          // this lane's first-gather row of the NEXT tile, resolved one tile ahead
+  if (lane == 0) ctl->bad[wid] = 0;
   for (;;) {
     const int64_t tile = ring.take(ctl);
     if (tile >= p.n_tiles) break;
@@ -600,37 +624,51 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     };
     stamp(1 + 16 * (unsigned long long)structure);
 
-    // ---- every index this warp will need, loaded once, up front (lane i <-> tile row
-    // wid*RPW + i).  The LOCAL table rows behind them are pulled into L2 during the first
-    // contraction (below), so the DRAM latency of the later gathers and of the scoring rows
-    // is hidden.  (Peer shards are never prefetched: a bulk L2 prefetch of a PEER address is
-    // ~100x slower than the NVLink loads it would hide -- profiles/r01_peer_gather_micro.md)
+    // ---- every index this warp will need (lane i <-> tile row wid*RPW + i) in three stages kept
+    // apart by long phases, so that no dependent load is waited for:
+    //   here            the RAW index loads (caller rows or node ids), all independent;
+    //   after the first A operand is handed over: the node-map lookups (index_lookup, one load
+    //                   each, only when the caller passed node ids) ...
+    //   ... and, after the deferred score of the previous tile, the bounds checks and the L2
+    //                   prefetches of the LOCAL table rows behind them.
+    // The first gather's own rows were resolved the same way while the PREVIOUS tile ran and
+    // arrive in a register (carry_row).  (Peer shards are never prefetched: a bulk L2 prefetch of
+    // a PEER address is ~100x slower than the NVLink loads it would hide --
+    // profiles/r01_peer_gather_micro.md)
     const bool mine = lane < RPW && my_r < n_valid;
     const uint32_t rm = s.remote_mask;
     const int ik = p.index_kind;
-    // caller index (table row, or node id through the mode's node map) -> checked table row
-    auto tgt_row = [&](const int32_t* src) { return resolve_index(p.mode[s.tgt_mode], s.tgt_mode, __ldg(src), ik, p.err); };
-    auto anc_row = [&](int k, const int32_t* src) {
-      return resolve_index(p.mode[s.anc_mode[k]], s.anc_mode[k], __ldg(src), ik, p.err);
+#define m_tgt (s.tgt_mode)
+#define m_a0 (s.anc_mode[0])
+#define m_a1 (s.anc_mode[1])
+#define m_a2 (s.anc_mode[2])
+    const int32_t* const p_s0 = chain ? p.anchor_rows + (T == 2 ? (row_begin + my_r) >> 1 : (row_begin + my_r) / T)
+                                      : p.target_rows + (row_begin + my_r) * T;
+    const int32_t* const p_g1 = p.anchor_rows + p.anchor_stride + row_begin + my_r;
+    // bounds check of a row candidate of `mode` (one unsigned compare: a negative candidate wraps);
+    // a miss reads row 0 and is only NOTED here (diagnose_indices reports it after the tile).
+    // Lanes without a row keep -1.
+    auto checked = [&](bool on, int32_t cand, int mode, int bit) -> int32_t {
+      const bool ok = (uint32_t)cand < p.mode[mode].rows;
+      if (on && !ok) ctl->bad[wid] = (uint8_t)bit;      // cold
+      return on ? (ok ? cand : 0) : -1;
     };
-    int32_t gsrc0 = -1, gsrc1 = -1, gsrc2 = -1;      // gather sources: anchors 0..2 or (chains) the targets
-    int32_t ssrc0 = -1, ssrc1 = -1;                  // scoring rows: the anchor (chains) or targets 0, 1
-    const bool carried = carry_tile == (int32_t)tile;         // first-gather rows resolved while the previous tile ran
-    if (chain) {
-      if (mine) {
-        gsrc0 = carried ? carry_row : tgt_row(p.target_rows + row_begin + my_r);
-        ssrc0 = anc_row(0, p.anchor_rows + (T == 2 ? (row_begin + my_r) >> 1 : (row_begin + my_r) / T));
+    // gather sources (anchors 0..2, or the targets of a chain) and scoring rows (the anchor of a
+    // chain, or targets 0, 1): raw index -> candidate -> checked row, in place
+    int32_t gsrc0 = -1, gsrc1 = 0, gsrc2 = 0, ssrc0 = 0, ssrc1 = 0;
+    const bool has_s = chain || !p.q_out, has_g1 = !chain, has_g2 = !chain && n_branch > 2, has_s1 = !chain && !p.q_out && T > 1;
+    if (mine) {
+      if (ring.k > 1) {          // every tile but the CTA's first was announced one tile ahead
+        gsrc0 = carry_row;
+      } else {   // this CTA's first tile: the one exposed index -> node map -> row chain
+        const int m0 = chain ? m_tgt : m_a0;
+        gsrc0 = checked(true, index_lookup(p.mode[m0], __ldg((chain ? p.target_rows : p.anchor_rows) + row_begin + my_r), ik), m0, 1);
       }
-    } else if (mine) {
-      gsrc0 = carried ? carry_row : anc_row(0, p.anchor_rows + row_begin + my_r);
-      gsrc1 = anc_row(1, p.anchor_rows + p.anchor_stride + row_begin + my_r);
-      if (n_branch > 2) gsrc2 = anc_row(2, p.anchor_rows + 2 * p.anchor_stride + row_begin + my_r);
-      if (!p.q_out) {
-        ssrc0 = tgt_row(p.target_rows + (row_begin + my_r) * T);
-        if (T > 1) ssrc1 = tgt_row(p.target_rows + (row_begin + my_r) * T + 1);
-      }
+      if (has_s) ssrc0 = __ldg(p_s0);
+      if (has_s1) ssrc1 = __ldg(p_s0 + 1);
+      if (has_g1) gsrc1 = __ldg(p_g1);
+      if (has_g2) gsrc2 = __ldg(p_g1 + p.anchor_stride);
     }
-
     PendTile cur;
     cur.valid = false;
     if (frag) {
@@ -640,7 +678,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 #pragma unroll
       for (int rs = 0; rs < 2; ++rs) {
         const int r = frag_row(wid, lane, rs);
-        cur.idx[rs] = r < n_valid ? anc_row(0, p.anchor_rows + (T == 2 ? (row_begin + r) >> 1 : (row_begin + r) / T)) : 0;
+        cur.idx[rs] = r < n_valid ? __ldg(p.anchor_rows + (T == 2 ? (row_begin + r) >> 1 : (row_begin + r) / T)) : 0;
       }
     }
 
@@ -658,8 +696,52 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       ptx::mbar_arrive(bar_a_ready);
 
       if (st == 0) {
-        // while the first contraction runs: the L2 prefetches of this tile's later rows (issued
-        // only now, so that they do not queue in front of the first gather's own loads) ...
+        // while the first contraction runs: the raw first-gather index of the NEXT tile of this CTA
+        // (its id was published by the scheduler while this tile's first gather ran) ...
+        const int64_t nt = ring.peek(ctl, 0);
+        int32_t raw_n = 0, m2 = 0;
+        bool has_n = false, remote2 = true;
+        const float* tab2 = nullptr;
+
+        if (nt < p.n_tiles) {
+          const SegDev& s2 = p.seg[seg_of_tile<STRUCT>(p, nt)];
+          const bool chain2 = (STRUCT >= 0 ? STRUCT : s2.structure) <= GQE_CHAIN3;
+          const int64_t rb2 = (chain2 ? s2.q_begin * T : s2.q_begin) + (nt - s2.tile_begin) * kRows;
+          const int64_t re2 = chain2 ? s2.q_end * T : s2.q_end;
+          remote2 = (s2.remote_mask & (chain2 ? 8u : 1u)) != 0;
+          tab2 = chain2 ? s2.tgt_table : s2.anc_table[0];
+          m2 = chain2 ? s2.tgt_mode : s2.anc_mode[0];
+          has_n = lane < RPW && rb2 + my_r < re2;
+          if (has_n) raw_n = __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r);
+        }
+        // ... the node-map lookups of every later index of this tile (independent loads, nothing
+        // waits for them yet; identity when the caller passed rows) ...
+        if (ik) {
+          if (mine) {
+            if (has_s) ssrc0 = index_lookup(p.mode[chain ? m_a0 : m_tgt], ssrc0, ik);
+            if (has_s1) ssrc1 = index_lookup(p.mode[m_tgt], ssrc1, ik);
+            if (has_g1) gsrc1 = index_lookup(p.mode[m_a1], gsrc1, ik);
+            if (has_g2) gsrc2 = index_lookup(p.mode[m_a2], gsrc2, ik);
+          }
+          if (frag) {
+#pragma unroll
+            for (int rs = 0; rs < 2; ++rs)
+              if (frag_row(wid, lane, rs) < n_valid) cur.idx[rs] = index_lookup(p.mode[m_a0], cur.idx[rs], ik);
+          }
+        }
+        // ... the score of the previous tile, straight from its TMEM region ...
+        if (pend.valid) {
+          stamp(9);
+          score_frag<D>(p, ctl, scratch, tmem_base, pend, wid, lane);
+          pend.valid = false;
+          stamp(8);
+        }
+        // ... then the bounds checks and the L2 prefetches of this tile's later rows (issued only
+        // now, so that they do not queue in front of the first gather's own loads)
+        ssrc0 = checked(mine && has_s, ssrc0, chain ? m_a0 : m_tgt, 1);
+        ssrc1 = checked(mine && has_s1, ssrc1, m_tgt, 1);
+        gsrc1 = checked(mine && has_g1, gsrc1, m_a1, 1);
+        gsrc2 = checked(mine && has_g2, gsrc2, m_a2, 1);
         if (chain) {
           if (!(rm & 1u)) prefetch_rows_l2<D>(s.anc_table[0], ssrc0, lane);
         } else {
@@ -670,35 +752,19 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
             if (T > 1) prefetch_rows_l2<D>(s.tgt_table, ssrc1, lane);
           }
         }
-        // ... and the first-gather rows of the NEXT tile of this CTA, so that its only exposed
-        // gather is an L2 hit (the index load is issued before, the prefetch after the deferred
-        // score, which hides the index latency)
-        const int64_t nt = ring.peek(ctl, 0);
-        int32_t r2 = -1;
-        const float* tab2 = nullptr;
-        bool remote2 = true;
+        if (frag) {
+#pragma unroll
+          for (int rs = 0; rs < 2; ++rs) {
+            const int32_t c = cur.idx[rs];   // (the same anchor indices were checked through ssrc0 above)
+            cur.idx[rs] = (uint32_t)c < p.mode[m_a0].rows ? c : 0;
+          }
+        }
+        // ... and the first-gather rows of the NEXT tile, carried into it in a register, so that
+        // its only exposed gather is an L2 hit
         if (nt < p.n_tiles) {
-          const SegDev& s2 = p.seg[seg_of_tile<STRUCT>(p, nt)];
-          const bool chain2 = (STRUCT >= 0 ? STRUCT : s2.structure) <= GQE_CHAIN3;
-          const int64_t rb2 = (chain2 ? s2.q_begin * T : s2.q_begin) + (nt - s2.tile_begin) * kRows;
-          const int64_t re2 = chain2 ? s2.q_end * T : s2.q_end;
-          remote2 = (s2.remote_mask & (chain2 ? 8u : 1u)) != 0;
-          tab2 = chain2 ? s2.tgt_table : s2.anc_table[0];
-          const int m2 = chain2 ? s2.tgt_mode : s2.anc_mode[0];
-          // resolved here (index + node map) and carried into the next tile in a register
-          if (lane < RPW && rb2 + my_r < re2)
-            r2 = resolve_index(p.mode[m2], m2, __ldg((chain2 ? p.target_rows : p.anchor_rows) + rb2 + my_r), ik, p.err);
-          carry_tile = (int32_t)nt;
-          carry_row = r2;
+          carry_row = checked(has_n, index_lookup(p.mode[m2], raw_n, ik), m2, 2);
+          if (!remote2) prefetch_rows_l2<D>(tab2, carry_row, lane);
         }
-        // the score of the previous tile, straight from its TMEM region
-        if (pend.valid) {
-          stamp(9);
-          score_frag<D>(p, ctl, scratch, tmem_base, pend, wid, lane);
-          pend.valid = false;
-          stamp(8);
-        }
-        if (tab2 && !remote2) prefetch_rows_l2<D>(tab2, r2, lane);
       }
 
       ptx::mbar_wait(bar_acc_full, gs & 1);
@@ -768,6 +834,13 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       ptx::tmem_wait_st();
       stamp(4);
       if (kind == E_AGG && (epi & F_DEST_ACC)) { ++gs; break; }
+    }
+
+    if (const int f = ctl->bad[wid]) {   // cold: which index was it?  (bit 1 = the carried row: next tile's turn)
+      if (f & 1) diagnose_indices<D>(p, s, chain, row_begin, n_valid, wid, lane);
+      __syncwarp();
+      if (lane == 0) ctl->bad[wid] = (uint8_t)(f >> 1);
+      __syncwarp();
     }
 
     // ---- score ------------------------------------------------------------------------
@@ -876,7 +949,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           }
           // more than one (pos, neg) pair per query (the eval shape): the remaining targets
           for (int t0 = 2; t0 < T; ++t0) {
-            const float4* c_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)tgt_row(p.target_rows + q * T + t0) * D);
+            const float4* c_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)resolve_index(p.mode[m_tgt], m_tgt, __ldg(p.target_rows + q * T + t0), ik, p.err) * D);
             float d2 = 0.f, n2 = 0.f;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
@@ -903,6 +976,10 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     }
     stamp(7);
   }
+#undef m_tgt
+#undef m_a0
+#undef m_a1
+#undef m_a2
   if (pend.valid) score_frag<D>(p, ctl, scratch, tmem_base, pend, wid, lane);  // (never: a deferred tile has a successor)
   if (threadIdx.x == 0) cta_stamp(p, 3);
   loss_finish<D>(p, ctl, wid, lane);

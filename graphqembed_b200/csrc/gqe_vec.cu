@@ -75,20 +75,23 @@ __global__ void __launch_bounds__(kVecThreads, 3) gqe_fused_vec(const __grid_con
     const int structure = s.structure;
     const bool chain = structure <= GQE_CHAIN3;
     const int na = s.n_anchor;
-    // lanes 0..na-1 hold the anchor indices of a query, lanes 8..8+T-1 its target indices
-    auto fetch = [&](int64_t q) -> int32_t {
+    // lanes 0..na-1 hold the anchor indices of a query, lanes 8..8+T-1 its target indices.  Three
+    // stages, one loop iteration apart, so that no dependent load is ever waited for: the raw index
+    // of query i+2, the node-map lookup of query i+1, the bounds check + row loads of query i.
+    const bool is_anc = lane < na, is_tgt = lane >= 8 && lane < 8 + T;
+    const int my_mode = is_anc ? s.anc_mode[lane] : s.tgt_mode;
+    const ModeDev& my_md = p.mode[my_mode];
+    auto fetch_raw = [&](int64_t q) -> int32_t {
       if (q >= s.q_end) return 0;
-      if (lane < na) {
-        const int m = s.anc_mode[lane];
-        return resolve_index(p.mode[m], m, __ldg(p.anchor_rows + (int64_t)lane * p.anchor_stride + q), ik, p.err);
-      }
-      if (lane >= 8 && lane < 8 + T)
-        return resolve_index(p.mode[s.tgt_mode], s.tgt_mode, __ldg(p.target_rows + q * T + (lane - 8)), ik, p.err);
+      if (is_anc) return __ldg(p.anchor_rows + (int64_t)lane * p.anchor_stride + q);
+      if (is_tgt) return __ldg(p.target_rows + q * T + (lane - 8));
       return 0;
     };
     int64_t q = s.q_begin + warp;
-    int32_t idx = fetch(q);
+    int32_t raw_cur = fetch_raw(q), raw_nxt = fetch_raw(q + n_warps);
+    int32_t cand = (is_anc || is_tgt) ? index_lookup(my_md, raw_cur, ik) : 0;
     for (; q < s.q_end; q += n_warps) {
+      const int32_t idx = (is_anc || is_tgt) ? index_check(my_md, my_mode, cand, raw_cur, ik, p.err) : 0;
       // ---- all row loads of this query
       float4 a[GQE_MAX_ANCHORS][NV], t[2][NV];
 #pragma unroll
@@ -105,8 +108,9 @@ __global__ void __launch_bounds__(kVecThreads, 3) gqe_fused_vec(const __grid_con
 #pragma unroll
         for (int j = 0; j < NV; ++j) t[tt][j] = (act && tt < T) ? __ldg(src + lane + 32 * j) : zero4;
       }
-      // ---- the next query's indices travel while the rows do
-      const int32_t idx_next = fetch(q + n_warps);
+      // ---- the later queries' indices travel while the rows do
+      const int32_t raw_nxt2 = fetch_raw(q + 2 * n_warps);
+      const int32_t cand_nxt = ((is_anc || is_tgt) && q + n_warps < s.q_end) ? index_lookup(my_md, raw_nxt, ik) : 0;
 
       float sc[2] = {0.f, 0.f};
       if (chain) {
@@ -206,7 +210,9 @@ __global__ void __launch_bounds__(kVecThreads, 3) gqe_fused_vec(const __grid_con
           local += (double)(h < 0.f ? 0.f : h);
         }
       }
-      idx = idx_next;
+      raw_cur = raw_nxt;
+      raw_nxt = raw_nxt2;
+      cand = cand_nxt;
     }
   }
 

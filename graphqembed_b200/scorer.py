@@ -61,6 +61,10 @@ class QueryEncoderDecoder(nn.Module):
         # the reference's own global-``random`` draws when reference_negatives is set
         self.negative_rng = None
         self.reference_negatives = False
+        # training with optim.SparseRowAdam: table gradients as (row, gradient) pairs and a hook
+        # called with the rows a differentiable forward is about to gather
+        self.sparse_table_grads = False
+        self.row_hook = None
         self._pinned = {}
         self._pinned_used = []
 

@@ -351,6 +351,29 @@ int gqe_cosine_bwd_device(gqe_ctx* ctx, int32_t d, int64_t n, const float* x, co
  * [table rows, d] dense gradient of the mode's table (what nn.Embedding's backward produces). */
 int gqe_encode_bwd_device(gqe_ctx* ctx, int32_t mode, int64_t n, const int32_t* rows, const float* gout, float* gtable);
 
+/* ---- sparse training step -------------------------------------------------------
+ * The reference trains with nn.Embedding tables and dense torch.optim.Adam
+ * (netquery/bio/train.py:59-62, train_helpers.py:78-79): a dense [rows, d] gradient and a full-table
+ * update per touched mode and step.  These two calls are the sparse equivalent.
+ * gqe_encode_bwd_rows_device: VJP of gqe_encode_device PER GATHERED ROW,
+ *   grad_rows[c, :] = (g_c - x_hat (x_hat . g_c)) / |t|  for column c of gout (DEVICE [d, n]) --
+ *   with `rows` the table gradient as (index, value) pairs: no dense tensor, no atomics. */
+int gqe_encode_bwd_rows_device(gqe_ctx* ctx, int32_t mode, int64_t n, const int32_t* rows, const float* gout,
+                               float* grad_rows /*DEVICE [n, d]*/);
+/* gqe_adam_rows_device: Adam on selected rows of one table with the trajectory of DENSE Adam.
+ * exp_avg / exp_avg_sq: DEVICE [table_rows, d] moments; last_step: DEVICE int32 [table_rows], the
+ * optimiser step of the TABLE up to which each row is up to date (all zero initially).
+ *   grad_rows == NULL: catch the listed rows (rows == NULL: every row) up to `step`, i.e. apply the
+ *     zero-gradient Adam steps last_step[r]+1 .. step that dense Adam applied to them (moments
+ *     decay, the row keeps moving); duplicates in `rows` are allowed.  Call it for the rows a batch
+ *     is about to read, and for all rows before evaluating / saving the table.
+ *   grad_rows != NULL: `rows` (DEVICE int64 [n]) are UNIQUE and grad_rows (DEVICE [n, d]) their summed
+ *     gradients: each row is caught up to step - 1, then takes Adam step `step` (numbered from 1;
+ *     bias corrections 1 - beta^step as torch.optim.Adam, no weight decay, no amsgrad). */
+int gqe_adam_rows_device(gqe_ctx* ctx, float* table, float* exp_avg, float* exp_avg_sq, int32_t* last_step,
+                         int64_t table_rows, int32_t d, int64_t n, const int64_t* rows, const float* grad_rows,
+                         int32_t step, float lr, float beta1, float beta2, float eps);
+
 /* ---- node-type-sharded tables across the GPUs of one box -------------------
  * (no counterpart in the reference, which is single-process: this is the
  * multi-GPU form of the `features` lookup of netquery/bio/data_utils.py:20-21.)

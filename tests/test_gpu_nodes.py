@@ -157,7 +157,7 @@ def test_weight_cache_follows_in_place_updates(setup):
     assert fresh.margin_loss_batch(batch).item() == l2 != l1
     # raw C ABI contract: stale until invalidated; cache off = always live
     with torch.no_grad():
-        model.path_dec.mats[key].data.mul_(0.5)     # .data: no version bump -> the model cannot see it
+        model.path_dec.mats[key].data.add_(0.03)    # .data: no version bump -> the model cannot see it
     stale = model.margin_loss_batch(batch).item()
     assert stale == l2
     model.context().invalidate_weights()
@@ -165,8 +165,9 @@ def test_weight_cache_follows_in_place_updates(setup):
     assert l3 != l2
     ctx.set_weight_cache(False)
     with torch.no_grad():
-        model.path_dec.mats[key].data.mul_(2.0)
-    assert model.margin_loss_batch(batch).item() == l2
+        model.path_dec.mats[key].data.sub_(0.03)
+    # (with the cache off small batches are not pre-composed: same algebra, different rounding)
+    assert abs(model.margin_loss_batch(batch).item() - l2) < 2e-6
     ctx.set_weight_cache(True)
 
 

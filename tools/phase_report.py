@@ -24,9 +24,16 @@ tables, rels, pre, post = bench.device_parameters(wl, torch, device, seed=1234)
 lookup = gqe.RowLookup(wl.kg.node_ids)
 mode_ids = {m: i for i, m in enumerate(wl.kg.modes)}
 rel_ids = {r: i for i, r in enumerate(wl.kg.rel_keys)}
-segs, anchor_rows, pair_rows = wl.lower(lookup, mode_ids, rel_ids)
+NODES = os.environ.get("GQE_NODES", "0") == "1"      # node ids mapped inside the kernel instead of host-lowered rows
+if NODES:
+    segs, anchor_rows, pair_rows = wl.node_arrays(mode_ids, rel_ids)
+else:
+    segs, anchor_rows, pair_rows = wl.lower(lookup, mode_ids, rel_ids)
 ctx = gqe.Context(0, torch.cuda.current_stream().cuda_stream)
 ctx.bind_tables([t.data_ptr() for t in tables], [t.size(0) for t in tables], wl.d)
+if NODES:
+    _maps = lookup.device_maps(wl.kg.modes, [t.size(0) for t in tables], device)
+    ctx.bind_node_maps(_maps[0], _maps[1], _maps[2])
 ctx.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
 ctx.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
 d_anchor, d_pairs = torch.from_numpy(anchor_rows).to(device), torch.from_numpy(pair_rows).to(device)
@@ -37,7 +44,8 @@ log = torch.zeros(n_tiles * 32, dtype=torch.int64, device=device)
 
 
 def step():
-    ctx.score_grouped_device(segs, wl.n_queries, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, None, 1.0, d_loss.data_ptr())
+    ctx.score_grouped_device(segs, wl.n_queries, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, None, 1.0, d_loss.data_ptr(),
+                             nodes=NODES)
 
 
 for _ in range(3):
