@@ -65,26 +65,47 @@ class QueryEncoderDecoder(nn.Module):
         # called with the rows a differentiable forward is about to gather
         self.sparse_table_grads = False
         self.row_hook = None
-        self._pinned = {}
-        self._pinned_used = []
+        self._stage = None     # [pinned buffer, device buffer, numpy view of the pinned one, last copy's event]
+        self._cache = None     # (parameters, operator parameters, device)
+        self._knobs = None
 
     # ---- context / binding ---------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() may move or replace parameter storage: re-bind on the next call
+        out = super(QueryEncoderDecoder, self)._apply(fn, *args, **kwargs)
+        self._cache = None
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super(QueryEncoderDecoder, self).load_state_dict(*args, **kwargs)
+        self._cache = None
+        return out
+
+    def _lists(self):
+        """(all parameters, operator matrices / vectors, device) -- cached: walking the module tree costs
+        more than a small scoring call."""
+        c = self._cache
+        if c is None:
+            allp = list(self.parameters())
+            ops = list(self.path_dec.parameters()) + list(self.inter_dec.parameters())
+            p0 = _require_cuda(next(self.enc.parameters()), "QueryEncoderDecoder parameters")
+            c = self._cache = (allp, ops, p0.device)
+        return c
+
     def _signature(self):
-        return tuple(p.data_ptr() for p in self.parameters())
+        return tuple(p.data_ptr() for p in self._lists()[0])
 
     def _weight_version(self):
         """Sum of the autograd version counters of every operator matrix / vector: changes
         whenever one of them is modified in place (optimizer.step(), copy_, load_state_dict)."""
         v = 0
-        for p in self.path_dec.parameters():
-            v += p._version
-        for p in self.inter_dec.parameters():
+        for p in self._lists()[1]:
             v += p._version
         return v
 
     def context(self):
-        p = _require_cuda(next(self.enc.parameters()), "QueryEncoderDecoder parameters")
-        dev = p.device.index if p.device.index is not None else torch.cuda.current_device()
+        allp, _, device = self._lists()
+        dev = device.index if device.index is not None else torch.cuda.current_device()
         st = self._state
         if st is None or st[1] != dev:
             st = [_lib.Context(dev), dev, None, None, False, None]   # ctx, device, pointers, weight version, node maps?, keep-alive
@@ -104,7 +125,7 @@ class QueryEncoderDecoder(nn.Module):
                 ctx.bind_intersection(_lib.INTER_ID[self.inter_dec.kind], None, None, self.enc.dim)
             # the node id -> row tables of the modes, uploaded once: the kernels then take node ids
             maps = self.enc.features.device_maps(self.enc.modes, [self.enc.table(m).size(0) for m in self.enc.modes],
-                                                 p.device)
+                                                 device)
             st[4] = maps is not None
             if maps is not None:
                 ctx.bind_node_maps(maps[0], maps[1], maps[2])
@@ -117,9 +138,13 @@ class QueryEncoderDecoder(nn.Module):
         if st[3] != ver:
             ctx.invalidate_weights()
             st[3] = ver
-        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-        ctx.set_precision(self.precision)
-        ctx.set_compose(self.compose)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        knobs = (stream, self.precision, self.compose)
+        if self._knobs != knobs:
+            ctx.set_stream(stream)
+            ctx.set_precision(self.precision)
+            ctx.set_compose(self.compose)
+            self._knobs = knobs
         return ctx
 
     def __getstate__(self):
@@ -127,12 +152,14 @@ class QueryEncoderDecoder(nn.Module):
         # copy.deepcopy / pickle / torch.save(model)
         state = dict(self.__dict__)
         state["_state"] = None
-        state["_pinned"] = {}
+        state["_stage"] = None
+        state["_cache"] = None
+        state["_knobs"] = None
         return state
 
     @property
     def device(self):
-        return next(self.enc.parameters()).device
+        return self._lists()[2]
 
     def plan(self, formula):
         """Lowered formula (cached): structure id, mode ids, relation ids."""
@@ -165,35 +192,38 @@ class QueryEncoderDecoder(nn.Module):
         a, t = self.lower_batch(batch)
         return a, t, False
 
-    def _to_dev(self, arr):
-        """numpy -> device tensor through a reusable pinned staging buffer (a true async copy;
-        torch's own pageable path is a synchronous staging copy inside the driver)."""
-        arr = np.ascontiguousarray(arr)
-        n = arr.nbytes
-        if n == 0:
-            return torch.empty(arr.shape, dtype=torch.from_numpy(arr).dtype, device=self.device)
-        key = len(self._pinned_used)
-        slot = self._pinned.get(key)
-        if slot is None or slot[0].numel() < n:
-            slot = [torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory(), None]
-            self._pinned[key] = slot
-        if slot[1] is not None:
-            slot[1].synchronize()            # the previous copy out of this buffer has landed
-        host = slot[0][:n].view(torch.from_numpy(arr).dtype).view(arr.shape)
-        host.numpy()[...] = arr
-        out = host.to(self.device, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
-        slot[1] = ev
-        self._pinned_used.append(key)
-        return out
+    def _to_dev(self, *arrays):
+        """numpy arrays -> device tensors through ONE reusable pinned staging buffer and ONE
+        asynchronous H2D copy (torch's own pageable path is a synchronous staging copy per array
+        inside the driver)."""
+        arrays = [np.ascontiguousarray(a) for a in arrays]
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (a.nbytes + 255) & ~255
+        st = self._stage
+        if st is None or st[0].numel() < total or st[1].device != self.device:
+            cap = max(total + total // 2, 1 << 16)
+            pin = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            st = self._stage = [pin, torch.empty(cap, dtype=torch.uint8, device=self.device), pin.numpy(), None]
+        if st[3] is not None:
+            st[3].synchronize()              # the previous copy out of the pinned buffer has landed
+        out = []
+        for a, o in zip(arrays, offs):
+            st[2][o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+            out.append(st[1][o:o + a.nbytes].view(torch.from_numpy(a[:0]).dtype).view(a.shape))
+        if total:
+            st[1][:total].copy_(st[0][:total], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            st[3] = ev
+        return out if len(out) > 1 else out[0]
 
     def _check_indices(self, ctx, nodes):
         """The reference raises KeyError inside forward() for a node that is not in node_maps;
         with the lookup on the device the kernels report it asynchronously.  ``check_indices``
         (default on) synchronises and raises here, like the reference; turn it off to keep the
         call asynchronous and poll ``context().index_error()`` yourself."""
-        self._pinned_used = []
         if self.check_indices:
             ctx.index_error()
 
@@ -203,9 +233,10 @@ class QueryEncoderDecoder(nn.Module):
         ctx = self.context()
         plan = self.plan(batch.formula)
         anchors, targets, nodes = self._indices(batch)
-        a = self._to_dev(anchors)
-        t = self._to_dev(targets)
-        off = None if batch.offsets is None else self._to_dev(batch.offsets)
+        if batch.offsets is None:
+            (a, t), off = self._to_dev(anchors, targets), None
+        else:
+            a, t, off = self._to_dev(anchors, targets, batch.offsets)
         out = torch.empty(batch.n_pairs, dtype=torch.float32, device=self.device)
         ctx.score_device(plan, batch.n_queries, a.data_ptr(), batch.n_pairs, t.data_ptr(),
                          None if off is None else off.data_ptr(), out.data_ptr(), nodes=nodes)
@@ -269,7 +300,7 @@ class QueryEncoderDecoder(nn.Module):
                 anchors[k] = np.fromiter((q.anchor_nodes[k] for q in queries), dtype=np.int64, count=n)
             pos_nodes = np.fromiter((q.target_node for q in queries), dtype=np.int64, count=n)
             neg_nodes = np.fromiter(neg_nodes, dtype=np.int64, count=n)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._lists()[0]):
             # training: the differentiable operator chain (autograd.py); its backward runs the
             # hand-written VJP kernels and leaves .grad tensors for the optimiser
             from . import autograd
@@ -286,8 +317,7 @@ class QueryEncoderDecoder(nn.Module):
         ctx = self.context()
         plan = self.plan(batch.formula)
         anchors, pairs, nodes = self._indices(batch)
-        a = self._to_dev(anchors)
-        t = self._to_dev(pairs)
+        a, t = self._to_dev(anchors, pairs)
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         scores = torch.empty((batch.n_queries, 2), dtype=torch.float32, device=self.device) if return_scores else None
         ctx.margin_loss_device(plan, batch.n_queries, a.data_ptr(), t.data_ptr(), margin, loss.data_ptr(),
@@ -315,8 +345,7 @@ class QueryEncoderDecoder(nn.Module):
             items.append((self.plan(b.formula), q0, q0 + b.n_queries))
             q0 += b.n_queries
         segs = _lib.make_segments(items)
-        a = self._to_dev(anchor_idx)
-        t = self._to_dev(pair_idx)
+        a, t = self._to_dev(anchor_idx, pair_idx)
         loss = torch.empty((), dtype=torch.float32, device=self.device)
         scores = torch.empty((total, 2), dtype=torch.float32, device=self.device) if return_scores else None
         ctx.score_grouped_device(segs, total, a.data_ptr(), t.data_ptr(), 2,
