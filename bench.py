@@ -226,7 +226,7 @@ class Timed(object):
 
 
 def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, formulas_per_structure=1, steps=None,
-            parity_slice=0, want_live=True):
+            parity_slice=0, want_live=True, routed=False):
     """One workload on this process group.  tables_mode:
          replicated  every rank holds every table; pure data parallel, no data-path collective
          p2p         tables sharded by node type, peers mapped with CUDA IPC, the fused kernel
@@ -246,10 +246,13 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
 
     steps = steps or args.steps
     device, stream, dist = tm.device, tm.stream, tm.dist
-    wl = make_workload(name, seed=rank, formulas_per_structure=formulas_per_structure)
-    kg = wl.kg
+    from graphqembed_b200.workloads import _kg_cached
+    kg = _kg_cached("large" if name.startswith("synth-10m") else "bio")
     n_modes = len(kg.modes)
     owner = None if tables_mode == "replicated" else sharded.owner_by_node_type(n_modes, world)
+    # routed: this rank scores the formulas whose TARGET node type it owns (sharded.route_by_target_mode)
+    tmodes = [kg.modes[m] for m in sharded.modes_owned_by(owner, rank)] if (routed and owner is not None) else None
+    wl = make_workload(name, seed=rank, kg=kg, formulas_per_structure=formulas_per_structure, target_modes=tmodes)
     tables, rels, pre, post = device_parameters(wl, torch, device, seed=1234, owner=owner, rank=rank)
     lookup = gqe.RowLookup(kg.node_ids)
     mode_ids = {m: i for i, m in enumerate(kg.modes)}
@@ -309,7 +312,14 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
         def slice_scores():
             ctx.score_grouped_device(sub, nq, d_anchor.data_ptr(), d_pairs.data_ptr(), 2, d_scores.data_ptr(), 1.0, None,
                                      nodes=True)
-        h2d = int(anchor_nodes.nbytes + pair_nodes.nbytes)
+        # bytes the host entry point really copies: per anchor slot only the query range of the
+        # segments that use the slot (chains fill one of the three slots), plus the target pairs
+        h2d = int(pair_nodes.nbytes)
+        for k in range(_lib.GQE_MAX_ANCHORS):
+            used = [(int(segs[i].query_begin), int(segs[i].query_end)) for i in range(len(segs))
+                    if segs[i].plan.anchor_mode[k] >= 0]
+            if used:
+                h2d += 4 * (max(e for _, e in used) - min(b for b, _ in used))
         call = "gqe_score_grouped_nodes_host (pinned int32 NODE IDS in, fp32 loss out; lookup + scoring in one kernel)"
         launch_ctxs = (ctx,)
     else:
@@ -816,12 +826,13 @@ def run_native(args):
     # whenever the job has more than one GPU; every rank checks its scores against the unsharded tables
     sharded_res = {}
     if world > 1 and args.workload is None and not args.no_sharded:
-        for mode in ("p2p", "staged"):
+        for key, mode, routed in (("p2p", "p2p", True), ("p2p_unrouted", "p2p", False), ("staged", "staged", True)):
             r = measure(args, LARGE_WORKLOAD, mode, tm, rank, world, local_rank, None, args.sharded_formulas,
                         steps=max(10, args.steps // 2), parity_slice=4096 // (6 * args.sharded_formulas) + 1,
-                        want_live=False)
+                        want_live=False, routed=routed)
             r.pop("params")
-            sharded_res[mode] = r
+            r["routed"] = routed
+            sharded_res[key] = r
             torch.cuda.empty_cache()
 
     # every other BASELINE config + the HBM-bound operators, on one GPU
@@ -900,6 +911,11 @@ def run_native(args):
                 "ms_per_step": round(r["dev_ms"], 5), "e2e_value": round(world * r["nq"] / (r["e2e_ms"] * 1e-3), 1),
                 "gpu_launches_per_step": round(r["launches"], 2), "formulas": r["formulas"], "loss_rank0": r["loss"],
                 "parity": r["parity"],
+                "queries": ("routed: every rank scores the formulas whose target node type it owns "
+                            "(sharded.route_by_target_mode)" if r["routed"] else
+                            "unrouted: formulas with arbitrary target node types on every rank"),
+                "remote_row_fraction_rank0": round(r["remote_rows"] / float(sum(
+                    b.n_queries * (len(b.formula.anchor_modes) + 2) for b in r["wl"].batches)), 4),
                 "hbm": {"achieved_gbs": round(r["wl"].algorithmic_bytes() / sec / 1e9, 2),
                         "frac": round(r["wl"].algorithmic_bytes() / sec / 1e9 / pk["hbm_gbs"], 4)},
                 "nvlink": {"remote_rows_per_step_rank0": r["remote_rows"], "bytes_per_step_rank0": nv_bytes,

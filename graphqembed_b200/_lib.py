@@ -123,6 +123,8 @@ _SIGNATURES = {
     "gqe_encode_bwd_rows_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "gqe_adam_rows_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int32, C.c_float,
                                        C.c_float, C.c_float, C.c_float]),
+    "gqe_segment_mean_device": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
+    "gqe_linear_device": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, C.c_int32, _P]),
     "gqe_ipc_export": (C.c_int, [_P, _P, C.c_char_p, C.POINTER(C.c_int64)]),
     "gqe_ipc_open": (C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(_P)]),
     "gqe_ipc_close": (C.c_int, [_P, _P]),
@@ -384,6 +386,12 @@ class Context(object):
         self._check(self._lib.gqe_adam_rows_device(self._h, table, exp_avg, exp_avg_sq, last_step, int(table_rows), int(d),
                                                    int(n), rows, grad_rows, int(step), float(lr), float(beta1),
                                                    float(beta2), float(eps)))
+
+    def segment_mean_device(self, src, n_src, d, n, ptr, cols, out):
+        self._check(self._lib.gqe_segment_mean_device(self._h, src, int(n_src), int(d), int(n), ptr, cols, out))
+
+    def linear_device(self, w, m, k, n, x, relu, out):
+        self._check(self._lib.gqe_linear_device(self._h, w, int(m), int(k), int(n), x, int(relu), out))
 
     # -- node-type-sharded tables ---------------------------------------------------------
     def ipc_export(self, dev_ptr):

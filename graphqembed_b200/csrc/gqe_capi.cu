@@ -869,8 +869,19 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
     if (!anchor_rows || !target_rows) return fail(c, GQE_ERR_INVALID, "index arrays are null");
     // in stream order, in front of the kernels: with the packed weights cached there is nothing
     // to overlap the copies with, and a second stream would only add event traffic to the call
-    GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_ANCHOR], anchor_rows, sizeof(int32_t) * (size_t)na * nq,
-                                cudaMemcpyHostToDevice, c->stream));
+    // anchor slot k is only read for the queries of segments with more than k anchors: copy, per
+    // slot, the query range those segments span (chains use one slot of the three-slot layout)
+    for (int k = 0; k < na; ++k) {
+      int64_t lo = nq, hi = 0;
+      for (int32_t i = 0; i < n_segs; ++i)
+        if (n_anchors_of(segs[i].plan.structure) > k && segs[i].query_end > segs[i].query_begin) {
+          lo = std::min(lo, std::max<int64_t>(segs[i].query_begin, 0));
+          hi = std::max(hi, std::min<int64_t>(segs[i].query_end, nq));
+        }
+      if (hi > lo)
+        GQE_CUDA(c, cudaMemcpyAsync((int32_t*)c->stage[ST_ANCHOR] + (size_t)k * nq + lo, anchor_rows + (size_t)k * nq + lo,
+                                    sizeof(int32_t) * (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
+    }
     GQE_CUDA(c, cudaMemcpyAsync(c->stage[ST_TARGET], target_rows, sizeof(int32_t) * (size_t)n_pairs,
                                 cudaMemcpyHostToDevice, c->stream));
     if (target_offsets)
@@ -1162,6 +1173,31 @@ extern "C" int gqe_adam_rows_device(gqe_ctx* c, float* table, float* exp_avg, fl
   drop_stale_error("gqe_adam_rows_device");
   GQE_BWD_LAUNCH(c, launch_adam_rows(table, exp_avg, exp_avg_sq, last_step, table_rows, d, n, rows, grad_rows, step, lr,
                                      beta1, beta2, eps, c->stream));
+  return GQE_OK;
+}
+
+// ---- GraphSAGE-style encoder steps ---------------------------------------------------
+extern "C" int gqe_segment_mean_device(gqe_ctx* c, const float* src, int64_t n_src, int32_t d, int64_t n,
+                                       const int64_t* ptr, const int32_t* cols, float* out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (n < 0 || n_src < 0 || d <= 0 || d % 4 != 0) return fail(c, GQE_ERR_INVALID, "gqe_segment_mean_device: bad size");
+  if (n == 0) return GQE_OK;
+  if (!src || !ptr || !cols || !out) return fail(c, GQE_ERR_INVALID, "gqe_segment_mean_device: null argument");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  drop_stale_error("gqe_segment_mean_device");
+  GQE_BWD_LAUNCH(c, launch_segment_mean(src, n_src, d, n, ptr, cols, out, c->d_err, c->stream));
+  return GQE_OK;
+}
+
+extern "C" int gqe_linear_device(gqe_ctx* c, const float* w, int32_t m, int32_t k, int64_t n, const float* x,
+                                 int32_t relu, float* out) {
+  if (!c) return GQE_ERR_INVALID;
+  if (m <= 0 || k <= 0 || n < 0) return fail(c, GQE_ERR_INVALID, "gqe_linear_device: bad size");
+  if (n == 0) return GQE_OK;
+  if (!w || !x || !out) return fail(c, GQE_ERR_INVALID, "gqe_linear_device: null argument");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  drop_stale_error("gqe_linear_device");
+  GQE_BWD_LAUNCH(c, launch_linear(w, m, k, n, x, relu, out, c->stream));
   return GQE_OK;
 }
 

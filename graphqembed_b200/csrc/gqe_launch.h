@@ -49,6 +49,11 @@ cudaError_t launch_adam_rows(float* table, float* m, float* v, int32_t* last, in
                              const int64_t* rows, const float* grads, int step, float lr, float beta1, float beta2,
                              float eps, cudaStream_t st);
 
+// GraphSAGE-style encoder steps (gqe_sage.cu)
+cudaError_t launch_segment_mean(const float* src, int64_t n_src, int d, int64_t n, const int64_t* ptr, const int32_t* cols,
+                                float* out, unsigned long long* err, cudaStream_t st);
+cudaError_t launch_linear(const float* w, int m, int k, int64_t n, const float* x, int relu, float* out, cudaStream_t st);
+
 // streaming kernel of the contraction-free decoders (gqe_vec.cu): TransE / DistMult chains and
 // element-wise intersections, any supported d, regular layout with T <= 2
 cudaError_t launch_fused_vec(int d, const LaunchParams& lp, cudaStream_t st);

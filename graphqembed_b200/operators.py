@@ -350,12 +350,10 @@ _SHARED_CTX = {}
 
 # ---- factories with the reference's names (netquery/utils.py:93-150) -------------
 def get_encoder(depth, graph, out_dims, feature_modules, cuda=True):
-    if depth < 0 or depth > 3:
-        raise Exception("Depth must be between 0 and 3 (inclusive)")
-    if depth != 0:
-        raise NotImplementedError("only the depth-0 DirectEncoder is on the accelerated path (Bio default, "
-                                  "reference bio/train.py:15)")
-    return DirectEncoder(graph.features, feature_modules)
+    """utils.py:93-126: depth 0 = DirectEncoder (the fused path), 1..3 = stacked GraphSAGE-style
+    Encoders (``sage.py``; un-fused operator chain)."""
+    from .sage import get_encoder as _get
+    return _get(depth, graph, out_dims, feature_modules, cuda)
 
 
 def get_metapath_decoder(graph, out_dims, decoder):

@@ -34,8 +34,12 @@ class QueryEncoderDecoder(nn.Module):
 
     def __init__(self, graph, enc, path_dec, inter_dec):
         super(QueryEncoderDecoder, self).__init__()
-        if not isinstance(enc, DirectEncoder):
-            raise TypeError("enc must be a graphqembed_b200.DirectEncoder")
+        from .sage import Encoder as SageEncoder
+        if not isinstance(enc, (DirectEncoder, SageEncoder)):
+            raise TypeError("enc must be a graphqembed_b200.DirectEncoder or a graphqembed_b200.sage.Encoder")
+        # the fused kernels gather + normalise table rows themselves: DirectEncoder only.  With a
+        # GraphSAGE-style encoder the operators run one after another as in model.py:70-109
+        self._fused = isinstance(enc, DirectEncoder)
         if not isinstance(path_dec, _MetapathDecoder):
             raise TypeError("path_dec must be a graphqembed_b200 metapath decoder")
         if not isinstance(inter_dec, (SetIntersection, SimpleSetIntersection)):
@@ -104,6 +108,9 @@ class QueryEncoderDecoder(nn.Module):
         return v
 
     def context(self):
+        if not self._fused:
+            raise RuntimeError("the fused calls gather table rows themselves and need a DirectEncoder; with a "
+                               "GraphSAGE-style encoder use forward() / margin_loss() (un-fused operator chain)")
         allp, _, device = self._lists()
         dev = device.index if device.index is not None else torch.cuda.current_device()
         st = self._state
@@ -247,6 +254,8 @@ class QueryEncoderDecoder(nn.Module):
         """model.py:70-109.  Unknown query types return None like the reference."""
         if formula.query_type not in QUERY_TYPES:
             return None
+        if not self._fused:
+            return self._forward_unfused(formula, queries, source_nodes)
         if isinstance(queries, StoreSlice):      # pair i = queries[i] against source_nodes[i]
             return self.score_batch(QueryBatch(formula, queries.anchors, np.asarray(source_nodes, dtype=np.int32)))
         batch, order = QueryBatch.from_queries(formula, queries, source_nodes)
@@ -256,6 +265,36 @@ class QueryEncoderDecoder(nn.Module):
         out = torch.empty_like(scores)
         out[self._to_dev(order)] = scores
         return out
+
+    def _forward_unfused(self, formula, queries, source_nodes):
+        """model.py:70-109 operator by operator (encoder calls in the reference's order: the
+        GraphSAGE-style encoder draws its neighbour samples from the global ``random`` stream)."""
+        from .operators import cosine_similarity_dim0
+        from .query import reverse_relation as rev
+        enc, dec, qt = self.enc, self.path_dec, formula.query_type
+        anchors = lambda k: [q.anchor_nodes[k] for q in queries]
+        if qt in ("1-chain", "2-chain", "3-chain"):
+            return dec.forward(enc.forward(source_nodes, formula.target_mode),
+                               enc.forward(anchors(0), formula.anchor_modes[0]), formula.rels)
+        target = enc.forward(source_nodes, formula.target_mode)
+        if qt == "3-chain_inter":
+            e1 = dec.project(enc.forward(anchors(0), formula.anchor_modes[0]), rev(formula.rels[1][0]))
+            e2 = dec.project(enc.forward(anchors(1), formula.anchor_modes[1]), rev(formula.rels[1][1]))
+            q = dec.project(self.inter_dec(e1, e2, formula.rels[0][-1]), rev(formula.rels[0]))
+            return cosine_similarity_dim0(target, q)
+        e1 = dec.project(enc.forward(anchors(0), formula.anchor_modes[0]), rev(formula.rels[0]))
+        e2 = enc.forward(anchors(1), formula.anchor_modes[1])
+        if len(formula.rels[1]) == 2:
+            for i_rel in formula.rels[1][::-1]:
+                e2 = dec.project(e2, rev(i_rel))
+        else:
+            e2 = dec.project(e2, rev(formula.rels[1]))
+        if qt == "3-inter":
+            e3 = dec.project(enc.forward(anchors(2), formula.anchor_modes[2]), rev(formula.rels[2]))
+            q = self.inter_dec(e1, e2, formula.target_mode, e3)
+        else:
+            q = self.inter_dec(e1, e2, formula.target_mode)
+        return cosine_similarity_dim0(target, q)
 
     def pick_negatives(self, formula, queries, hard_negatives=False):
         """model.py:113-120 -- same draws from the global ``random`` stream."""
@@ -286,6 +325,12 @@ class QueryEncoderDecoder(nn.Module):
         anchors / targets are array views, the negatives one vectorised draw
         (``self.negative_rng``; ``self.reference_negatives = True`` draws with the global
         ``random`` module in the reference's order instead)."""
+        if not self._fused:
+            # inference only: two operator-chain passes like model.py:122-127
+            neg_nodes = self.pick_negatives(formula, queries, hard_negatives)
+            affs = self.forward(formula, queries, [q.target_node for q in queries])
+            neg_affs = self.forward(formula, queries, neg_nodes)
+            return torch.clamp(margin - (affs - neg_affs), min=0).mean()
         if isinstance(queries, StoreSlice):
             if "inter" not in formula.query_type and hard_negatives:
                 raise Exception("Hard negative examples can only be used with intersection queries")

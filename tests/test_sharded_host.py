@@ -132,3 +132,25 @@ def test_row_exchange_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_route_by_target_mode_keeps_targets_local():
+    """sharded.route_by_target_mode: a formula is scored where its target node type lives."""
+    from graphqembed_b200 import sharded
+    from graphqembed_b200.query import Formula
+    from graphqembed_b200.synth import STRUCTURES, bio_shaped
+    kg = bio_shaped(scale=0.01)
+    rng = np.random.RandomState(0)
+    formulas = [Formula(s, kg.sample_rels(s, rng)) for s in STRUCTURES for _ in range(5)]
+    mode_ids = {m: i for i, m in enumerate(kg.modes)}
+    for world in (1, 2, 4, 8):
+        owner = sharded.owner_by_node_type(len(kg.modes), world)
+        routed = sharded.route_by_target_mode(formulas, mode_ids, owner)
+        assert sum(len(v) for v in routed.values()) == len(formulas)
+        for rank, fs in routed.items():
+            assert all(owner[mode_ids[f.target_mode]] == rank for f in fs)
+            assert set(mode_ids[f.target_mode] for f in fs) <= set(sharded.modes_owned_by(owner, rank))
+    # the workload generator can draw a rank's formulas from the node types it owns
+    from graphqembed_b200.workloads import make_workload
+    wl = make_workload("bio-mix-d256-b65536", kg=kg, total=60, target_modes=[kg.modes[1], kg.modes[3]])
+    assert set(b.formula.target_mode for b in wl.batches) <= {kg.modes[1], kg.modes[3]}
