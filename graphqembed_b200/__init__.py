@@ -14,7 +14,7 @@ from .lowering import RowLookup, lower_formula, relation_order
 from .query import Formula, Query, QueryBatch, reverse_relation
 from .store import FormulaBlock, QueryStore, StoreSlice
 
-__all__ = ["Context", "GqeError", "GqeIndexError", "QueryStore", "StoreSlice", "FormulaBlock", "SparseRowAdam", "Plan", "Segment", "build", "load", "make_segments", "RowLookup", "lower_formula",
+__all__ = ["Context", "GqeError", "GqeIndexError", "QueryStore", "StoreSlice", "FormulaBlock", "SparseRowAdam", "NativeAdam", "Plan", "Segment", "build", "load", "make_segments", "RowLookup", "lower_formula",
            "relation_order", "Formula", "Query", "QueryBatch", "reverse_relation", "DirectEncoder",
            "BilinearMetapathDecoder", "TransEMetapathDecoder", "BilinearDiagMetapathDecoder", "SetIntersection",
            "SimpleSetIntersection", "QueryEncoderDecoder", "get_encoder", "get_metapath_decoder",
@@ -25,7 +25,7 @@ _TORCH_SIDE = {
     "DirectEncoder": "operators", "BilinearMetapathDecoder": "operators", "TransEMetapathDecoder": "operators",
     "BilinearDiagMetapathDecoder": "operators", "SetIntersection": "operators", "SimpleSetIntersection": "operators",
     "get_encoder": "operators", "get_metapath_decoder": "operators", "get_intersection_decoder": "operators",
-    "cosine_similarity_dim0": "operators", "QueryEncoderDecoder": "scorer", "SparseRowAdam": "optim",
+    "cosine_similarity_dim0": "operators", "QueryEncoderDecoder": "scorer", "SparseRowAdam": "optim", "NativeAdam": "optim",
     "eval_auc_queries": "evaluation", "eval_perc_queries": "evaluation",
     "load_graph": "data", "load_queries": "data", "load_queries_by_formula": "data", "load_queries_by_type": "data",
     "load_test_queries_by_formula": "data", "run_batch": "data", "pick_batch": "data",

@@ -65,6 +65,14 @@ class Plan(C.Structure):
         return (self.structure, self.target_mode, tuple(self.anchor_mode), self.inter_mode, tuple(self.rel))
 
 
+class AdamHyper(C.Structure):
+    """gqe_adam: torch.optim.Adam's hyper-parameters (defaults as torch's)."""
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+    def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        C.Structure.__init__(self, float(lr), float(beta1), float(beta2), float(eps))
+
+
 class Segment(C.Structure):
     _fields_ = [("plan", Plan), ("query_begin", C.c_int64), ("query_end", C.c_int64)]
 
@@ -123,6 +131,13 @@ _SIGNATURES = {
     "gqe_encode_bwd_rows_device": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "gqe_adam_rows_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int32, C.c_float,
                                        C.c_float, C.c_float, C.c_float]),
+    "gqe_train_step_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_train_step_nodes_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_train_step_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_train_step_nodes_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_train_flush": (C.c_int, [_P]),
+    "gqe_train_reset": (C.c_int, [_P]),
+    "gqe_train_steps": (C.c_int64, [_P, C.c_int32]),
     "gqe_segment_mean_device": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
     "gqe_linear_device": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, C.c_int32, _P]),
     "gqe_ipc_export": (C.c_int, [_P, _P, C.c_char_p, C.POINTER(C.c_int64)]),
@@ -386,6 +401,28 @@ class Context(object):
         self._check(self._lib.gqe_adam_rows_device(self._h, table, exp_avg, exp_avg_sq, last_step, int(table_rows), int(d),
                                                    int(n), rows, grad_rows, int(step), float(lr), float(beta1),
                                                    float(beta2), float(eps)))
+
+    # -- native training step ------------------------------------------------------------
+    def train_step_device(self, plan, n_queries, anchors, pairs, margin, hyper, out_loss, nodes=False):
+        """hyper: an AdamHyper; anchors / pairs / out_loss: device pointers."""
+        fn = self._lib.gqe_train_step_nodes_device if nodes else self._lib.gqe_train_step_device
+        self._check(fn(self._h, C.byref(plan), int(n_queries), anchors, pairs, float(margin), C.byref(hyper), out_loss))
+
+    def train_step_host(self, plan, n_queries, anchors, pairs, margin, hyper, nodes=False):
+        """anchors / pairs: host pointers (ideally pinned); -> the loss before the update."""
+        fn = self._lib.gqe_train_step_nodes_host if nodes else self._lib.gqe_train_step_host
+        out = C.c_float(0.0)
+        self._check(fn(self._h, C.byref(plan), int(n_queries), anchors, pairs, float(margin), C.byref(hyper), C.byref(out)))
+        return out.value
+
+    def train_flush(self):
+        self._check(self._lib.gqe_train_flush(self._h))
+
+    def train_reset(self):
+        self._check(self._lib.gqe_train_reset(self._h))
+
+    def train_steps(self, mode):
+        return int(self._lib.gqe_train_steps(self._h, int(mode)))
 
     def segment_mean_device(self, src, n_src, d, n, ptr, cols, out):
         self._check(self._lib.gqe_segment_mean_device(self._h, src, int(n_src), int(d), int(n), ptr, cols, out))

@@ -49,6 +49,14 @@ cudaError_t launch_adam_rows(float* table, float* m, float* v, int32_t* last, in
                              const int64_t* rows, const float* grads, int step, float lr, float beta1, float beta2,
                              float eps, cudaStream_t st);
 
+// native training step (gqe_train.cu): row-wise Adam over a dense accumulated-gradient buffer (rows may
+// repeat; gsum == nullptr: catch the rows up to `step`), and Adam on a small dense parameter
+cudaError_t launch_adam_rows_accum(float* table, float* m, float* v, int32_t* last, int64_t table_rows, int d, int64_t n,
+                                   const int32_t* rows, float* gsum, int step, float lr, float beta1, float beta2, float eps,
+                                   cudaStream_t st);
+cudaError_t launch_adam_dense(float* p, float* m, float* v, const float* g, int64_t n, int step, float lr, float beta1,
+                              float beta2, float eps, cudaStream_t st);
+
 // GraphSAGE-style encoder steps (gqe_sage.cu)
 cudaError_t launch_segment_mean(const float* src, int64_t n_src, int d, int64_t n, const int64_t* ptr, const int32_t* cols,
                                 float* out, unsigned long long* err, cudaStream_t st);

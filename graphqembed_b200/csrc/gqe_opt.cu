@@ -96,17 +96,24 @@ __device__ __forceinline__ void adam_catch_up(float* __restrict__ p, float* __re
 
 // grads == nullptr: catch the listed rows (or, rows == nullptr, ALL rows) up to `step`;
 //                   duplicate rows in the list are fine (one claimant per row).
-// grads != nullptr: `rows` are UNIQUE; catch each up to step - 1, then apply Adam step `step`
-//                   with its gradient row.
+// grads != nullptr, !GSUM: `rows` are UNIQUE and grads holds one gradient row per list entry; catch each
+//                   row up to step - 1, then apply Adam step `step` with its gradient row.
+// grads != nullptr, GSUM: grads is a DENSE [table_rows, d] buffer into which the batch's row gradients
+//                   were accumulated (k_encode_bwd); `rows` may repeat.  The first warp to claim a row
+//                   (last[row] <- -step while it works) catches it up, applies Adam step `step` with
+//                   the accumulated row and ZEROES that row of the buffer again; the other claimants
+//                   of the row skip it.  Rows already at `step` (an earlier list of the same step) are
+//                   skipped as well.
+template <typename I, bool GSUM>
 __global__ void __launch_bounds__(256) k_adam_rows(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v,
                                                    int32_t* __restrict__ last, int64_t table_rows, int d, int64_t n,
-                                                   const int64_t* __restrict__ rows, const float* __restrict__ grads,
+                                                   const I* __restrict__ rows, float* __restrict__ grads,
                                                    int step, const AdamHyper h) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp0; i < n; i += n_warps) {
-    const int64_t row = rows ? rows[i] : i;
+    const int64_t row = rows ? (int64_t)rows[i] : i;
     if (row < 0 || row >= table_rows) continue;
     float* p = table + row * d;
     float* pm = m + row * d;
@@ -116,7 +123,8 @@ __global__ void __launch_bounds__(256) k_adam_rows(float* __restrict__ table, fl
     bool mine = false;
     if (lane == 0) {
       from = last[row];
-      if (from < target) mine = atomicCAS(last + row, from, target) == from;
+      if (GSUM) mine = from >= 0 && from < step && atomicCAS(last + row, from, -step) == from;
+      else if (from < target) mine = atomicCAS(last + row, from, target) == from;
       else mine = grads != nullptr && from == target;
     }
     from = __shfl_sync(0xffffffffu, from, 0);
@@ -126,17 +134,37 @@ __global__ void __launch_bounds__(256) k_adam_rows(float* __restrict__ table, fl
     if (grads) {
       const float bc1 = (float)(1.0 - pow((double)h.beta1, (double)step));
       const float bc2s = sqrtf((float)(1.0 - pow((double)h.beta2, (double)step)));
-      const float* g = grads + (size_t)i * d;
+      float* g = grads + (size_t)(GSUM ? row : i) * d;
       for (int k = lane; k < d; k += 32) {
         const float gk = g[k];
+        if (GSUM) g[k] = 0.f;
         const float mk = pm[k] + (gk - pm[k]) * (1.f - h.beta1);     // exp_avg.lerp_(grad, 1 - beta1)
         const float vk = pv[k] * h.beta2 + (1.f - h.beta2) * gk * gk;
         pm[k] = mk;
         pv[k] = vk;
         p[k] -= (h.lr / bc1) * (mk / (sqrtf(vk) / bc2s + h.eps));
       }
-      if (lane == 0) last[row] = step;
+      __syncwarp();
+      if (lane == 0) {
+        if (GSUM) __threadfence();
+        last[row] = step;
+      }
     }
+  }
+}
+
+// torch.optim.Adam on a small dense parameter (relation matrices / vectors, DeepSets pre / post)
+__global__ void __launch_bounds__(256) k_adam_dense(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                    const float* __restrict__ g, int64_t n, int step, const AdamHyper h) {
+  const float bc1 = (float)(1.0 - pow((double)h.beta1, (double)step));
+  const float bc2s = sqrtf((float)(1.0 - pow((double)h.beta2, (double)step)));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gk = g[i];
+    const float mk = m[i] + (gk - m[i]) * (1.f - h.beta1);
+    const float vk = v[i] * h.beta2 + (1.f - h.beta2) * gk * gk;
+    m[i] = mk;
+    v[i] = vk;
+    p[i] -= (h.lr / bc1) * (mk / (sqrtf(vk) / bc2s + h.eps));
   }
 }
 
@@ -162,7 +190,26 @@ cudaError_t launch_adam_rows(float* table, float* m, float* v, int32_t* last, in
                              float eps, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   AdamHyper h{lr, beta1, beta2, eps};
-  k_adam_rows<<<opt_grid(n), 256, 0, st>>>(table, m, v, last, table_rows, d, n, rows, grads, step, h);
+  k_adam_rows<int64_t, false><<<opt_grid(n), 256, 0, st>>>(table, m, v, last, table_rows, d, n, rows, const_cast<float*>(grads), step, h);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam_rows_accum(float* table, float* m, float* v, int32_t* last, int64_t table_rows, int d, int64_t n,
+                                   const int32_t* rows, float* gsum, int step, float lr, float beta1, float beta2, float eps,
+                                   cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  AdamHyper h{lr, beta1, beta2, eps};
+  if (gsum) k_adam_rows<int32_t, true><<<opt_grid(n), 256, 0, st>>>(table, m, v, last, table_rows, d, n, rows, gsum, step, h);
+  else k_adam_rows<int32_t, false><<<opt_grid(n), 256, 0, st>>>(table, m, v, last, table_rows, d, n, rows, nullptr, step, h);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam_dense(float* p, float* m, float* v, const float* g, int64_t n, int step, float lr, float beta1,
+                              float beta2, float eps, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  AdamHyper h{lr, beta1, beta2, eps};
+  const int64_t blocks = (n + 255) / 256;
+  k_adam_dense<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(p, m, v, g, n, step, h);
   return cudaGetLastError();
 }
 

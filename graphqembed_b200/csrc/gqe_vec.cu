@@ -7,11 +7,16 @@
 // operators, the cosine (raw dot for DistMult chains) against the positive and the negative
 // target and the hinge (model.py:112-127) -- touches (A + T) table rows of 4d bytes and does
 // O(d) flops on them.  It is bound by the HBM gather, so there is no tile, no shared memory
-// and no block-level synchronisation here: ONE WARP owns one query, issues the 128-bit loads
-// of all its rows at once (up to 5 rows x d/128 float4 per lane in flight, 24 warps per SM),
-// keeps everything in registers and reduces with warp shuffles.  The indices of the warp's
-// next query are fetched (and mapped through the node map) while the rows of the current one
-// are in flight.
+// and no block-level synchronisation here: a 16-lane HALF WARP owns one query (a warp scores two
+// queries of the same formula side by side, so every shuffle butterfly, index lookup and scalar
+// epilogue instruction is shared by two queries -- the kernel was issue-bound with a warp per
+// query: 626 warp instructions per query, 59 % issue-slot use at 0.44 of the HBM roofline),
+// issues the 128-bit loads of all its rows at once (up to 5 rows x d/64 float4 per lane in
+// flight), keeps everything in registers and reduces with shuffles inside the half.  Blocks walk
+// over groups of 16 consecutive queries of one formula, so the structure branches are uniform;
+// the indices of the next group are fetched (and mapped through the node map) while the rows of
+// the current one are in flight.  Norms and cosines use MUFU.RSQ forms (~2^-22 relative) instead
+// of IEEE sqrt / division, whose checked slow paths cost ~10 instructions each.
 //
 // Same arithmetic, in the same order per element, as the tile kernels of gqe_simt.cuh (which
 // remain the path for the ragged / many-target layouts and for DeepSets intersections on top
@@ -27,17 +32,11 @@ namespace {
 constexpr int kVecThreads = 256;
 constexpr int kVecWarps = kVecThreads / 32;
 
-__device__ __forceinline__ float vsum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 __device__ __forceinline__ double vsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float vmin_nan(float a, float b) { return (a < b || a != a) ? a : b; }
 __device__ __forceinline__ float sq4(const float4 v, float s) {
   s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); return fmaf(v.w, v.w, s);
 }
@@ -56,38 +55,64 @@ __device__ __forceinline__ float4 rel4(const float4 x, const float4 v, bool mul)
              : make_float4(x.x + v.x, x.y + v.y, x.z + v.z, x.w + v.w);
 }
 
-// butterflies of several values in lockstep (their shuffle latencies overlap)
+// x / max(|x|, eps) and friends, branch-free (no IEEE slow paths: a sqrtf / division each costs a
+// checked call sequence, ~10 instructions, and this kernel is issue-bound).  ~2^-22 relative.
+//   unit_dot(d, nn)  = d / sqrt(nn)        (nn = 0 -> 0 * inf = NaN, the reference's 0 / 0)
+//   clamped_norm(nn) = max(sqrt(nn), eps)  (keeps NaN)
+__device__ __forceinline__ float unit_dot(float d, float nn) { return d * rsqrtf(nn); }
+__device__ __forceinline__ float clamped_norm(float nn) {
+  const float n = nn > 0.f ? nn * rsqrtf(nn) : nn;
+  return n >= kCosEps ? n : (n != n ? n : kCosEps);
+}
+// torch.min over the stacked operands propagates NaN: one instruction
+__device__ __forceinline__ float min_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+#ifndef GQE_VEC_PREFETCH
+#define GQE_VEC_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+constexpr int kHalf = 16;                 // lanes per query
+constexpr int kQW = 32 / kHalf;           // queries per warp
+constexpr int kQB = kVecWarps * kQW;      // queries per block and iteration (a "group")
+
+// butterflies of several values inside each 16-lane half, in lockstep
 template <int N>
-__device__ __forceinline__ void vsum_n(float (&v)[N]) {
+__device__ __forceinline__ void hsum_n(float (&v)[N]) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = kHalf / 2; o > 0; o >>= 1) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
   }
 }
 
-// One query, everything in registers.  `idx`: lanes 0..NA-1 hold the anchor rows, lanes 8, 9 the
-// target rows (lane 9 = lane 8 when the query has one target).  Returns the two scores.
+// One query per 16-lane half of the warp (two queries of the SAME formula per warp), everything in
+// registers.  `idx`: sub-lanes 0..NA-1 of each half hold the anchor rows of its query, sub-lanes 8, 9
+// the target rows (9 = 8 when the query has one target).  Returns the half's two scores.
 template <int D, int NA, bool CHAIN>
-__device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int lane, bool mul, bool use_min, float (&sc)[2]) {
-  constexpr int NV = (D + 127) / 128;          // float4 per lane per row
-  constexpr int LANES = D >= 128 ? 32 : D / 4; // d < 128: the upper lanes idle
-  const bool act = LANES == 32 || lane < LANES;
+__device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int sl, bool mul, bool use_min, float (&sc)[2]) {
+  constexpr int LANES = D / 4 < kHalf ? D / 4 : kHalf;   // d = 32: the upper sub-lanes idle
+  constexpr int NV = D / 4 / LANES;                      // float4 per lane per row
+  const bool act = LANES == kHalf || sl < LANES;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto ld = [&](const float* base, int j) {
-    return act ? __ldg(reinterpret_cast<const float4*>(base) + lane + 32 * j) : zero4;
+    return act ? __ldg(reinterpret_cast<const float4*>(base) + sl + LANES * j) : zero4;
   };
-  // ---- all row loads of this query, back to back
+  // ---- all row loads of both queries, back to back
   float4 a[NA][NV], t[2][NV];
 #pragma unroll
   for (int b = 0; b < NA; ++b) {
-    const float* src = s.anc_table[b] + (size_t)__shfl_sync(0xffffffffu, idx, b) * D;
+    const float* src = s.anc_table[b] + (size_t)__shfl_sync(0xffffffffu, idx, b, kHalf) * D;
 #pragma unroll
     for (int j = 0; j < NV; ++j) a[b][j] = ld(src, j);
   }
 #pragma unroll
   for (int tt = 0; tt < 2; ++tt) {
-    const float* src = s.tgt_table + (size_t)__shfl_sync(0xffffffffu, idx, 8 + tt) * D;
+    const float* src = s.tgt_table + (size_t)__shfl_sync(0xffffffffu, idx, 8 + tt, kHalf) * D;
 #pragma unroll
     for (int j = 0; j < NV; ++j) t[tt][j] = ld(src, j);
   }
@@ -97,10 +122,9 @@ __device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int la
     float n2[3] = {0.f, 0.f, 0.f};               // |a|^2, |t0|^2, |t1|^2
 #pragma unroll
     for (int j = 0; j < NV; ++j) { n2[0] = sq4(a[0][j], n2[0]); n2[1] = sq4(t[0][j], n2[1]); n2[2] = sq4(t[1][j], n2[2]); }
-    vsum_n(n2);
-    // x / |x| as x * (1 / |x|): one IEEE reciprocal per row instead of a division per element
-    // (<= 1 ulp from the reference's true division; |x| = 0 gives 0 * inf = NaN like 0 / 0)
-    const float ia = __frcp_rn(sqrtf(n2[0])), it0 = __frcp_rn(sqrtf(n2[1])), it1 = __frcp_rn(sqrtf(n2[2]));
+    hsum_n(n2);
+    // x / |x| as x * rsqrt(|x|^2): |x| = 0 gives 0 * inf = NaN like the reference's 0 / 0
+    const float ia = rsqrtf(n2[0]), it0 = rsqrtf(n2[1]), it1 = rsqrtf(n2[2]);
     const int hops = s.structure + 1;
     float r[4] = {0.f, 0.f, 0.f, 0.f};           // y0.a_hat, |y0|^2, y1.a_hat, |y1|^2
 #pragma unroll
@@ -116,9 +140,9 @@ __device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int la
       r[0] = dot4(y0, ah, r[0]); r[1] = sq4(y0, r[1]);
       r[2] = dot4(y1, ah, r[2]); r[3] = sq4(y1, r[3]);
     }
-    vsum_n(r);
-    sc[0] = mul ? r[0] : r[0] / fmaxf(sqrtf(r[1]), kCosEps);
-    sc[1] = mul ? r[2] : r[2] / fmaxf(sqrtf(r[3]), kCosEps);
+    hsum_n(r);
+    sc[0] = mul ? r[0] : __fdividef(r[0], clamped_norm(r[1]));
+    sc[1] = mul ? r[2] : __fdividef(r[2], clamped_norm(r[3]));
   } else {
     // q = agg_b project(a_hat_b) [projected once more for 3-chain_inter]; cos(t_hat, q)  (model.py:77-109)
     float n2[NA];
@@ -128,10 +152,10 @@ __device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int la
 #pragma unroll
       for (int j = 0; j < NV; ++j) n2[b] = sq4(a[b][j], n2[b]);
     }
-    vsum_n(n2);
+    hsum_n(n2);
     float ib[NA];
 #pragma unroll
-    for (int b = 0; b < NA; ++b) ib[b] = __frcp_rn(sqrtf(n2[b]));
+    for (int b = 0; b < NA; ++b) ib[b] = rsqrtf(n2[b]);
     const int structure = s.structure;
     float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};      // |q|^2, |t0|^2, t0.q, |t1|^2, t1.q
 #pragma unroll
@@ -147,7 +171,7 @@ __device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int la
           e = rel4(e, ld(s.rel[b], j), mul);
         }
         if (b == 0) q = e;
-        else if (use_min) q = make_float4(vmin_nan(q.x, e.x), vmin_nan(q.y, e.y), vmin_nan(q.z, e.z), vmin_nan(q.w, e.w));
+        else if (use_min) q = make_float4(min_nan(q.x, e.x), min_nan(q.y, e.y), min_nan(q.z, e.z), min_nan(q.w, e.w));
         else q = make_float4(q.x + e.x, q.y + e.y, q.z + e.z, q.w + e.w);
       }
       if (!use_min) q = scale4(q, NA == 2 ? 0.5f : 1.f / 3.f);                    // torch.mean over the stack
@@ -157,90 +181,112 @@ __device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int la
       r[1] = sq4(t[0][j], r[1]); r[2] = dot4(t[0][j], q, r[2]);
       r[3] = sq4(t[1][j], r[3]); r[4] = dot4(t[1][j], q, r[4]);
     }
-    vsum_n(r);
-    const float nq = fmaxf(sqrtf(r[0]), kCosEps);
+    hsum_n(r);
+    const float nq = clamped_norm(r[0]);
     // t_hat = t/|t| has unit norm: cos(t_hat, q) = (t.q/|t|) / max(|q|, eps); a zero target row gives
     // 0/0 = NaN as in the reference
-    sc[0] = __fdiv_rn(r[2], sqrtf(r[1])) / nq;
-    sc[1] = __fdiv_rn(r[4], sqrtf(r[3])) / nq;
+    sc[0] = __fdividef(unit_dot(r[2], r[1]), nq);
+    sc[1] = __fdividef(unit_dot(r[4], r[3]), nq);
   }
 }
 
 #ifndef GQE_VEC_BLOCKS_D256
-#define GQE_VEC_BLOCKS_D256 3
+#define GQE_VEC_BLOCKS_D256 2
 #endif
 template <int D>
-__global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 : 4)) gqe_fused_vec(const __grid_constant__ LaunchParams p) {
+__global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 : 3)) gqe_fused_vec(const __grid_constant__ LaunchParams p) {
   __shared__ double red[kVecWarps];
   __shared__ int last;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t warp = (int64_t)blockIdx.x * kVecWarps + wib;
-  const int64_t n_warps = (int64_t)gridDim.x * kVecWarps;
+  const int sl = lane & (kHalf - 1);
+  const int qslot = wib * kQW + lane / kHalf;     // this half-warp's query inside a group
   const bool mul = p.decoder == GQE_DEC_DISTMULT;
   const bool use_min = p.inter == GQE_INTER_DEEPSETS_MIN || p.inter == GQE_INTER_SIMPLE_MIN;
   const int T = p.T;
   const int ik = p.index_kind;
   double local = 0.0;
 
-  // The queries of ALL segments form one flat iteration space g = 0 .. total-1 (segment after
-  // segment); warp w takes g = w, w + n_warps, ...  so that the software pipeline below never
-  // drains at a formula boundary and the last wave is one query per warp, not one per formula.
+  // Iteration space: GROUPS of kQB consecutive queries of one formula (the last group of a formula
+  // may be partly empty); block b takes groups b, b + gridDim.x, ...  Which formula a group belongs
+  // to depends on blockIdx and the loop counter only, so every branch on the query structure below
+  // is uniform across the block: no divergence, the warp shuffles need no convergence barriers.
+  auto groups_of = [&](int i) -> int64_t { return (p.seg[i].q_end - p.seg[i].q_begin + kQB - 1) / kQB; };
   int64_t total = 0;
-  for (int i = 0; i < p.n_segs; ++i) total += p.seg[i].q_end - p.seg[i].q_begin;
-  struct Cursor { int si; int64_t base; };                 // g -> (segment, query); only moves forward
-  auto locate = [&](Cursor& c, int64_t g) -> int64_t {    // the query index, -1 past the end
-    if (g >= total) return -1;
-    while (g >= c.base + (p.seg[c.si].q_end - p.seg[c.si].q_begin)) {
-      c.base += p.seg[c.si].q_end - p.seg[c.si].q_begin;
+  for (int i = 0; i < p.n_segs; ++i) total += groups_of(i);
+  struct Cursor { int si; int64_t base; };                 // group -> (segment, first group of it); only moves forward
+  auto locate = [&](Cursor& c, int64_t g) -> bool {       // false past the end
+    if (g >= total) return false;
+    while (g >= c.base + groups_of(c.si)) {
+      c.base += groups_of(c.si);
       ++c.si;
     }
-    return p.seg[c.si].q_begin + (g - c.base);
+    return true;
   };
-  // lanes 0..na-1 hold the anchor indices of a query, lanes 8, 9 its target indices (lane 9 repeats
-  // target 0 when T == 1).  Three stages, one loop iteration apart, so that no dependent load is ever
-  // waited for: the raw index of query i+2, the node-map lookup of query i+1, the bounds check + row
-  // loads of query i.
-  const int tslot = lane == 9 && T > 1 ? 1 : 0;
+  // this half-warp's query of group g (-1: none)
+  auto query_of = [&](const Cursor& c, int64_t g, bool in) -> int64_t {
+    if (!in) return -1;
+    const int64_t q = p.seg[c.si].q_begin + (g - c.base) * kQB + qslot;
+    return q < p.seg[c.si].q_end ? q : -1;
+  };
+  // sub-lanes 0..na-1 of a half hold the anchor indices of its query, sub-lanes 8, 9 its target indices
+  // (9 repeats target 0 when T == 1).
+  const int tslot = sl == 9 && T > 1 ? 1 : 0;
   auto lane_mode = [&](const SegDev& sg) -> int {        // this lane's node type in a query of `sg`, -1: none
-    if (lane < sg.n_anchor) return sg.anc_mode[lane];
-    if (lane == 8 || lane == 9) return sg.tgt_mode;
+    if (sl < sg.n_anchor) return sg.anc_mode[sl];
+    if (sl == 8 || sl == 9) return sg.tgt_mode;
     return -1;
   };
-  auto fetch_raw = [&](int64_t q, const Cursor& c) -> int32_t {
+  auto fetch_raw = [&](int64_t q, const SegDev& sg) -> int32_t {
     if (q < 0) return 0;
-    if (lane < p.seg[c.si].n_anchor) return __ldg(p.anchor_rows + (int64_t)lane * p.anchor_stride + q);
-    if (lane == 8 || lane == 9) return __ldg(p.target_rows + q * T + tslot);
+    if (sl < sg.n_anchor) return __ldg(p.anchor_rows + (int64_t)sl * p.anchor_stride + q);
+    if (sl == 8 || sl == 9) return __ldg(p.target_rows + q * T + tslot);
     return 0;
   };
-  Cursor c0{0, 0}, c1{0, 0}, c2{0, 0};
-  int64_t g = warp;
-  int64_t q = locate(c0, g), q1 = locate(c1, g + n_warps);
-  int32_t raw_cur = fetch_raw(q, c0), raw_nxt = fetch_raw(q1, c1);
-  int32_t cand = 0;
-  if (q >= 0) {
-    const int m = lane_mode(p.seg[c0.si]);
-    if (m >= 0) cand = index_lookup(p.mode[m], raw_cur, ik);
+  // Software pipeline over this block's groups, stage k = the group k iterations ahead:
+  //   3  raw indices fetched        2  node-map lookups issued, and -- at the END of the iteration, when
+  //   they have landed -- the rows' lines requested into L2 (prefetch.global.L2: no registers held)
+  //   1  (in flight)                0  bounds check, row loads (L2 hits by now), arithmetic
+  // so that no dependent load is ever waited for and every row has a whole iteration to come up
+  // from HBM.  (Prefetching right behind the lookup instead stalls the warp on the lookup.)
+  const int64_t G = gridDim.x;
+  Cursor cu[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  bool in[4];
+  int64_t qq[4];
+  int32_t raw[4], cand[3] = {0, 0, 0};
+  int64_t g = blockIdx.x;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    in[k] = locate(cu[k], g + k * G);
+    qq[k] = query_of(cu[k], g + k * G, in[k]);
+    raw[k] = in[k] ? fetch_raw(qq[k], p.seg[cu[k].si]) : 0;
   }
-  for (; q >= 0; g += n_warps) {
-    const SegDev& s = p.seg[c0.si];
-    int32_t idx = 0;
-    {
-      const int my_mode = lane_mode(s);
-      if (my_mode >= 0) idx = index_check(p.mode[my_mode], my_mode, cand, raw_cur, ik, p.err);
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (qq[k] >= 0) {
+      const int m = lane_mode(p.seg[cu[k].si]);
+      if (m >= 0) cand[k] = index_lookup(p.mode[m], raw[k], ik);
     }
-    // the later queries' indices travel while this query's rows do
-    const int64_t q2 = locate(c2, g + 2 * n_warps);
-    const int32_t raw_nxt2 = fetch_raw(q2, c2);
-    int32_t cand_nxt = 0;
-    if (q1 >= 0) {
-      const int m = lane_mode(p.seg[c1.si]);
-      if (m >= 0) cand_nxt = index_lookup(p.mode[m], raw_nxt, ik);
+  for (; in[0]; g += G) {
+    const SegDev& s = p.seg[cu[0].si];
+    const int64_t q = qq[0];
+    int32_t idx = 0;
+    if (q >= 0) {
+      const int my_mode = lane_mode(s);
+      if (my_mode >= 0) idx = index_check(p.mode[my_mode], my_mode, cand[0], raw[0], ik, p.err);
+    }
+    in[3] = locate(cu[3], g + 3 * G);
+    qq[3] = query_of(cu[3], g + 3 * G, in[3]);
+    raw[3] = in[3] ? fetch_raw(qq[3], p.seg[cu[3].si]) : 0;
+    int m2 = -1;
+    if (qq[2] >= 0) {
+      m2 = lane_mode(p.seg[cu[2].si]);
+      if (m2 >= 0) cand[2] = index_lookup(p.mode[m2], raw[2], ik);
     }
     float sc[2];
-    if (s.structure <= GQE_CHAIN3) score_query<D, 1, true>(s, idx, lane, mul, use_min, sc);
-    else if (s.n_anchor == 2) score_query<D, 2, false>(s, idx, lane, mul, use_min, sc);
-    else score_query<D, 3, false>(s, idx, lane, mul, use_min, sc);
-    if (lane == 0) {
+    if (s.structure <= GQE_CHAIN3) score_query<D, 1, true>(s, idx, sl, mul, use_min, sc);
+    else if (s.n_anchor == 2) score_query<D, 2, false>(s, idx, sl, mul, use_min, sc);
+    else score_query<D, 3, false>(s, idx, sl, mul, use_min, sc);
+    if (sl == 0 && q >= 0) {
       if (p.out_scores) {
         p.out_scores[q * T] = sc[0];
         if (T > 1) p.out_scores[q * T + 1] = sc[1];
@@ -250,13 +296,23 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
         local += (double)(h < 0.f ? 0.f : h);
       }
     }
-    raw_cur = raw_nxt;
-    raw_nxt = raw_nxt2;
-    cand = cand_nxt;
-    q = q1;
-    q1 = q2;
-    c0 = c1;
-    c1 = c2;
+    if (GQE_VEC_PREFETCH && m2 >= 0) {
+      // each lane that holds a row index of the group two iterations ahead asks for the D*4/128
+      // lines of its row.  (Not for a peer GPU's shard: see gqe_tc.cuh.)
+      const SegDev& s2 = p.seg[cu[2].si];
+      const bool tgt = sl >= 8;
+      const bool remote = ((s2.remote_mask >> (tgt ? 3 : sl)) & 1u) != 0;
+      if (!remote && (uint32_t)cand[2] < p.mode[m2].rows) {
+        const float* row = (tgt ? s2.tgt_table : s2.anc_table[sl]) + (size_t)cand[2] * D;
+#pragma unroll
+        for (int l = 0; l < D / 32; ++l) prefetch_line(row + 32 * l);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { cu[k] = cu[k + 1]; in[k] = in[k + 1]; qq[k] = qq[k + 1]; raw[k] = raw[k + 1]; }
+    cand[0] = cand[1];
+    cand[1] = cand[2];
+    cand[2] = 0;
   }
 
   if (!p.out_loss) return;
@@ -292,7 +348,7 @@ cudaError_t launch_vec_t(const LaunchParams& lp, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // never more CTAs than 64-row tiles (the margin-loss partials are sized by the tile count)
-  const int64_t cap = (int64_t)sms * (D >= 256 ? GQE_VEC_BLOCKS_D256 : 4);
+  const int64_t cap = (int64_t)sms * (D >= 256 ? GQE_VEC_BLOCKS_D256 : 3);
   const int grid = (int)(lp.n_tiles < cap ? (lp.n_tiles > 0 ? lp.n_tiles : 1) : cap);
   gqe_fused_vec<D><<<grid, kVecThreads, 0, st>>>(lp);
   return cudaGetLastError();

@@ -20,7 +20,79 @@ matrices / vectors, DeepSets pre / post) go through ``torch.optim.Adam`` unchang
     loss = model.margin_loss(formula, queries); loss.backward(); opt.step(); opt.zero_grad()
     opt.flush()                                   # before evaluation / torch.save: all rows up to date
 """
+import numpy as np
 import torch
+
+from . import _lib
+from .query import QueryBatch
+from .store import StoreSlice
+
+
+class NativeAdam(object):
+    """The whole loop body of the reference's training (netquery/train_helpers.py:76-79) as ONE
+    native call per batch:
+
+        opt = NativeAdam(model, lr=0.01)                 # instead of optim.Adam(model.parameters(), lr=0.01)
+        loss = opt.step(formula, queries)                # zero_grad + margin_loss + backward + optimizer.step()
+        opt.flush()                                      # before evaluation / torch.save: all rows up to date
+
+    ``gqe_train_step_nodes_host`` runs the exact-fp32 forward pass, the backward pass and the Adam
+    update (dense torch.optim.Adam trajectory; the tables are updated row-wise with exact catch-up,
+    see ``SparseRowAdam``) without returning to Python between kernels.  The model's parameters are
+    updated in place; the optimiser state lives in the model's native context.  ``queries``: a list of
+    ``Query`` objects or a ``StoreSlice``; negatives are drawn exactly as ``margin_loss`` draws them.
+    """
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        self.hyper = _lib.AdamHyper(lr, betas[0], betas[1], eps)
+        self._pin = None
+
+    def _pinned(self, n_int32):
+        if self._pin is None or self._pin.numel() < n_int32:
+            self._pin = torch.empty(max(n_int32 + n_int32 // 2, 4096), dtype=torch.int32).pin_memory()
+        return self._pin
+
+    def step(self, formula, queries, hard_negatives=False, margin=1):
+        """-> the batch's margin loss before the update (Python float)."""
+        m = self.model
+        ctx = m.context()
+        if isinstance(queries, StoreSlice):
+            if "inter" not in formula.query_type and hard_negatives:
+                raise Exception("Hard negative examples can only be used with intersection queries")
+            full = m._full_array(formula.target_mode) if formula.query_type == "1-chain" else None
+            neg = queries.draw_negatives(hard_negatives, full, m.negative_rng, m.reference_negatives)
+            anchors, pos = np.asarray(queries.anchors), np.asarray(queries.targets)
+        else:
+            neg = m.pick_negatives(formula, queries, hard_negatives)
+            n = len(queries)
+            anchors = np.empty((len(formula.anchor_modes), n), dtype=np.int64)
+            for k in range(anchors.shape[0]):
+                anchors[k] = np.fromiter((q.anchor_nodes[k] for q in queries), dtype=np.int64, count=n)
+            pos = np.fromiter((q.target_node for q in queries), dtype=np.int64, count=n)
+        n = len(pos)
+        pairs = np.empty((n, 2), dtype=np.int64)
+        pairs[:, 0] = pos
+        pairs[:, 1] = np.asarray(neg)
+        batch = QueryBatch(formula, anchors, pairs.reshape(-1))
+        a, t, nodes = m._indices(batch)                    # node ids (device lookup) or host-lowered rows
+        na = a.shape[0]
+        pin = self._pinned(na * n + 2 * n)
+        view = pin.numpy()
+        view[:na * n] = np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
+        view[na * n:na * n + 2 * n] = np.ascontiguousarray(t, dtype=np.int32).reshape(-1)
+        base = pin.data_ptr()
+        loss = ctx.train_step_host(m.plan(formula), n, base, base + 4 * na * n, margin, self.hyper, nodes=nodes)
+        return loss
+
+    def flush(self):
+        self.model.context().train_flush()
+
+    def reset(self):
+        self.model.context().train_reset()
+
+    def zero_grad(self, set_to_none=True):     # (nothing to clear: gradients never leave the native step)
+        pass
 
 
 class SparseRowAdam(object):

@@ -374,6 +374,44 @@ int gqe_adam_rows_device(gqe_ctx* ctx, float* table, float* exp_avg, float* exp_
                          int64_t table_rows, int32_t d, int64_t n, const int64_t* rows, const float* grad_rows,
                          int32_t step, float lr, float beta1, float beta2, float eps);
 
+/* ---- native training step -----------------------------------------------------------
+ * The body of the reference's training loop for one formula batch (netquery/train_helpers.py:76-79,
+ * netquery/bio/train.py:59-62):
+ *     optimizer.zero_grad(); loss = enc_dec.margin_loss(formula, queries); loss.backward(); optimizer.step()
+ * with torch.optim.Adam (no weight decay, no amsgrad), as ONE call: the forward pass of
+ * netquery/model.py:70-127 in exact fp32, its backward pass and the Adam update of every parameter
+ * that received a gradient are launched back to back from native code.  The bound tables and operator
+ * parameters are updated IN PLACE (they alias the owner's storage).  Optimiser state -- moments, step
+ * counters, one [rows, d] gradient-accumulation buffer per trained table -- lives in the context.
+ *   tables: only the rows the batch gathered are touched; a row is first caught up with the
+ *     zero-gradient steps dense Adam applied to it since it was last touched (gqe_adam_rows_device),
+ *     so the trajectory is dense torch.optim.Adam's.  Call gqe_train_flush before reading the tables
+ *     outside the training step (evaluation, torch.save).
+ *   operators: dense Adam on the relation matrices / vectors and pre / post matrices the formula used
+ *     (torch.optim.Adam skips parameters without a gradient; so does this).
+ * anchors: int32 [n_anchors, n_queries]; pairs: int32 [n_queries, 2] = (positive, negative) target --
+ * table rows, or node ids for the *_nodes calls (gqe_bind_node_maps).  out_loss: the batch's margin
+ * loss BEFORE the update, DEVICE (or, *_host: HOST) float.  The *_host calls take HOST index buffers,
+ * synchronise and report a bad index as GQE_ERR_INDEX (the step has then been applied with row 0 in its
+ * place); the *_device calls are asynchronous (poll gqe_index_error). */
+typedef struct gqe_adam {
+  float lr, beta1, beta2, eps;
+} gqe_adam;
+int gqe_train_step_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                          const int32_t* pair_rows, float margin, const gqe_adam* hyper, float* out_loss);
+int gqe_train_step_nodes_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_nodes,
+                                const int32_t* pair_nodes, float margin, const gqe_adam* hyper, float* out_loss);
+int gqe_train_step_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                        const int32_t* pair_rows, float margin, const gqe_adam* hyper, float* out_loss);
+int gqe_train_step_nodes_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_nodes,
+                              const int32_t* pair_nodes, float margin, const gqe_adam* hyper, float* out_loss);
+/* every row of every trained table up to date (the zero-gradient steps it still owes) */
+int gqe_train_flush(gqe_ctx* ctx);
+/* forget the optimiser state (moments, step counters); the parameters keep their values */
+int gqe_train_reset(gqe_ctx* ctx);
+/* Adam steps the table of `mode` has taken so far */
+int64_t gqe_train_steps(const gqe_ctx* ctx, int32_t mode);
+
 /* ---- GraphSAGE-style encoder (the --depth > 0 path; reference netquery/encoders.py:47-129,
  *      netquery/aggregators.py:17-68, built by netquery/utils.py:93-126) ---------------------
  * MeanAggregator.forward after its neighbour sampling: out[i, :] = mean of src[cols[j], :] over

@@ -70,8 +70,8 @@ def test_segment_mean_and_linear_calls():
     ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     cols = rng.randint(0, 500, size=int(ptr[-1])).astype(np.int32)
     out = torch.empty(300, 256, device="cuda")
-    ctx.segment_mean_device(src.data_ptr(), 500, 256, 300, torch.from_numpy(ptr).cuda().data_ptr(),
-                            torch.from_numpy(cols).cuda().data_ptr(), out.data_ptr())
+    d_ptr, d_cols = torch.from_numpy(ptr).cuda(), torch.from_numpy(cols).cuda()     # (kept alive across the launch)
+    ctx.segment_mean_device(src.data_ptr(), 500, 256, 300, d_ptr.data_ptr(), d_cols.data_ptr(), out.data_ptr())
     want = torch.stack([src[torch.from_numpy(cols[ptr[i]:ptr[i + 1]]).long().cuda()].mean(0) for i in range(300)])
     assert float((out - want).abs().max()) < 1e-6
     w, x = torch.randn(96, 200, device="cuda"), torch.randn(200, 77, device="cuda")
@@ -81,8 +81,8 @@ def test_segment_mean_and_linear_calls():
     assert float((y - torch.relu(w.double().mm(x.double())).float()).abs().max()) < 1e-4
     # a column outside the source is reported like every other bad row index
     bad = torch.tensor([0, 700], dtype=torch.int32, device="cuda")
-    ctx.segment_mean_device(src.data_ptr(), 500, 256, 1, torch.tensor([0, 2], device="cuda").data_ptr(), bad.data_ptr(),
-                            out.data_ptr())
+    one = torch.tensor([0, 2], dtype=torch.int64, device="cuda")
+    ctx.segment_mean_device(src.data_ptr(), 500, 256, 1, one.data_ptr(), bad.data_ptr(), out.data_ptr())
     with pytest.raises(IndexError):
         ctx.index_error()
 

@@ -147,3 +147,60 @@ def test_catch_up_alone_equals_zero_gradient_adam_steps():
     st = opt.state[ref]
     np.testing.assert_allclose(m.cpu().numpy(), st["exp_avg"].cpu().numpy(), rtol=1e-4, atol=1e-9)
     np.testing.assert_allclose(v.cpu().numpy(), st["exp_avg_sq"].cpu().numpy(), rtol=1e-4, atol=1e-12)
+
+
+@pytest.mark.parametrize("decoder,inter,d", [("bilinear", "mean", 128), ("transe", "min-simple", 64),
+                                             ("bilinear-diag", "min", 32), ("bilinear", "min-simple", 32)])
+def test_native_train_step_matches_dense_adam(decoder, inter, d):
+    """gqe_train_step_nodes_host (NativeAdam.step: forward + backward + Adam in one native call)
+    against the reference's loop body run through autograd + torch.optim.Adam: the same loss at
+    every step, the same tables and operator parameters after 14 steps over all 7 structures."""
+    case = make_case(seed=4, d=d, decoder=decoder, inter=inter, n_queries=160, n_neg=3, nodes_per_mode=400)
+    dense_model = build_package_model(case)
+    native_model = copy.deepcopy(dense_model)
+    dense_opt = torch.optim.Adam(dense_model.parameters(), lr=0.01)
+    native_opt = gqe.NativeAdam(native_model, lr=0.01)
+    order = ["1-chain", "3-inter", "2-chain", "3-inter_chain", "1-chain", "2-inter", "3-chain_inter", "3-chain",
+             "1-chain", "3-inter", "2-inter", "1-chain", "3-inter_chain", "2-chain"]
+    for it, s in enumerate(order):
+        f = case.formula(s, cls=gqe.Formula)
+        qs = case.queries(s, cls=gqe.Query)
+        lo = (it * 37) % 100
+        batch = qs[lo:lo + 48]
+        hard = "inter" in s and it % 2 == 1
+        random.seed(1000 + it)
+        dense_opt.zero_grad()
+        loss = dense_model.margin_loss(f, batch, hard_negatives=hard)
+        loss.backward()
+        dense_opt.step()
+        random.seed(1000 + it)
+        got = native_opt.step(f, batch, hard_negatives=hard)
+        assert abs(loss.item() - got) <= 2e-5 * max(1.0, abs(got)), (it, s, loss.item(), got)
+    ctx = native_model.context()
+    assert sum(ctx.train_steps(i) for i in range(len(case.kg.modes))) > 0
+    native_opt.flush()
+    torch.cuda.synchronize()
+    for m in case.kg.modes:
+        a, b = dense_model.enc.table(m).detach(), native_model.enc.table(m).detach()
+        assert torch.isfinite(b).all()
+        close = torch.isclose(b, a, rtol=1e-3, atol=1e-5)
+        assert close.float().mean().item() > 0.99, m          # (see test_sparse_row_adam_matches_dense_adam)
+        assert (a - b).abs().max().item() < 0.01 * len(order), m
+        assert (a - case.tables[m].to(a.device)).abs().max().item() > 1e-3, "the tables did not train"
+    for (na, pa), (nb, pb) in zip(dense_model.named_parameters(), native_model.named_parameters()):
+        if "feat-" not in na:
+            np.testing.assert_allclose(pb.detach().cpu().numpy(), pa.detach().cpu().numpy(), rtol=2e-3, atol=2e-5, err_msg=na)
+    # the fused scoring path sees the updated operators (its packed-weight cache was dropped)
+    f = case.formula("2-inter", cls=gqe.Formula)
+    with torch.no_grad():
+        random.seed(7)
+        la = dense_model.margin_loss(f, case.queries("2-inter", cls=gqe.Query)).item()
+        random.seed(7)
+        lb = native_model.margin_loss(f, case.queries("2-inter", cls=gqe.Query)).item()
+    assert abs(la - lb) < 1e-4
+    # a node id that is not in the graph: reported like every other call
+    bad = case.queries("1-chain", cls=gqe.Query)[:8]
+    bad[3].anchor_nodes = (10 ** 8,)
+    with pytest.raises((KeyError, IndexError)):
+        native_opt.step(case.formula("1-chain", cls=gqe.Formula), bad)
+    native_opt.reset()
