@@ -1084,6 +1084,7 @@ extern "C" int gqe_adam_rows_device(gqe_ctx* c, float* table, float* exp_avg, fl
                                     int32_t step, float lr, float beta1, float beta2, float eps) {
   if (!c) return GQE_ERR_INVALID;
   if (n < 0 || table_rows <= 0 || d <= 0 || step < 0) return fail(c, GQE_ERR_INVALID, "gqe_adam_rows_device: bad size");
+  if (d > 256) return fail(c, GQE_ERR_UNSUPPORTED, "gqe_adam_rows_device: d = %d > 256", d);
   if (n == 0) return GQE_OK;
   if (!table || !exp_avg || !exp_avg_sq || !last_step) return fail(c, GQE_ERR_INVALID, "gqe_adam_rows_device: null argument");
   if (grad_rows && !rows) return fail(c, GQE_ERR_INVALID, "gqe_adam_rows_device: gradient rows need their row indices");

@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
+
 #include "gqe_launch.h"
 
 namespace gqe {
@@ -64,33 +66,53 @@ __global__ void __launch_bounds__(256) k_encode_bwd_rows(const float* __restrict
 
 struct AdamHyper {
   float lr, beta1, beta2, eps;
+  float bc1, bc2s;   // bias corrections of the step being applied: 1 - beta1^step, sqrt(1 - beta2^step) (host, double)
 };
 
-// zero-gradient Adam steps (from, to] of one row (lane-strided over d)
+// zero-gradient Adam steps (from, to] of one row (lane-strided over d <= 256).
+// 1 - beta^s is carried as om <- om * beta + (1 - beta) (no cancellation: ~1e-7 relative in fp32; the
+// start value comes from one double pow per row), so the per-step work is fp32 only -- the first
+// version walked beta^s in double per element, ~30x the cost on this part's fp64 rate.
 __device__ __forceinline__ void adam_catch_up(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int d,
                                               int lane, int from, int to, const AdamHyper h) {
   if (to <= from) return;
+  constexpr int kMaxPer = 8;                        // d <= 256
   const int exact = min(to - from, kExactSteps);
-  for (int k = lane; k < d; k += 32) {
-    float pm = m[k], pv = v[k], pp = p[k];
-    if (pm != 0.f || pv != 0.f) {
-      double b1p = pow((double)h.beta1, (double)from), b2p = pow((double)h.beta2, (double)from);
-      for (int s = 0; s < exact; ++s) {
-        b1p *= (double)h.beta1;
-        b2p *= (double)h.beta2;
-        pm *= h.beta1;
-        pv *= h.beta2;
-        const float step = h.lr / (float)(1.0 - b1p);
-        const float denom = sqrtf(pv) / sqrtf((float)(1.0 - b2p)) + h.eps;
-        pp -= step * (pm / denom);
-      }
-      const int rest = to - from - exact;
-      if (rest > 0) {
-        pm *= powf(h.beta1, (float)rest);
-        pv *= powf(h.beta2, (float)rest);
-      }
-      m[k] = pm; v[k] = pv; p[k] = pp;
+  float om1 = 0.f, om2 = 0.f;
+  if (lane == 0) om1 = (float)(1.0 - pow((double)h.beta1, (double)from));
+  if (lane == 1) om2 = (float)(1.0 - pow((double)h.beta2, (double)from));
+  om1 = __shfl_sync(0xffffffffu, om1, 0);
+  om2 = __shfl_sync(0xffffffffu, om2, 1);
+  float pm[kMaxPer], pv[kMaxPer], pp[kMaxPer];
+  bool live = false;
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    const int k = lane + 32 * j;
+    pm[j] = k < d ? m[k] : 0.f;
+    pv[j] = k < d ? v[k] : 0.f;
+    pp[j] = k < d ? p[k] : 0.f;
+    live = live || pm[j] != 0.f || pv[j] != 0.f;
+  }
+  if (!__any_sync(0xffffffffu, live)) return;       // never touched: m = v = 0, nothing moves
+  const float c1 = 1.f - h.beta1, c2 = 1.f - h.beta2;
+  for (int s = 0; s < exact; ++s) {
+    om1 = fmaf(om1, h.beta1, c1);
+    om2 = fmaf(om2, h.beta2, c2);
+    const float step = h.lr / om1;
+    const float inv_bc2s = rsqrtf(om2);
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {
+      pm[j] *= h.beta1;
+      pv[j] *= h.beta2;
+      pp[j] -= step * (pm[j] / (sqrtf(pv[j]) * inv_bc2s + h.eps));
     }
+  }
+  const int rest = to - from - exact;
+  const float r1 = rest > 0 ? powf(h.beta1, (float)rest) : 1.f, r2 = rest > 0 ? powf(h.beta2, (float)rest) : 1.f;
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    const int k = lane + 32 * j;
+    if (k < d) { m[k] = pm[j] * r1; v[k] = pv[j] * r2; p[k] = pp[j]; }
   }
 }
 
@@ -132,8 +154,7 @@ __global__ void __launch_bounds__(256) k_adam_rows(float* __restrict__ table, fl
     if (!mine) continue;                       // another warp of this launch owns the row
     if (from < target && from > 0) adam_catch_up(p, pm, pv, d, lane, from, target, h);
     if (grads) {
-      const float bc1 = (float)(1.0 - pow((double)h.beta1, (double)step));
-      const float bc2s = sqrtf((float)(1.0 - pow((double)h.beta2, (double)step)));
+      const float bc1 = h.bc1, bc2s = h.bc2s;
       float* g = grads + (size_t)(GSUM ? row : i) * d;
       for (int k = lane; k < d; k += 32) {
         const float gk = g[k];
@@ -156,8 +177,7 @@ __global__ void __launch_bounds__(256) k_adam_rows(float* __restrict__ table, fl
 // torch.optim.Adam on a small dense parameter (relation matrices / vectors, DeepSets pre / post)
 __global__ void __launch_bounds__(256) k_adam_dense(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                     const float* __restrict__ g, int64_t n, int step, const AdamHyper h) {
-  const float bc1 = (float)(1.0 - pow((double)h.beta1, (double)step));
-  const float bc2s = sqrtf((float)(1.0 - pow((double)h.beta2, (double)step)));
+  const float bc1 = h.bc1, bc2s = h.bc2s;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gk = g[i];
     const float mk = m[i] + (gk - m[i]) * (1.f - h.beta1);
@@ -166,6 +186,15 @@ __global__ void __launch_bounds__(256) k_adam_dense(float* __restrict__ p, float
     v[i] = vk;
     p[i] -= (h.lr / bc1) * (mk / (sqrtf(vk) / bc2s + h.eps));
   }
+}
+
+AdamHyper make_hyper(float lr, float beta1, float beta2, float eps, int step) {
+  AdamHyper h{lr, beta1, beta2, eps, 1.f, 1.f};
+  if (step > 0) {
+    h.bc1 = (float)(1.0 - std::pow((double)beta1, (double)step));
+    h.bc2s = std::sqrt((float)(1.0 - std::pow((double)beta2, (double)step)));
+  }
+  return h;
 }
 
 int opt_grid(int64_t warps_wanted) {
@@ -189,7 +218,7 @@ cudaError_t launch_adam_rows(float* table, float* m, float* v, int32_t* last, in
                              const int64_t* rows, const float* grads, int step, float lr, float beta1, float beta2,
                              float eps, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  AdamHyper h{lr, beta1, beta2, eps};
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, step);
   k_adam_rows<int64_t, false><<<opt_grid(n), 256, 0, st>>>(table, m, v, last, table_rows, d, n, rows, const_cast<float*>(grads), step, h);
   return cudaGetLastError();
 }
@@ -198,7 +227,7 @@ cudaError_t launch_adam_rows_accum(float* table, float* m, float* v, int32_t* la
                                    const int32_t* rows, float* gsum, int step, float lr, float beta1, float beta2, float eps,
                                    cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  AdamHyper h{lr, beta1, beta2, eps};
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, step);
   if (gsum) k_adam_rows<int32_t, true><<<opt_grid(n), 256, 0, st>>>(table, m, v, last, table_rows, d, n, rows, gsum, step, h);
   else k_adam_rows<int32_t, false><<<opt_grid(n), 256, 0, st>>>(table, m, v, last, table_rows, d, n, rows, nullptr, step, h);
   return cudaGetLastError();
@@ -207,7 +236,7 @@ cudaError_t launch_adam_rows_accum(float* table, float* m, float* v, int32_t* la
 cudaError_t launch_adam_dense(float* p, float* m, float* v, const float* g, int64_t n, int step, float lr, float beta1,
                               float beta2, float eps, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  AdamHyper h{lr, beta1, beta2, eps};
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, step);
   const int64_t blocks = (n + 255) / 256;
   k_adam_dense<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(p, m, v, g, n, step, h);
   return cudaGetLastError();

@@ -109,6 +109,27 @@ __global__ void __launch_bounds__(1024) k_hinge(const float* __restrict__ pos, c
   }
 }
 
+// out[k, c] = in[k, c mod n] for c < 2n: one query side against the positive and the negative targets
+__global__ void __launch_bounds__(256) k_dup(const float* __restrict__ in, float* __restrict__ out, int d, int64_t n) {
+  const int64_t total = (int64_t)d * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / n, c = i - k * n;
+    const float x = in[i];
+    out[k * 2 * n + c] = x;
+    out[k * 2 * n + n + c] = x;
+  }
+}
+// its backward: gin[k, c] (+)= gout[k, c] + gout[k, n + c]
+__global__ void __launch_bounds__(256) k_fold(const float* __restrict__ gout, float* __restrict__ gin, int d, int64_t n,
+                                              int accumulate) {
+  const int64_t total = (int64_t)d * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / n, c = i - k * n;
+    const float g = gout[k * 2 * n + c] + gout[k * 2 * n + n + c];
+    gin[i] = accumulate ? gin[i] + g : g;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_add(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] += src[i];
@@ -130,7 +151,7 @@ struct Tape {
   int64_t launches = 0;
 
   struct Var { float* v; float* g; int64_t n; };   // value [d, n] (scores: [n]), gradient (lazily allocated)
-  enum Kind { ENCODE, MATMUL, VEC, AGG, COS };
+  enum Kind { ENCODE, MATMUL, VEC, AGG, COS, DUP };
   struct Node {
     Kind k;
     int in[3], out;
@@ -214,6 +235,16 @@ struct Tape {
                              vars[out].v, c->stream));
     ++launches;
     nodes.push_back(Node{AGG, {e1, e2, e3}, out, nullptr, relu, use_min, 0, nullptr});
+    return out;
+  }
+  int dup(int x) {     // [d, n] -> [d, 2n], both halves equal
+    const int64_t n = vars[x].n;
+    const int out = new_var(2 * n);
+    if (rc != GQE_OK) return out;
+    k_dup<<<(unsigned)std::min<int64_t>(((int64_t)d * n + 255) / 256, 1184), 256, 0, c->stream>>>(vars[x].v, vars[out].v, d, n);
+    TR_CUDA(cudaGetLastError());
+    ++launches;
+    nodes.push_back(Node{DUP, {x, -1, -1}, out, nullptr, 0, 0, 0, nullptr});
     return out;
   }
   int cosine(int x, int y, int raw) {
@@ -336,6 +367,17 @@ struct Tape {
           accumulate(nd.in[0], g1, f1);
           accumulate(nd.in[1], g2, f2);
           if (nd.in[2] >= 0) accumulate(nd.in[2], g3, f3);
+          break;
+        }
+        case DUP: {
+          Var& x = vars[nd.in[0]];
+          const bool fresh = x.g == nullptr;
+          if (fresh) x.g = take((size_t)d * x.n);
+          if (rc != GQE_OK) break;
+          k_fold<<<(unsigned)std::min<int64_t>(((int64_t)d * x.n + 255) / 256, 1184), 256, 0, c->stream>>>(gout, x.g, d, x.n,
+                                                                                                     fresh ? 0 : 1);
+          TR_CUDA(cudaGetLastError());
+          ++launches;
           break;
         }
         case ENCODE: {
@@ -494,8 +536,8 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
   for (int l = 0; l < kLists; ++l) {
     if (modes[l] < 0) continue;
     gqe_train_state::Table& t = ts->tables[modes[l]];
-    if (t.step <= 0) continue;
-    GQE_CUDA(c, launch_adam_rows_accum(const_cast<float*>(c->tables[modes[l]]), t.m, t.v, t.last, t.rows, c->d, n, rows[l], nullptr,
+    if (t.step <= 0 || l == 4) continue;               // (list 4 = the negatives, adjacent to list 3: one call for both)
+    GQE_CUDA(c, launch_adam_rows_accum(const_cast<float*>(c->tables[modes[l]]), t.m, t.v, t.last, t.rows, c->d, l == 3 ? 2 * n : n, rows[l], nullptr,
                                        (int)t.step, h.lr, h.beta1, h.beta2, h.eps, c->stream));
     c->launches += 1;
   }
@@ -504,14 +546,14 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
   Tape tp;
   tp.c = c; tp.ts = ts; tp.d = c->d;
   auto project = [&](int x, const float* r) { return bilinear ? tp.matmul(r, x, 0) : tp.vec(r, x, mul); };   // decoders.py:150 / 208 / 236
-  int score[2];
+  // the positive and the negative targets form ONE [d, 2n] block (columns [0, n) positive, [n, 2n)
+  // negative: their row lists are adjacent in ts->idx), scored against the duplicated query side
+  int score;
   if (chain) {
-    const int a = tp.encode(modes[0], rows[0], n);
-    for (int t = 0; t < 2; ++t) {
-      int act = tp.encode(modes[3], rows[3 + t], n);
-      for (int k = 0; k < nr; ++k) act = bilinear ? tp.matmul(rel[k], act, 1) : tp.vec(rel[k], act, mul);   // decoders.py:143-145
-      score[t] = tp.cosine(act, a, mul);                                                                    // raw dot for DistMult
-    }
+    const int a2 = tp.dup(tp.encode(modes[0], rows[0], n));
+    int act = tp.encode(modes[3], rows[3], 2 * n);
+    for (int k = 0; k < nr; ++k) act = bilinear ? tp.matmul(rel[k], act, 1) : tp.vec(rel[k], act, mul);   // decoders.py:143-145
+    score = tp.cosine(act, a2, mul);                                                                      // raw dot for DistMult
   } else {
     int e[3] = {-1, -1, -1};
     e[0] = project(tp.encode(modes[0], rows[0], n), rel[0]);
@@ -527,15 +569,15 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
       q = tp.agg(e[0], e[1], e[2], 0, use_min);                              // decoders.py:311-319
     }
     if (st == GQE_CHAIN_INTER3) q = project(q, rel[2]);                      // model.py:107
-    for (int t = 0; t < 2; ++t) score[t] = tp.cosine(tp.encode(modes[3], rows[3 + t], n), q, 0);
+    score = tp.cosine(tp.encode(modes[3], rows[3], 2 * n), tp.dup(q), 0);
   }
   if (tp.rc != GQE_OK) return tp.rc;
 
   // ---- loss and its gradient ------------------------------------------------------------------
-  for (int t = 0; t < 2; ++t) tp.vars[score[t]].g = tp.take((size_t)n);
+  tp.vars[score].g = tp.take((size_t)2 * n);
   if (tp.rc != GQE_OK) return tp.rc;
-  k_hinge<<<1, 1024, 0, c->stream>>>(tp.vars[score[0]].v, tp.vars[score[1]].v, n, margin, tp.vars[score[0]].g,
-                                    tp.vars[score[1]].g, out_loss);
+  k_hinge<<<1, 1024, 0, c->stream>>>(tp.vars[score].v, tp.vars[score].v + n, n, margin, tp.vars[score].g,
+                                    tp.vars[score].g + n, out_loss);
   GQE_CUDA(c, cudaGetLastError());
   c->launches += 1;
 
@@ -551,9 +593,9 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
     if (!t.touched) continue;
     t.touched = false;
     t.step += 1;
-    for (int l = 0; l < kLists; ++l) {
+    for (int l = 0; l < 4; ++l) {
       if (modes[l] != m) continue;
-      GQE_CUDA(c, launch_adam_rows_accum(const_cast<float*>(c->tables[m]), t.m, t.v, t.last, t.rows, c->d, n, rows[l], t.gsum,
+      GQE_CUDA(c, launch_adam_rows_accum(const_cast<float*>(c->tables[m]), t.m, t.v, t.last, t.rows, c->d, l == 3 ? 2 * n : n, rows[l], t.gsum,
                                          (int)t.step, h.lr, h.beta1, h.beta2, h.eps, c->stream));
       c->launches += 1;
     }

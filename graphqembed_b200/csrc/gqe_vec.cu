@@ -14,7 +14,7 @@
 // issues the 128-bit loads of all its rows at once (up to 5 rows x d/64 float4 per lane in
 // flight), keeps everything in registers and reduces with shuffles inside the half.  Blocks walk
 // over groups of 16 consecutive queries of one formula, so the structure branches are uniform;
-// the indices of the next group are fetched (and mapped through the node map) while the rows of
+// the indices of the next groups are fetched (and mapped through the node map) while the rows of
 // the current one are in flight.  Norms and cosines use MUFU.RSQ forms (~2^-22 relative) instead
 // of IEEE sqrt / division, whose checked slow paths cost ~10 instructions each.
 //
@@ -70,11 +70,6 @@ __device__ __forceinline__ float min_nan(float a, float b) {
   asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
-
-#ifndef GQE_VEC_PREFETCH
-#define GQE_VEC_PREFETCH 1
-#endif
-__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 constexpr int kHalf = 16;                 // lanes per query
 constexpr int kQW = 32 / kHalf;           // queries per warp
@@ -242,45 +237,36 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
     if (sl == 8 || sl == 9) return __ldg(p.target_rows + q * T + tslot);
     return 0;
   };
-  // Software pipeline over this block's groups, stage k = the group k iterations ahead:
-  //   3  raw indices fetched        2  node-map lookups issued, and -- at the END of the iteration, when
-  //   they have landed -- the rows' lines requested into L2 (prefetch.global.L2: no registers held)
-  //   1  (in flight)                0  bounds check, row loads (L2 hits by now), arithmetic
-  // so that no dependent load is ever waited for and every row has a whole iteration to come up
-  // from HBM.  (Prefetching right behind the lookup instead stalls the warp on the lookup.)
-  const int64_t G = gridDim.x;
-  Cursor cu[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-  bool in[4];
-  int64_t qq[4];
-  int32_t raw[4], cand[3] = {0, 0, 0};
+  // Three stages, one loop iteration apart, so that no dependent load is ever waited for: the raw
+  // index of group i+2, the node-map lookup of group i+1, the bounds check + row loads of group i.
+  // [Measured, not kept: requesting the NEXT groups' rows into L2 (prefetch.global.L2 right behind
+  // the lookup, or one iteration later with a four-stage pipeline) is 4-8 % slower on both the
+  // 10 GB and the L2-resident tables -- profiles/r02_vec_experiments.md.]
+  Cursor c0{0, 0}, c1{0, 0}, c2{0, 0};
   int64_t g = blockIdx.x;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    in[k] = locate(cu[k], g + k * G);
-    qq[k] = query_of(cu[k], g + k * G, in[k]);
-    raw[k] = in[k] ? fetch_raw(qq[k], p.seg[cu[k].si]) : 0;
+  bool in0 = locate(c0, g), in1 = locate(c1, g + gridDim.x);
+  int64_t q = query_of(c0, g, in0), q1 = query_of(c1, g + gridDim.x, in1);
+  int32_t raw_cur = in0 ? fetch_raw(q, p.seg[c0.si]) : 0, raw_nxt = in1 ? fetch_raw(q1, p.seg[c1.si]) : 0;
+  int32_t cand = 0;
+  if (q >= 0) {
+    const int m = lane_mode(p.seg[c0.si]);
+    if (m >= 0) cand = index_lookup(p.mode[m], raw_cur, ik);
   }
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-    if (qq[k] >= 0) {
-      const int m = lane_mode(p.seg[cu[k].si]);
-      if (m >= 0) cand[k] = index_lookup(p.mode[m], raw[k], ik);
-    }
-  for (; in[0]; g += G) {
-    const SegDev& s = p.seg[cu[0].si];
-    const int64_t q = qq[0];
+  for (; in0; g += gridDim.x) {
+    const SegDev& s = p.seg[c0.si];
     int32_t idx = 0;
     if (q >= 0) {
       const int my_mode = lane_mode(s);
-      if (my_mode >= 0) idx = index_check(p.mode[my_mode], my_mode, cand[0], raw[0], ik, p.err);
+      if (my_mode >= 0) idx = index_check(p.mode[my_mode], my_mode, cand, raw_cur, ik, p.err);
     }
-    in[3] = locate(cu[3], g + 3 * G);
-    qq[3] = query_of(cu[3], g + 3 * G, in[3]);
-    raw[3] = in[3] ? fetch_raw(qq[3], p.seg[cu[3].si]) : 0;
-    int m2 = -1;
-    if (qq[2] >= 0) {
-      m2 = lane_mode(p.seg[cu[2].si]);
-      if (m2 >= 0) cand[2] = index_lookup(p.mode[m2], raw[2], ik);
+    // the later groups' indices travel while this group's rows do
+    const bool in2 = locate(c2, g + 2 * (int64_t)gridDim.x);
+    const int64_t q2 = query_of(c2, g + 2 * (int64_t)gridDim.x, in2);
+    const int32_t raw_nxt2 = in2 ? fetch_raw(q2, p.seg[c2.si]) : 0;
+    int32_t cand_nxt = 0;
+    if (q1 >= 0) {
+      const int m = lane_mode(p.seg[c1.si]);
+      if (m >= 0) cand_nxt = index_lookup(p.mode[m], raw_nxt, ik);
     }
     float sc[2];
     if (s.structure <= GQE_CHAIN3) score_query<D, 1, true>(s, idx, sl, mul, use_min, sc);
@@ -296,23 +282,15 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
         local += (double)(h < 0.f ? 0.f : h);
       }
     }
-    if (GQE_VEC_PREFETCH && m2 >= 0) {
-      // each lane that holds a row index of the group two iterations ahead asks for the D*4/128
-      // lines of its row.  (Not for a peer GPU's shard: see gqe_tc.cuh.)
-      const SegDev& s2 = p.seg[cu[2].si];
-      const bool tgt = sl >= 8;
-      const bool remote = ((s2.remote_mask >> (tgt ? 3 : sl)) & 1u) != 0;
-      if (!remote && (uint32_t)cand[2] < p.mode[m2].rows) {
-        const float* row = (tgt ? s2.tgt_table : s2.anc_table[sl]) + (size_t)cand[2] * D;
-#pragma unroll
-        for (int l = 0; l < D / 32; ++l) prefetch_line(row + 32 * l);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { cu[k] = cu[k + 1]; in[k] = in[k + 1]; qq[k] = qq[k + 1]; raw[k] = raw[k + 1]; }
-    cand[0] = cand[1];
-    cand[1] = cand[2];
-    cand[2] = 0;
+    raw_cur = raw_nxt;
+    raw_nxt = raw_nxt2;
+    cand = cand_nxt;
+    q = q1;
+    q1 = q2;
+    c0 = c1;
+    c1 = c2;
+    in0 = in1;
+    in1 = in2;
   }
 
   if (!p.out_loss) return;
