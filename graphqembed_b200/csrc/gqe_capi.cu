@@ -599,13 +599,18 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
         }
       };
       std::stable_sort(lp.seg, lp.seg + n, [&](const SegDev& a, const SegDev& b) { return cost(a) > cost(b); });
+      // CTA pairs (tc::producer<PAIR>): every segment is padded to an even number of tiles, so that
+      // tiles (2j, 2j+1) always belong to one formula; a padding tile has no rows
+      lp.pair = use_tc ? tc_use_pair(c->d, tiles) : 0;
       int64_t t = 0;
       for (int k = 0; k < n; ++k) {
         const int64_t nq = lp.seg[k].q_end - lp.seg[k].q_begin;
         const int64_t rows = lp.seg[k].structure <= GQE_CHAIN3 ? (target_offsets ? n_pairs : nq * T) : nq;
         lp.seg[k].tile_begin = t;
-        t += (rows + tile_rows - 1) / tile_rows;
+        const int64_t nt = (rows + tile_rows - 1) / tile_rows;
+        t += lp.pair ? ((nt + 1) & ~(int64_t)1) : nt;
       }
+      tiles = t;
     }
     lp.n_segs = n;
     lp.n_tiles = tiles;

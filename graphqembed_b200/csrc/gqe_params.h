@@ -91,6 +91,7 @@ struct LaunchParams {
   int32_t index_kind;           // 0: the index arrays hold table rows, 1: node ids
   unsigned long long* err;      // DEVICE [2]: (kind << 32 | mode, offending value) of the first bad index
   unsigned long long* err_host; // mapped pinned copy written by the last CTA of a *_host call, or null
+  int32_t pair;                 // tensor-core path: launched as clusters of two CTAs (tiles padded to pairs per segment)
   ModeDev mode[kMaxModes];
 };
 constexpr int kPhaseSlots = 32;

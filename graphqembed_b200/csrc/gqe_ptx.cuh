@@ -61,6 +61,32 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// ---- thread-block clusters (CTA pairs that share every weight stage) ----------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the SAME shared-memory offset of every CTA in `cta_mask`, completing `bytes` on the
+// mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                                       uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive, when they retire, on the mbarrier at this offset in every
+// CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // ---- programmatic dependent launch -------------------------------------------------
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the
 // kernel before it in the stream is still running (once every CTA of that kernel has executed

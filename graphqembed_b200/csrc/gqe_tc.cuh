@@ -986,11 +986,21 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 }
 
 // ---- TMA producer + tile scheduler: streams the packed planes of every step's matrix ---
-template <int D, int STRUCT>
+// PAIR (EXPERIMENT, off unless GQE_PAIR=1 is set; measured, not faster -- DESIGN.md 3.1): the CTA is one of
+// a cluster of two that walk the SAME formula's tiles in lockstep (virtual tiles 2j, 2j+1: the host pads
+// every segment to an even tile count, see gqe_capi.cu).  Each CTA fetches HALF of every weight stage and
+// multicasts it into both CTAs' rings (cp.async.bulk ... .multicast::cluster), the MMA issuers release a
+// stage in both CTAs (tcgen05.commit ... .multicast::cluster): the weight stream is read from L2 once per
+// 256 rows instead of once per 128.  Tiles are dealt round-robin (tile + gridDim.x): the pair needs the same
+// sequence in both CTAs.  Result on the benchmark mix: bit-identical scores, 0.146 ms against 0.132 -- the
+// contractions are not bound by the weight stream (halving it changes their duration by < 2 %), and the
+// round-robin deal loses 12 us to imbalance that the dynamic scheduler does not have.
+template <int D, int STRUCT, bool PAIR>
 __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
   uint32_t slot = 0, phase = 0;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
   // tile k of this CTA: the first is blockIdx.x, the rest come from the global counter.
   // Tile k+1 is published while tile k's weights are being streamed, so the workers can
   // prefetch its rows; an id >= n_tiles is the stop marker.
@@ -1007,7 +1017,7 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
   // the workers (tables and indices only) overlap its tail.  Only this thread reads weights.
   ptx::griddep_wait();
   for (uint32_t k = 0; tile < p.n_tiles; ++k) {
-    const int64_t next = (int64_t)gridDim.x + (int64_t)atomicAdd(p.tile_counter, 1u);
+    const int64_t next = PAIR ? tile + (int64_t)gridDim.x : (int64_t)gridDim.x + (int64_t)atomicAdd(p.tile_counter, 1u);
     publish(k + 1, next < p.n_tiles ? next : p.n_tiles);
     const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
     Prog pg;
@@ -1017,10 +1027,17 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
 #pragma unroll 1
       for (int i = 0; i < 2 * C::kKB; ++i) {
         const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
-        ptx::mbar_wait(empty, phase ^ 1);
+        ptx::mbar_wait(empty, phase ^ 1);          // PAIR: released by BOTH CTAs' MMA issuers (the copy lands in both rings)
         ptx::mbar_arrive_expect_tx(full, C::kStageBytes);
-        ptx::tma_bulk_g2s(ptx::smem_u32(smem + C::kOffB + slot * C::kStageBytes), src + (size_t)i * C::kStageBytes,
-                          C::kStageBytes, full);
+        if (PAIR) {
+          constexpr uint32_t kHalf = C::kStageBytes / 2;
+          const uint32_t off = rank * kHalf;
+          ptx::tma_bulk_g2s_multicast(ptx::smem_u32(smem + C::kOffB + slot * C::kStageBytes) + off,
+                                      src + (size_t)i * C::kStageBytes + off, kHalf, full, (uint16_t)3);
+        } else {
+          ptx::tma_bulk_g2s(ptx::smem_u32(smem + C::kOffB + slot * C::kStageBytes), src + (size_t)i * C::kStageBytes,
+                            C::kStageBytes, full);
+        }
         if (++slot == kStages) { slot = 0; phase ^= 1; }
       }
     }
@@ -1029,7 +1046,7 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
 }
 
 // ---- MMA issuer ------------------------------------------------------------------------
-template <int D, int STRUCT>
+template <int D, int STRUCT, bool PAIR>
 __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
@@ -1070,7 +1087,7 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
           for (int k = 0; k < 4; ++k)
             ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_lo + kb * C::kABlockBytes + 32 * k),
                               ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
-          ptx::umma_commit(empty);
+          if (PAIR) ptx::umma_commit_multicast(empty, (uint16_t)3); else ptx::umma_commit(empty);
           if (++slot == kStages) { slot = 0; phase ^= 1; }
         }
         // plane 1: B_lo, used by A_hi
@@ -1083,7 +1100,7 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
           for (int k = 0; k < 4; ++k)
             ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
                               ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
-          ptx::umma_commit(empty);
+          if (PAIR) ptx::umma_commit_multicast(empty, (uint16_t)3); else ptx::umma_commit(empty);
           if (++slot == kStages) { slot = 0; phase ^= 1; }
         }
       }
@@ -1096,7 +1113,7 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
 // STRUCT >= 0: the single-formula kernel of that query structure; STRUCT < 0: the grouped
 // kernel, which looks its tile's structure up at run time (CTA-uniform).  Persistent:
 // launched with min(n_tiles, SMs x CTAs/SM) CTAs.
-template <int D, int STRUCT>
+template <int D, int STRUCT, bool PAIR = false>
 __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fused_tc(const __grid_constant__ LaunchParams p) {
   using C = Cfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1108,7 +1125,7 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(ptx::smem_u32(&ctl->full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&ctl->empty[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ctl->empty[i]), PAIR ? 2 : 1);
     }
     ptx::mbar_init(ptx::smem_u32(&ctl->a_ready), C::kWorkerThreads);
     ptx::mbar_init(ptx::smem_u32(&ctl->acc_full), 1);
@@ -1123,21 +1140,23 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync();   // the partner's barriers exist before anything is sent to them
   ptx::tc_fence_after_sync();
   if (threadIdx.x == 0) cta_stamp(p, 1);
 
   if (wid < C::kWorkerWarps) {
     worker<D, STRUCT>(p, smem, ctl);
   } else if (wid == C::kWorkerWarps) {
-    if (lane == 0) producer<D, STRUCT>(p, smem, ctl);
+    if (lane == 0) producer<D, STRUCT, PAIR>(p, smem, ctl);
     __syncwarp();
   } else {
-    if (lane == 0) mma_issuer<D, STRUCT>(p, smem, ctl);
+    if (lane == 0) mma_issuer<D, STRUCT, PAIR>(p, smem, ctl);
     __syncwarp();
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync();   // no CTA leaves while its partner may still signal its barriers
   if (wid == C::kWorkerWarps + 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(ctl->tmem_base, C::kTmemCols);

@@ -14,6 +14,46 @@ static int tc_current_device() {
   return dev & 63;
 }
 
+// CTA-pair launch: clusters of two, as many as fit the device at once (tiles are dealt round-robin)
+template <int D, int STRUCT>
+static cudaError_t tc_launch_pair(const LaunchParams& lp, int64_t tiles, int slots, cudaStream_t st) {
+  static bool configured[64] = {false};
+  static int clusters[64] = {0};
+  auto kern = tc::gqe_fused_tc<D, STRUCT, true>;
+  const int dev = tc_current_device();
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(tc::Cfg<D>::kThreads);
+  cfg.dynamicSmemBytes = tc::Cfg<D>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int pdl = [] { const char* e = std::getenv("GQE_PDL"); return e ? std::atoi(e) : 1; }();
+  attr[1].val.programmaticStreamSerializationAllowed = pdl;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<D>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    cfg.gridDim = dim3((unsigned)slots);
+    int n = 0;
+    cfg.numAttrs = 1;                       // (the occupancy query looks at the cluster shape only)
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    cfg.numAttrs = 2;
+    if (e != cudaSuccess) return e;
+    if (n <= 0) return cudaErrorInvalidConfiguration;
+    clusters[dev] = n < slots / 2 ? n : slots / 2;
+    configured[dev] = true;
+  }
+  const int64_t pairs = tiles / 2;          // (tiles is even: every segment was padded)
+  const int64_t nc = pairs < clusters[dev] ? pairs : clusters[dev];
+  cfg.gridDim = dim3((unsigned)(2 * nc));
+  return cudaLaunchKernelEx(&cfg, kern, lp);
+}
+
 // Persistent launch: one CTA per SM slot (SMs x CTAs/SM), never more CTAs than tiles.
 template <int D, int STRUCT>
 static cudaError_t tc_launch_one(const LaunchParams& lp, int64_t tiles, cudaStream_t st) {
@@ -30,6 +70,7 @@ static cudaError_t tc_launch_one(const LaunchParams& lp, int64_t tiles, cudaStre
     slots[dev] = sms * tc::Cfg<D>::kCtasPerSm;
     configured[dev] = true;
   }
+  if (lp.pair == 1) return tc_launch_pair<D, STRUCT>(lp, tiles, slots[dev], st);
   const int64_t grid = tiles < slots[dev] ? tiles : slots[dev];
   // programmatic dependent launch on gqe_pack (see tc::producer); GQE_PDL=0 in the environment
   // turns it off (diagnostics: measured 2.6 us per call on the benchmark mix)
@@ -63,6 +104,10 @@ static cudaError_t tc_launch_struct(int structure, const LaunchParams& lp, int64
 
 #if GQE_DIM == 256
 int score_col_src_host(int n) { return tc::score_col_src(n); }
+int tc_use_pair(int d, int64_t tiles) {   // experiment, see tc::producer<PAIR>: only with GQE_PAIR=1 in the environment
+  const char* e = std::getenv("GQE_PAIR");
+  return (e && std::atoi(e) == 1 && d == 256 && tiles >= 2 * 148) ? 1 : 0;
+}
 #endif
 
 #define GQE_CAT2(a, b) a##b

@@ -535,3 +535,34 @@ def test_training_step_with_a_torch_optimiser_reduces_the_loss():
         random.seed(1)
         unfused = model.margin_loss(f, qs).item()
     assert abs(fused - unfused) < 1e-4
+
+
+def test_cta_pair_experiment_bit_identical(monkeypatch):
+    """GQE_PAIR=1: the cluster-of-two kernel that multicasts every weight stage to both CTAs
+    (tc::producer<PAIR>) scores the full-size mix bit-identically to the default kernel."""
+    from graphqembed_b200 import _lib
+    from graphqembed_b200.workloads import make_workload
+    import bench
+    device = torch.device("cuda", 0)
+    wl = make_workload("bio-mix-d256-b65536", seed=3)
+    tables, rels, pre, post = bench.device_parameters(wl, torch, device, seed=99)
+    lookup = gqe.RowLookup(wl.kg.node_ids)
+    mode_ids = {m: i for i, m in enumerate(wl.kg.modes)}
+    rel_ids = {r: i for i, r in enumerate(wl.kg.rel_keys)}
+    segs, a, t = wl.lower(lookup, mode_ids, rel_ids)
+    ctx = gqe.Context(0, torch.cuda.current_stream().cuda_stream)
+    ctx.bind_tables([x.data_ptr() for x in tables], [x.size(0) for x in tables], wl.d)
+    ctx.bind_relations(_lib.DECODER_ID[wl.decoder], [r.data_ptr() for r in rels], wl.d)
+    ctx.bind_intersection(_lib.INTER_ID[wl.inter], [p.data_ptr() for p in pre], [p.data_ptr() for p in post], wl.d)
+    da, dt = torch.from_numpy(a).to(device), torch.from_numpy(t).to(device)
+    out = {}
+    for pair in ("0", "1"):
+        monkeypatch.setenv("GQE_PAIR", pair)
+        scores = torch.empty(wl.n_queries * 2, device=device)
+        loss = torch.zeros(1, device=device)
+        for _ in range(2):
+            ctx.score_grouped_device(segs, wl.n_queries, da.data_ptr(), dt.data_ptr(), 2, scores.data_ptr(), 1.0, loss.data_ptr())
+        torch.cuda.synchronize()
+        out[pair] = (scores.clone(), float(loss))
+    assert torch.equal(out["0"][0], out["1"][0])
+    assert out["0"][1] == out["1"][1]
