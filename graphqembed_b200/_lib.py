@@ -35,7 +35,7 @@ DECODER_ID = {"bilinear": 0, "transe": 1, "bilinear-diag": 2}
 INTER_ID = {"mean": 0, "min": 1, "mean-simple": 2, "min-simple": 3}
 PRECISION_ID = {"bf16x3": 0, "fp32": 1}
 COMPOSE_ID = {"off": 0, "auto": 1, "always": 2}
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 GQE_ERR_INDEX = -6

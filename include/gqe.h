@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GQE_ABI_VERSION 4
+#define GQE_ABI_VERSION 5
 #define GQE_MAX_ANCHORS 3
 #define GQE_MAX_RELS 3
 
