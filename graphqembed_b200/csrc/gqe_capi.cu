@@ -758,6 +758,10 @@ int gqe_stage_reserve(gqe_ctx* c, int slot, size_t bytes) {
   return GQE_OK;
 }
 enum { ST_ANCHOR = 0, ST_TARGET = 1, ST_OFFSETS = 2, ST_SCORES = 3, ST_LOSS = 4 };
+static const size_t kInPlaceIndexBytes = [] {   // GQE_INPLACE_BYTES in the environment overrides (0 = always copy)
+  const char* e = getenv("GQE_INPLACE_BYTES");
+  return e ? (size_t)atoll(e) : (size_t)128 << 10;
+}();
 
 static int max_anchors(const gqe_segment* segs, int n) {
   int m = 0;
@@ -789,7 +793,22 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
     }
     loss_dst = c->h_loss_dev;
   }
-  if (nq > 0) {
+  // Small calls on pinned (mapped) host buffers: the kernels read the indices in place over PCIe.  A
+  // copy operation costs ~8 us of fixed latency, two or three of them are most of a 512-query call
+  // (configs[0]); the in-place reads add one ~2 us round trip to the first tile instead.  Large calls keep
+  // the copies (in place they stall every tile's first gather: profiles/r02_experiments.md).
+  const int32_t *zc_anchor = nullptr, *zc_target = nullptr;
+  if (nq > 0 && anchor_rows && target_rows && !target_offsets &&
+      sizeof(int32_t) * ((size_t)na * nq + (size_t)n_pairs) <= kInPlaceIndexBytes) {
+    cudaPointerAttributes pa, pt;
+    if (cudaPointerGetAttributes(&pa, anchor_rows) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+        cudaPointerGetAttributes(&pt, target_rows) == cudaSuccess && pt.type == cudaMemoryTypeHost && pt.devicePointer) {
+      zc_anchor = (const int32_t*)pa.devicePointer;
+      zc_target = (const int32_t*)pt.devicePointer;
+    }
+    (void)cudaGetLastError();    // (a pageable pointer is an error to the query on some drivers)
+  }
+  if (nq > 0 && !zc_anchor) {
     if (!anchor_rows || !target_rows) return fail(c, GQE_ERR_INVALID, "index arrays are null");
     // in stream order, in front of the kernels: with the packed weights cached there is nothing
     // to overlap the copies with, and a second stream would only add event traffic to the call
@@ -814,7 +833,8 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
   }
   c->h_err[0] = 0ull;
   c->err_posted = false;
-  rc = run_fused(c, segs, n_segs, nq, (const int32_t*)c->stage[ST_ANCHOR], n_pairs, (const int32_t*)c->stage[ST_TARGET],
+  rc = run_fused(c, segs, n_segs, nq, zc_anchor ? zc_anchor : (const int32_t*)c->stage[ST_ANCHOR], n_pairs,
+                 zc_target ? zc_target : (const int32_t*)c->stage[ST_TARGET],
                  target_offsets ? (const int64_t*)c->stage[ST_OFFSETS] : nullptr, T,
                  out_scores ? (float*)c->stage[ST_SCORES] : nullptr, margin, loss_dst, index_kind, c->h_err_dev);
   if (rc != GQE_OK) return rc;
