@@ -490,6 +490,19 @@ def measure_python_surface(args, tm, res, steps=20):
         step_store()
         model.context().index_error()
     store_ms = (time.perf_counter() - t0) * 1e3 / steps
+
+    def step_mix():
+        with torch.no_grad():
+            return float(model.margin_loss_mix([(blk.formula, blk.all()) for blk in blocks]))
+    for _ in range(3):
+        step_mix()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tm.flush.zero_()
+        step_mix()
+        model.context().index_error()
+    mix_ms = (time.perf_counter() - t0) * 1e3 / steps
     # lists of Query objects
     qlists = []
     for blk in blocks:
@@ -510,6 +523,10 @@ def measure_python_surface(args, tm, res, steps=20):
     return {"from_store": {"value": round(wl.n_queries / (store_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(store_ms, 4),
                            "call": "QueryEncoderDecoder.margin_loss(formula, StoreSlice) x %d formulas: vectorised negative "
                                    "draw + pinned H2D of node ids + fused kernel + loss read" % len(blocks)},
+            "from_store_one_call": {"value": round(wl.n_queries / (mix_ms * 1e-3), 1), "unit": UNIT,
+                                    "ms_per_step": round(mix_ms, 4),
+                                    "call": "QueryEncoderDecoder.margin_loss_mix([(formula, StoreSlice)] x %d): the same in ONE "
+                                            "grouped launch" % len(blocks)},
             "from_query_objects": {"value": round(wl.n_queries / (obj_ms * 1e-3), 1), "unit": UNIT,
                                    "ms_per_step": round(obj_ms, 4),
                                    "call": "QueryEncoderDecoder.margin_loss(formula, [Query]) x %d formulas: the reference's "

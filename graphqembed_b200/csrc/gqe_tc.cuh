@@ -319,7 +319,7 @@ struct TileRing {  // consumer side of the tile-id ring
 // written to p.partials[tile]; the last CTA to finish adds them up in tile order, so the
 // result does not depend on which CTA ran which tile (model.py:126 mean).
 template <int D>
-__device__ __forceinline__ void loss_finish(const LaunchParams& p, Ctl* ctl, int wid, int lane) {
+__device__ __forceinline__ void loss_finish(const LaunchParams& p, Ctl* ctl, uint8_t* smem, int wid, int lane) {
   using C = Cfg<D>;
   // (launched programmatically dependent on the previous kernel in the stream -- with the weights
   // cached that is the previous call's fused kernel, whose last CTA reset the words read here)
@@ -330,11 +330,21 @@ __device__ __forceinline__ void loss_finish(const LaunchParams& p, Ctl* ctl, int
     ctl->last = (t == gridDim.x - 1);
   }
   ptx::named_bar_sync(1, C::kWorkerThreads);
-  if (ctl->last && wid == 0) {
-    __threadfence();
+  if (!ctl->last) return;
+  __threadfence();
+  // every worker thread of the last CTA fetches its share of the per-tile sums (one or two independent
+  // loads each instead of n_tiles / 32 dependent ones per lane of one warp), fixed assignment and order
+  double* red2 = reinterpret_cast<double*>(smem);   // the A planes are dead by now
+  if (p.out_loss) {
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < p.n_tiles; i += C::kWorkerThreads) s += __ldcg(p.partials + i);
+    red2[threadIdx.x] = s;
+    ptx::named_bar_sync(1, C::kWorkerThreads);
+  }
+  if (wid == 0) {
     if (p.out_loss) {
       double s = 0.0;
-      for (int64_t i = lane; i < p.n_tiles; i += 32) s += __ldcg(p.partials + i);
+      for (int i = lane; i < C::kWorkerThreads; i += 32) s += red2[i];
       s = warp_sum_d(s);
       if (lane == 0) {
         const double acc = *p.loss_acc + s;
@@ -982,7 +992,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 #undef m_a2
   if (pend.valid) score_frag<D>(p, ctl, scratch, tmem_base, pend, wid, lane);  // (never: a deferred tile has a successor)
   if (threadIdx.x == 0) cta_stamp(p, 3);
-  loss_finish<D>(p, ctl, wid, lane);
+  loss_finish<D>(p, ctl, smem, wid, lane);
 }
 
 // ---- TMA producer + tile scheduler: streams the packed planes of every step's matrix ---

@@ -370,6 +370,20 @@ class QueryEncoderDecoder(nn.Module):
         self._check_indices(ctx, nodes)
         return (loss, scores) if return_scores else loss
 
+    def margin_loss_mix(self, items, hard_negatives=False, margin=1):
+        """The margin loss of MANY formulas' batches in one launch: ``items`` = [(formula, StoreSlice)].
+        Negatives are drawn per slice exactly as ``margin_loss(formula, slice)`` draws them; the result is
+        the mean hinge over all queries of all slices (= the size-weighted mean of the per-formula
+        losses).  What a loop over ``margin_loss`` costs per formula -- a host call, an H2D copy, a
+        small kernel, a loss read -- is paid once."""
+        batches = []
+        for formula, sl in items:
+            if "inter" not in formula.query_type and hard_negatives:
+                raise Exception("Hard negative examples can only be used with intersection queries")
+            full = self._full_array(formula.target_mode) if formula.query_type == "1-chain" else None
+            batches.append(sl.margin_batch(sl.draw_negatives(hard_negatives, full, self.negative_rng, self.reference_negatives)))
+        return self.margin_loss_grouped(batches, margin)
+
     def margin_loss_grouped(self, batches, margin=1, return_scores=False):
         """One call for many formulas (the "full mix" workload): mean hinge over
         ALL queries of all batches.  Each batch holds (positive, negative) pairs."""

@@ -125,7 +125,13 @@ class StoreSlice(object):
         if reference_stream:
             pick = np.fromiter((random.randrange(int(k)) for k in lens), dtype=np.int64, count=n)
         else:
-            pick = (rng or _default_rng()).integers(0, lens)
+            # uniform over [0, len_i) per query from ONE block of 32-bit words: (r * len) >> 32 (the
+            # bias, len / 2^32, is far below anything a training run resolves); Generator.integers with
+            # an array of bounds costs 12 ns per element, 0.8 ms for a 65 536-query batch
+            r = (rng or _default_rng()).integers(0, 1 << 32, size=n, dtype=np.uint32)
+            pick = np.multiply(r, lens.astype(np.uint32), dtype=np.uint64)
+            np.right_shift(pick, 32, out=pick)
+            pick = pick.view(np.int64)
         return vals[ptr[:-1] + pick]
 
     def margin_batch(self, negatives):

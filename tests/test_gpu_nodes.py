@@ -244,3 +244,30 @@ def test_store_slice_is_scored_without_query_objects(setup):
     with pytest.raises(Exception):
         model.margin_loss(case.formula("2-chain", cls=gqe.Formula), store[case.formula("2-chain", cls=gqe.Formula)].all(),
                           hard_negatives=True)
+
+
+def test_margin_loss_mix_equals_weighted_per_formula_losses():
+    """margin_loss_mix([(formula, StoreSlice)]): one grouped launch, the same negatives (same Generator
+    state) and the size-weighted mean of the per-formula losses."""
+    from graphqembed_b200.store import QueryStore
+    from graphqembed_b200.synth import SynthKG
+    from helpers import build_package_model
+    from oracle.cases import make_case
+    case = make_case(seed=5, d=128, decoder="bilinear", inter="mean", n_queries=300, n_neg=4, nodes_per_mode=900)
+    model = build_package_model(case)
+    raw = []
+    for s in case.batches:
+        b = case.batches[s]
+        for i in range(len(b["target"])):
+            negs = [int(x) for x in b["negs"][i]]
+            raw.append((SynthKG.query_graph(s, b["rels"], b["target"][i], b["anchors"][:, i]), negs,
+                        negs if "inter" in s else None))
+    store = QueryStore.from_records(raw)
+    items = [(case.formula(s, cls=gqe.Formula), store[case.formula(s, cls=gqe.Formula)].window(0, 100 + 20 * k))
+             for k, s in enumerate(case.batches)]
+    with torch.no_grad():
+        model.negative_rng = np.random.default_rng(42)
+        want = sum(float(model.margin_loss(f, sl)) * len(sl) for f, sl in items) / sum(len(sl) for _, sl in items)
+        model.negative_rng = np.random.default_rng(42)
+        got = float(model.margin_loss_mix(items))
+    assert abs(got - want) < 2e-6, (got, want)
