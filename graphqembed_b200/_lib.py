@@ -135,6 +135,11 @@ _SIGNATURES = {
     "gqe_train_step_nodes_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
     "gqe_train_step_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
     "gqe_train_step_nodes_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
+    "gqe_train_backward_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, C.c_float, _P, _P]),
+    "gqe_train_backward_nodes_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, C.c_float, _P, _P]),
+    "gqe_train_backward_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, C.c_float, _P, _P]),
+    "gqe_train_backward_nodes_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, C.c_float, _P, _P]),
+    "gqe_train_apply": (C.c_int, [_P, _P]),
     "gqe_train_flush": (C.c_int, [_P]),
     "gqe_train_reset": (C.c_int, [_P]),
     "gqe_train_steps": (C.c_int64, [_P, C.c_int32]),
@@ -414,6 +419,17 @@ class Context(object):
         out = C.c_float(0.0)
         self._check(fn(self._h, C.byref(plan), int(n_queries), anchors, pairs, float(margin), C.byref(hyper), C.byref(out)))
         return out.value
+
+    def train_backward_host(self, plan, n_queries, anchors, pairs, margin, weight, hyper, nodes=False):
+        """forward + backward, gradients x weight accumulated, no update; -> the batch's own loss."""
+        fn = self._lib.gqe_train_backward_nodes_host if nodes else self._lib.gqe_train_backward_host
+        out = C.c_float(0.0)
+        self._check(fn(self._h, C.byref(plan), int(n_queries), anchors, pairs, float(margin), float(weight), C.byref(hyper),
+                       C.byref(out)))
+        return out.value
+
+    def train_apply(self, hyper):
+        self._check(self._lib.gqe_train_apply(self._h, C.byref(hyper)))
 
     def train_flush(self):
         self._check(self._lib.gqe_train_flush(self._h))

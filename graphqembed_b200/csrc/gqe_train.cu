@@ -51,8 +51,10 @@ struct gqe_train_state {
   // workspace of one step: [d, n] activations and gradients, bump-allocated
   std::vector<std::pair<float*, size_t>> blocks;   // (base, capacity in floats)
   size_t used = 0;                                 // floats used of blocks.back()
-  int32_t* idx = nullptr;                          // lowered table rows, 5 lists
-  size_t idx_cap = 0;
+  int32_t* idx = nullptr;                          // lowered table rows of the batches since the last apply
+  size_t idx_cap = 0, idx_used = 0;
+  struct Pending { int mode; size_t offset; int64_t count; };
+  std::vector<Pending> pending;                    // row lists whose accumulated gradients wait for the Adam step
   gqe_adam last_hyper{1e-3f, 0.9f, 0.999f, 1e-8f};
 };
 
@@ -81,11 +83,13 @@ __global__ void __launch_bounds__(256) k_lower(const __grid_constant__ LowerPara
 
 // model.py:124-126: loss = mean(clamp(margin - (pos - neg), 0)); d loss / d pos = -[active] / n, d loss / d neg = +[active] / n.
 // One block: the mean is summed in a fixed order (deterministic).
+// `weight` scales the gradient (the reference sums several batches' losses with weights before backward():
+// train_helpers.py:63-75); the loss written is the batch's own, unweighted.
 __global__ void __launch_bounds__(1024) k_hinge(const float* __restrict__ pos, const float* __restrict__ neg, int64_t n,
-                                                float margin, float* __restrict__ gpos, float* __restrict__ gneg,
-                                                float* __restrict__ out_loss) {
+                                                float margin, float weight, float* __restrict__ gpos,
+                                                float* __restrict__ gneg, float* __restrict__ out_loss) {
   __shared__ double red[32];
-  const float inv = 1.f / (float)n;
+  const float inv = weight / (float)n;
   double local = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const float h = margin - (pos[i] - neg[i]);
@@ -427,8 +431,9 @@ int n_rels_of(int structure) {
   }
 }
 
-int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* anchors, const int32_t* pairs, float margin,
-               const gqe_adam* hyper, float* out_loss, int index_kind) {
+// forward + backward of one batch: gradients (scaled by `weight`) are ACCUMULATED in the state
+int train_backward(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* anchors, const int32_t* pairs, float margin,
+                   float weight, const gqe_adam* hyper, float* out_loss, int index_kind) {
   if (!c) return GQE_ERR_INVALID;
   if (!plan || !hyper || !out_loss) return gqe_fail(c, GQE_ERR_INVALID, "gqe_train_step: null argument");
   if (n <= 0) return gqe_fail(c, GQE_ERR_INVALID, "gqe_train_step: empty batch");
@@ -491,15 +496,18 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
     ts->blocks.emplace_back(base, total);
   }
   ts->used = 0;
-  if (ts->idx_cap < (size_t)kLists * n) {
+  if (ts->idx_cap < ts->idx_used + (size_t)kLists * n) {   // (the lists of earlier batches of this step are kept)
     GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t cap = 2 * (ts->idx_used + (size_t)kLists * n);
+    int32_t* grown = nullptr;
+    GQE_CUDA(c, cudaMalloc(&grown, cap * sizeof(int32_t)));
+    if (ts->idx_used) GQE_CUDA(c, cudaMemcpy(grown, ts->idx, ts->idx_used * sizeof(int32_t), cudaMemcpyDeviceToDevice));
     cudaFree(ts->idx);
-    ts->idx = nullptr;
-    ts->idx_cap = 0;
-    const size_t cap = (size_t)kLists * n + (size_t)kLists * n / 2;
-    GQE_CUDA(c, cudaMalloc(&ts->idx, cap * sizeof(int32_t)));
+    ts->idx = grown;
     ts->idx_cap = cap;
   }
+  const size_t idx0 = ts->idx_used;
+  ts->idx_used += (size_t)kLists * n;
   for (int l = 0; l < kLists; ++l)
     if (modes[l] >= 0) {
       int rc = ensure_table_state(c, ts, modes[l]);
@@ -511,7 +519,7 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
   LowerParams lw;
   std::memset(&lw, 0, sizeof lw);
   for (int l = 0; l < kLists; ++l) {
-    rows[l] = ts->idx + (size_t)l * n;
+    rows[l] = ts->idx + idx0 + (size_t)l * n;
     if (modes[l] < 0) continue;
     const bool tgt = l >= 3;
     lw.src[l] = tgt ? pairs : anchors + (size_t)l * n;
@@ -576,7 +584,7 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
   // ---- loss and its gradient ------------------------------------------------------------------
   tp.vars[score].g = tp.take((size_t)2 * n);
   if (tp.rc != GQE_OK) return tp.rc;
-  k_hinge<<<1, 1024, 0, c->stream>>>(tp.vars[score].v, tp.vars[score].v + n, n, margin, tp.vars[score].g,
+  k_hinge<<<1, 1024, 0, c->stream>>>(tp.vars[score].v, tp.vars[score].v + n, n, margin, weight, tp.vars[score].g,
                                     tp.vars[score].g + n, out_loss);
   GQE_CUDA(c, cudaGetLastError());
   c->launches += 1;
@@ -587,19 +595,35 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
   c->launches += tp.launches;
   if (tp.rc != GQE_OK) return tp.rc;
 
-  // ---- Adam -------------------------------------------------------------------------------------
+  // the rows whose gradients now sit in the accumulation buffers
+  for (int l = 0; l < 4; ++l)
+    if (modes[l] >= 0) ts->pending.push_back(gqe_train_state::Pending{modes[l], idx0 + (size_t)l * n, l == 3 ? 2 * n : n});
+  return GQE_OK;
+}
+
+// Adam on everything that received a gradient since the last apply
+int train_apply(gqe_ctx* c, const gqe_adam* hyper) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!hyper) return gqe_fail(c, GQE_ERR_INVALID, "gqe_train_apply: null argument");
+  if (!c->train) return GQE_OK;
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  gqe_train_state* ts = c->train;
+  ts->last_hyper = *hyper;
+  const gqe_adam& h = *hyper;
   for (int m = 0; m < (int)ts->tables.size(); ++m) {
     gqe_train_state::Table& t = ts->tables[m];
     if (!t.touched) continue;
     t.touched = false;
     t.step += 1;
-    for (int l = 0; l < 4; ++l) {
-      if (modes[l] != m) continue;
-      GQE_CUDA(c, launch_adam_rows_accum(const_cast<float*>(c->tables[m]), t.m, t.v, t.last, t.rows, c->d, l == 3 ? 2 * n : n, rows[l], t.gsum,
-                                         (int)t.step, h.lr, h.beta1, h.beta2, h.eps, c->stream));
+    for (const auto& pr : ts->pending) {
+      if (pr.mode != m) continue;
+      GQE_CUDA(c, launch_adam_rows_accum(const_cast<float*>(c->tables[m]), t.m, t.v, t.last, t.rows, c->d, pr.count,
+                                         ts->idx + pr.offset, t.gsum, (int)t.step, h.lr, h.beta1, h.beta2, h.eps, c->stream));
       c->launches += 1;
     }
   }
+  ts->pending.clear();
+  ts->idx_used = 0;
   for (auto& kv : ts->dense) {
     gqe_train_state::Dense& ds = kv.second;
     if (!ds.touched) continue;
@@ -612,6 +636,14 @@ int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* ancho
   // the operator matrices changed: packed / pre-multiplied images of the tensor-core path are stale
   c->wcache.clear();
   return GQE_OK;
+}
+
+int train_step(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* anchors, const int32_t* pairs, float margin,
+               const gqe_adam* hyper, float* out_loss, int index_kind) {
+  if (c && c->train && !c->train->pending.empty())
+    return gqe_fail(c, GQE_ERR_INVALID, "gqe_train_step: gradients of gqe_train_backward calls are pending; call gqe_train_apply first");
+  int rc = train_backward(c, plan, n, anchors, pairs, margin, 1.f, hyper, out_loss, index_kind);
+  return rc != GQE_OK ? rc : train_apply(c, hyper);
 }
 
 }  // namespace
@@ -639,7 +671,8 @@ extern "C" int gqe_train_step_nodes_device(gqe_ctx* c, const gqe_plan* plan, int
 // host index buffers in, host loss out: one H2D copy per array in front, the loss through the mapped
 // pinned word, the index-error word fetched with it
 static int train_step_host(gqe_ctx* c, const gqe_plan* plan, int64_t n, const int32_t* anchors, const int32_t* pairs,
-                           float margin, const gqe_adam* hyper, float* out_loss, int index_kind) {
+                           float margin, const gqe_adam* hyper, float* out_loss, int index_kind, bool apply = true,
+                           float weight = 1.f) {
   if (!c) return GQE_ERR_INVALID;
   if (!plan || !hyper || !out_loss || !anchors || !pairs) return gqe_fail(c, GQE_ERR_INVALID, "gqe_train_step_host: null argument");
   if (n <= 0) return gqe_fail(c, GQE_ERR_INVALID, "gqe_train_step_host: empty batch");
@@ -655,7 +688,9 @@ static int train_step_host(gqe_ctx* c, const gqe_plan* plan, int64_t n, const in
   }
   GQE_CUDA(c, cudaMemcpyAsync(c->stage[0], anchors, sizeof(int32_t) * (size_t)na * n, cudaMemcpyHostToDevice, c->stream));
   GQE_CUDA(c, cudaMemcpyAsync(c->stage[1], pairs, sizeof(int32_t) * (size_t)2 * n, cudaMemcpyHostToDevice, c->stream));
-  rc = train_step(c, plan, n, (const int32_t*)c->stage[0], (const int32_t*)c->stage[1], margin, hyper, c->h_loss_dev, index_kind);
+  rc = apply ? train_step(c, plan, n, (const int32_t*)c->stage[0], (const int32_t*)c->stage[1], margin, hyper, c->h_loss_dev, index_kind)
+             : train_backward(c, plan, n, (const int32_t*)c->stage[0], (const int32_t*)c->stage[1], margin, weight, hyper,
+                              c->h_loss_dev, index_kind);
   if (rc != GQE_OK) return rc;
   GQE_CUDA(c, cudaMemcpyAsync(c->h_err, c->d_err, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   GQE_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -675,6 +710,30 @@ extern "C" int gqe_train_step_nodes_host(gqe_ctx* c, const gqe_plan* plan, int64
                                          const int32_t* pair_nodes, float margin, const gqe_adam* hyper, float* out_loss) {
   return train_step_host(c, plan, n_queries, anchor_nodes, pair_nodes, margin, hyper, out_loss, 1);
 }
+
+// gradient accumulation over several batches, then one Adam step (the reference's loop sums weighted losses
+// of several query types before backward(): train_helpers.py:63-79)
+extern "C" int gqe_train_backward_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                                         const int32_t* pair_rows, float margin, float weight, const gqe_adam* hyper,
+                                         float* out_loss) {
+  return train_backward(c, plan, n_queries, anchor_rows, pair_rows, margin, weight, hyper, out_loss, 0);
+}
+extern "C" int gqe_train_backward_nodes_device(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_nodes,
+                                               const int32_t* pair_nodes, float margin, float weight, const gqe_adam* hyper,
+                                               float* out_loss) {
+  return train_backward(c, plan, n_queries, anchor_nodes, pair_nodes, margin, weight, hyper, out_loss, 1);
+}
+extern "C" int gqe_train_backward_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                                       const int32_t* pair_rows, float margin, float weight, const gqe_adam* hyper,
+                                       float* out_loss) {
+  return train_step_host(c, plan, n_queries, anchor_rows, pair_rows, margin, hyper, out_loss, 0, false, weight);
+}
+extern "C" int gqe_train_backward_nodes_host(gqe_ctx* c, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_nodes,
+                                             const int32_t* pair_nodes, float margin, float weight, const gqe_adam* hyper,
+                                             float* out_loss) {
+  return train_step_host(c, plan, n_queries, anchor_nodes, pair_nodes, margin, hyper, out_loss, 1, false, weight);
+}
+extern "C" int gqe_train_apply(gqe_ctx* c, const gqe_adam* hyper) { return train_apply(c, hyper); }
 
 extern "C" int gqe_train_flush(gqe_ctx* c) {
   if (!c) return GQE_ERR_INVALID;

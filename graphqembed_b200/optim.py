@@ -55,6 +55,26 @@ class NativeAdam(object):
 
     def step(self, formula, queries, hard_negatives=False, margin=1):
         """-> the batch's margin loss before the update (Python float)."""
+        return self._run(formula, queries, hard_negatives, margin, None)
+
+    def backward(self, formula, queries, hard_negatives=False, weight=1.0, margin=1):
+        """Forward + backward of one batch, its gradients times ``weight`` ACCUMULATED on top of earlier
+        ``backward`` calls, no update; -> the batch's own (unweighted) loss.  With ``apply()`` this is the
+        reference's multi-task iteration (train_helpers.py:63-79):
+
+            loss = opt.backward(f_edge, edge_batch)                                  # run_batch(train_queries["1-chain"], ...)
+            loss += path_weight * opt.backward(f_path, path_batch, weight=path_weight)
+            loss += inter_weight * opt.backward(f_int, int_batch, weight=inter_weight)
+            loss += inter_weight * opt.backward(f_int, int_batch, hard_negatives=True, weight=inter_weight)
+            opt.apply()                                                              # loss.backward(); optimizer.step()
+        """
+        return self._run(formula, queries, hard_negatives, margin, float(weight))
+
+    def apply(self):
+        """One Adam step on everything that received a gradient since the last ``apply`` / ``step``."""
+        self.model.context().train_apply(self.hyper)
+
+    def _run(self, formula, queries, hard_negatives, margin, weight):
         m = self.model
         ctx = m.context()
         if isinstance(queries, StoreSlice):
@@ -82,8 +102,9 @@ class NativeAdam(object):
         view[:na * n] = np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
         view[na * n:na * n + 2 * n] = np.ascontiguousarray(t, dtype=np.int32).reshape(-1)
         base = pin.data_ptr()
-        loss = ctx.train_step_host(m.plan(formula), n, base, base + 4 * na * n, margin, self.hyper, nodes=nodes)
-        return loss
+        if weight is None:
+            return ctx.train_step_host(m.plan(formula), n, base, base + 4 * na * n, margin, self.hyper, nodes=nodes)
+        return ctx.train_backward_host(m.plan(formula), n, base, base + 4 * na * n, margin, weight, self.hyper, nodes=nodes)
 
     def flush(self):
         self.model.context().train_flush()

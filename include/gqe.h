@@ -405,6 +405,23 @@ int gqe_train_step_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, c
                         const int32_t* pair_rows, float margin, const gqe_adam* hyper, float* out_loss);
 int gqe_train_step_nodes_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_nodes,
                               const int32_t* pair_nodes, float margin, const gqe_adam* hyper, float* out_loss);
+/* The reference's loop sums the weighted losses of several batches before ONE backward() / optimizer.step()
+ * (netquery/train_helpers.py:63-79: the edge batch, plus path_weight / inter_weight times the other query
+ * types, intersections also with hard negatives).  gqe_train_backward_*: forward + backward of one batch, the
+ * gradients SCALED BY `weight` accumulated on top of those of earlier calls, no update (out_loss: the batch's own,
+ * unweighted loss); gqe_train_apply: the Adam step on every parameter and table row that received a gradient
+ * since the last apply.  gqe_train_step_* == gqe_train_backward_*(weight 1) + gqe_train_apply. */
+int gqe_train_backward_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                              const int32_t* pair_rows, float margin, float weight, const gqe_adam* hyper, float* out_loss);
+int gqe_train_backward_nodes_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_nodes,
+                                    const int32_t* pair_nodes, float margin, float weight, const gqe_adam* hyper,
+                                    float* out_loss);
+int gqe_train_backward_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_rows,
+                            const int32_t* pair_rows, float margin, float weight, const gqe_adam* hyper, float* out_loss);
+int gqe_train_backward_nodes_host(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries, const int32_t* anchor_nodes,
+                                  const int32_t* pair_nodes, float margin, float weight, const gqe_adam* hyper,
+                                  float* out_loss);
+int gqe_train_apply(gqe_ctx* ctx, const gqe_adam* hyper);
 /* every row of every trained table up to date (the zero-gradient steps it still owes) */
 int gqe_train_flush(gqe_ctx* ctx);
 /* forget the optimiser state (moments, step counters); the parameters keep their values */

@@ -208,3 +208,53 @@ def test_native_train_step_matches_dense_adam(decoder, inter, d):
     with pytest.raises((KeyError, IndexError)):
         native_opt.step(case.formula("1-chain", cls=gqe.Formula), bad)
     native_opt.reset()
+
+
+def test_native_multitask_iteration_matches_weighted_loss_backward():
+    """The reference's multi-task iteration (train_helpers.py:63-79): the edge batch plus path_weight /
+    inter_weight times other query types (intersections also with hard negatives), ONE backward() and
+    ONE optimizer.step().  NativeAdam.backward(weight=...) x k + apply() against autograd + optim.Adam."""
+    case = make_case(seed=6, d=64, decoder="bilinear", inter="mean", n_queries=120, n_neg=3, nodes_per_mode=300)
+    dense_model = build_package_model(case)
+    native_model = copy.deepcopy(dense_model)
+    dense_opt = torch.optim.Adam(dense_model.parameters(), lr=0.01)
+    native_opt = gqe.NativeAdam(native_model, lr=0.01)
+    plan = [("1-chain", False, 1.0), ("2-chain", False, 0.01), ("3-chain", False, 0.01), ("2-inter", False, 0.005),
+            ("2-inter", True, 0.005), ("3-inter_chain", False, 0.005), ("3-inter_chain", True, 0.005)]
+    for it in range(5):
+        random.seed(50 + it)
+        dense_opt.zero_grad()
+        total = 0.0
+        parts = []
+        for s, hard, w in plan:
+            f, qs = case.formula(s, cls=gqe.Formula), case.queries(s, cls=gqe.Query)
+            l = dense_model.margin_loss(f, qs[it * 10:it * 10 + 40], hard_negatives=hard)
+            parts.append(float(l))
+            total = total + w * l
+        total.backward()
+        dense_opt.step()
+        random.seed(50 + it)
+        got = []
+        for s, hard, w in plan:
+            f, qs = case.formula(s, cls=gqe.Formula), case.queries(s, cls=gqe.Query)
+            got.append(native_opt.backward(f, qs[it * 10:it * 10 + 40], hard_negatives=hard, weight=w))
+        native_opt.apply()
+        np.testing.assert_allclose(got, parts, rtol=2e-5, atol=2e-6)
+    f, qs = case.formula("1-chain", cls=gqe.Formula), case.queries("1-chain", cls=gqe.Query)
+    random.seed(99)
+    native_opt.backward(f, qs[:8])
+    with pytest.raises(gqe.GqeError):          # a pending backward blocks the one-call step
+        native_opt.step(f, qs[:8])
+    native_opt.apply()
+    random.seed(99)                            # (the dense model takes the same extra step)
+    dense_opt.zero_grad()
+    dense_model.margin_loss(f, qs[:8]).backward()
+    dense_opt.step()
+    native_opt.flush()
+    torch.cuda.synchronize()
+    for m in case.kg.modes:
+        a, b = dense_model.enc.table(m).detach(), native_model.enc.table(m).detach()
+        assert torch.isclose(b, a, rtol=1e-3, atol=1e-5).float().mean().item() > 0.99, m
+    for (na, pa), (nb, pb) in zip(dense_model.named_parameters(), native_model.named_parameters()):
+        if "feat-" not in na:
+            assert torch.isclose(pb.detach(), pa.detach(), rtol=2e-3, atol=2e-5).float().mean().item() > 0.995, na
