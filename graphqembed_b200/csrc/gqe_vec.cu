@@ -89,13 +89,18 @@ __device__ __forceinline__ void hsum_n(float (&v)[N]) {
 // registers.  `idx`: sub-lanes 0..NA-1 of each half hold the anchor rows of its query, sub-lanes 8, 9
 // the target rows (9 = 8 when the query has one target).  Returns the half's two scores.
 template <int D, int NA, bool CHAIN>
-__device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int sl, bool mul, bool use_min, float (&sc)[2]) {
+__device__ __forceinline__ void score_query(const SegDev& s, const float (*rel_sm)[D], int32_t idx, int sl, bool mul,
+                                            bool use_min, float (&sc)[2]) {
   constexpr int LANES = D / 4 < kHalf ? D / 4 : kHalf;   // d = 32: the upper sub-lanes idle
   constexpr int NV = D / 4 / LANES;                      // float4 per lane per row
   const bool act = LANES == kHalf || sl < LANES;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto ld = [&](const float* base, int j) {
     return act ? __ldg(reinterpret_cast<const float4*>(base) + sl + LANES * j) : zero4;
+  };
+  // relation vector h of the formula, from the block's shared-memory copy (see the kernel)
+  auto ldr = [&](int h, int j) {
+    return act ? *(reinterpret_cast<const float4*>(rel_sm[h]) + sl + LANES * j) : zero4;
   };
   // ---- all row loads of both queries, back to back
   float4 a[NA][NV], t[2][NV];
@@ -126,7 +131,7 @@ __device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int sl
     for (int j = 0; j < NV; ++j) {
       float4 y0 = scale4(t[0][j], it0), y1 = scale4(t[1][j], it1);
       for (int h = 0; h < hops; ++h) {
-        const float4 v = ld(s.rel[h], j);
+        const float4 v = ldr(h, j);
         y0 = rel4(y0, v, mul);
         y1 = rel4(y1, v, mul);
       }
@@ -160,17 +165,17 @@ __device__ __forceinline__ void score_query(const SegDev& s, int32_t idx, int sl
       for (int b = 0; b < NA; ++b) {
         float4 e = scale4(a[b][j], ib[b]);
         if (NA == 2 && b == 1 && structure == GQE_INTER_CHAIN3) {
-          e = rel4(e, ld(s.rel[1], j), mul);     // reverse(r2b) first (model.py:85)
-          e = rel4(e, ld(s.rel[2], j), mul);     // then reverse(r2a)
+          e = rel4(e, ldr(1, j), mul);     // reverse(r2b) first (model.py:85)
+          e = rel4(e, ldr(2, j), mul);     // then reverse(r2a)
         } else {
-          e = rel4(e, ld(s.rel[b], j), mul);
+          e = rel4(e, ldr(b, j), mul);
         }
         if (b == 0) q = e;
         else if (use_min) q = make_float4(min_nan(q.x, e.x), min_nan(q.y, e.y), min_nan(q.z, e.z), min_nan(q.w, e.w));
         else q = make_float4(q.x + e.x, q.y + e.y, q.z + e.z, q.w + e.w);
       }
       if (!use_min) q = scale4(q, NA == 2 ? 0.5f : 1.f / 3.f);                    // torch.mean over the stack
-      if (NA == 2 && structure == GQE_CHAIN_INTER3) q = rel4(q, ld(s.rel[2], j), mul);   // model.py:107
+      if (NA == 2 && structure == GQE_CHAIN_INTER3) q = rel4(q, ldr(2, j), mul);   // model.py:107
       if (!act) q = zero4;
       r[0] = sq4(q, r[0]);
       r[1] = sq4(t[0][j], r[1]); r[2] = dot4(t[0][j], q, r[2]);
@@ -192,6 +197,11 @@ template <int D>
 __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 : 3)) gqe_fused_vec(const __grid_constant__ LaunchParams p) {
   __shared__ double red[kVecWarps];
   __shared__ int last;
+  // the (<= 3) relation vectors of the formula the block is working on: every query of the formula reads
+  // them in the middle of its dependent arithmetic, where an L1 miss (the streaming rows evict them) was
+  // 12 % of all stall samples; reloaded when the block moves on to another formula
+  __shared__ __align__(16) float rel_sm[GQE_MAX_RELS][D];
+  int rel_of = -1;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int sl = lane & (kHalf - 1);
   const int qslot = wib * kQW + lane / kHalf;     // this half-warp's query inside a group
@@ -268,10 +278,19 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
       const int m = lane_mode(p.seg[c1.si]);
       if (m >= 0) cand_nxt = index_lookup(p.mode[m], raw_nxt, ik);
     }
+    if (rel_of != c0.si) {             // (block-uniform: c0 depends on blockIdx and the loop counter only)
+      __syncthreads();
+      for (int i = threadIdx.x; i < GQE_MAX_RELS * D; i += kVecThreads) {
+        const float* r = s.rel[i / D];
+        rel_sm[i / D][i % D] = r ? __ldg(r + i % D) : 0.f;
+      }
+      __syncthreads();
+      rel_of = c0.si;
+    }
     float sc[2];
-    if (s.structure <= GQE_CHAIN3) score_query<D, 1, true>(s, idx, sl, mul, use_min, sc);
-    else if (s.n_anchor == 2) score_query<D, 2, false>(s, idx, sl, mul, use_min, sc);
-    else score_query<D, 3, false>(s, idx, sl, mul, use_min, sc);
+    if (s.structure <= GQE_CHAIN3) score_query<D, 1, true>(s, rel_sm, idx, sl, mul, use_min, sc);
+    else if (s.n_anchor == 2) score_query<D, 2, false>(s, rel_sm, idx, sl, mul, use_min, sc);
+    else score_query<D, 3, false>(s, rel_sm, idx, sl, mul, use_min, sc);
     if (sl == 0 && q >= 0) {
       if (p.out_scores) {
         p.out_scores[q * T] = sc[0];
