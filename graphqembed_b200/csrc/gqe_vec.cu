@@ -98,6 +98,15 @@ __device__ __forceinline__ void score_query(const SegDev& s, const float (*rel_s
   auto ld = [&](const float* base, int j) {
     return act ? __ldg(reinterpret_cast<const float4*>(base) + sl + LANES * j) : zero4;
   };
+  // table rows are read once: keep them out of L1, so that what IS re-read (relation vectors, node maps) stays
+  auto ldrow = [&](const float* base, int j) {
+    float4 v = zero4;
+    if (act)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "l"(reinterpret_cast<const float4*>(base) + sl + LANES * j));
+    return v;
+  };
   // relation vector h of the formula, from the block's shared-memory copy (see the kernel)
   auto ldr = [&](int h, int j) {
     return act ? *(reinterpret_cast<const float4*>(rel_sm[h]) + sl + LANES * j) : zero4;
@@ -108,13 +117,13 @@ __device__ __forceinline__ void score_query(const SegDev& s, const float (*rel_s
   for (int b = 0; b < NA; ++b) {
     const float* src = s.anc_table[b] + (size_t)__shfl_sync(0xffffffffu, idx, b, kHalf) * D;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) a[b][j] = ld(src, j);
+    for (int j = 0; j < NV; ++j) a[b][j] = ldrow(src, j);
   }
 #pragma unroll
   for (int tt = 0; tt < 2; ++tt) {
     const float* src = s.tgt_table + (size_t)__shfl_sync(0xffffffffu, idx, 8 + tt, kHalf) * D;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) t[tt][j] = ld(src, j);
+    for (int j = 0; j < NV; ++j) t[tt][j] = ldrow(src, j);
   }
   if (CHAIN) {
     // cos(a_hat, t_hat (+|*) v_r1 ... v_rn), raw dot for DistMult (decoders.py:200-205,228-233).
@@ -200,8 +209,10 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
   // the (<= 3) relation vectors of the formula the block is working on: every query of the formula reads
   // them in the middle of its dependent arithmetic, where an L1 miss (the streaming rows evict them) was
   // 12 % of all stall samples; reloaded when the block moves on to another formula
-  __shared__ __align__(16) float rel_sm[GQE_MAX_RELS][D];
-  int rel_of = -1;
+  // (two buffers: the next formula's vectors are fetched into registers while the current group is scored)
+  __shared__ __align__(16) float rel_sm[2][GQE_MAX_RELS][D];
+  constexpr int kRelPer = (GQE_MAX_RELS * D + kVecThreads - 1) / kVecThreads;   // values per thread
+  int rel_of = -1, rel_buf = 0;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int sl = lane & (kHalf - 1);
   const int qslot = wib * kQW + lane / kHalf;     // this half-warp's query inside a group
@@ -278,19 +289,39 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
       const int m = lane_mode(p.seg[c1.si]);
       if (m >= 0) cand_nxt = index_lookup(p.mode[m], raw_nxt, ik);
     }
-    if (rel_of != c0.si) {             // (block-uniform: c0 depends on blockIdx and the loop counter only)
-      __syncthreads();
+    if (rel_of != c0.si) {             // the block's first group (block-uniform: c0 depends on blockIdx and the loop counter only)
       for (int i = threadIdx.x; i < GQE_MAX_RELS * D; i += kVecThreads) {
         const float* r = s.rel[i / D];
-        rel_sm[i / D][i % D] = r ? __ldg(r + i % D) : 0.f;
+        rel_sm[rel_buf][i / D][i % D] = r ? __ldg(r + i % D) : 0.f;
       }
       __syncthreads();
       rel_of = c0.si;
     }
+    // the NEXT group belongs to another formula: its vectors travel while this group is scored
+    const bool rel_next = in1 && c1.si != rel_of;
+    float rel_pf[kRelPer];
+    if (rel_next) {
+#pragma unroll
+      for (int u = 0; u < kRelPer; ++u) {
+        const int i = threadIdx.x + u * kVecThreads;
+        const float* r = i < GQE_MAX_RELS * D ? p.seg[c1.si].rel[i / D] : nullptr;
+        rel_pf[u] = r ? __ldg(r + i % D) : 0.f;
+      }
+    }
     float sc[2];
-    if (s.structure <= GQE_CHAIN3) score_query<D, 1, true>(s, rel_sm, idx, sl, mul, use_min, sc);
-    else if (s.n_anchor == 2) score_query<D, 2, false>(s, rel_sm, idx, sl, mul, use_min, sc);
-    else score_query<D, 3, false>(s, rel_sm, idx, sl, mul, use_min, sc);
+    if (s.structure <= GQE_CHAIN3) score_query<D, 1, true>(s, rel_sm[rel_buf], idx, sl, mul, use_min, sc);
+    else if (s.n_anchor == 2) score_query<D, 2, false>(s, rel_sm[rel_buf], idx, sl, mul, use_min, sc);
+    else score_query<D, 3, false>(s, rel_sm[rel_buf], idx, sl, mul, use_min, sc);
+    if (rel_next) {                    // (the other buffer was last read before the previous switch's barrier)
+#pragma unroll
+      for (int u = 0; u < kRelPer; ++u) {
+        const int i = threadIdx.x + u * kVecThreads;
+        if (i < GQE_MAX_RELS * D) rel_sm[rel_buf ^ 1][i / D][i % D] = rel_pf[u];
+      }
+      __syncthreads();
+      rel_buf ^= 1;
+      rel_of = c1.si;
+    }
     if (sl == 0 && q >= 0) {
       if (p.out_scores) {
         p.out_scores[q * T] = sc[0];
