@@ -223,38 +223,58 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
   double local = 0.0;
 
   // Iteration space: GROUPS of kQB consecutive queries of one formula (the last group of a formula
-  // may be partly empty); block b takes groups b, b + gridDim.x, ...  Which formula a group belongs
-  // to depends on blockIdx and the loop counter only, so every branch on the query structure below
-  // is uniform across the block: no divergence, the warp shuffles need no convergence barriers.
-  auto groups_of = [&](int i) -> int64_t { return (p.seg[i].q_end - p.seg[i].q_begin + kQB - 1) / kQB; };
-  int64_t total = 0;
-  for (int i = 0; i < p.n_segs; ++i) total += groups_of(i);
-  struct Cursor { int si; int64_t base; };                 // group -> (segment, first group of it); only moves forward
-  auto locate = [&](Cursor& c, int64_t g) -> bool {       // false past the end
-    if (g >= total) return false;
-    while (g >= c.base + groups_of(c.si)) {
-      c.base += groups_of(c.si);
-      ++c.si;
+  // may be partly empty).  Block b takes the group PAIRS b, b + gridDim.x, ... (two consecutive groups
+  // mostly share their formula: half as many relation-vector switches as with single groups).  Which
+  // formula a group belongs to depends on blockIdx and the loop counter only, so every branch on the
+  // query structure below is uniform across the block: no divergence, the warp shuffles need no
+  // convergence barriers.
+  // Per-segment facts the bookkeeping needs every iteration, as 32-bit words in shared memory (the
+  // launch parameters live in the constant bank, where a dynamically indexed 64-bit field costs a
+  // dependent LDC each: 16 % of the stall samples went there).
+  __shared__ int sg_gbase[kMaxSegs + 1];   // first group of segment i (prefix sum), [n_segs] = total
+  __shared__ int sg_q0[kMaxSegs], sg_nq[kMaxSegs];
+  __shared__ int sg_mode[kMaxSegs];        // anchor modes in bytes 0..2, target mode in byte 3, n_anchor in bits 28..31
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < p.n_segs; ++i) {
+      const SegDev& sd = p.seg[i];
+      sg_gbase[i] = acc;
+      sg_q0[i] = (int)sd.q_begin;
+      sg_nq[i] = (int)(sd.q_end - sd.q_begin);
+      acc += (sg_nq[i] + kQB - 1) / kQB;
+      sg_mode[i] = (sd.anc_mode[0] & 15) | ((sd.anc_mode[1] & 15) << 4) | ((sd.anc_mode[2] & 15) << 8) |
+                   ((sd.tgt_mode & 15) << 12) | (sd.n_anchor << 28);
     }
+    sg_gbase[p.n_segs] = acc;
+  }
+  __syncthreads();
+  const int total = sg_gbase[p.n_segs];
+  const int G = (int)gridDim.x;
+  auto group_of = [&](int t) -> int { return (((t >> 1) * G + (int)blockIdx.x) << 1) | (t & 1); };   // t-th group of this block
+  struct Cursor { int si; };                                // segment of a group; only moves forward
+  auto locate = [&](Cursor& c, int g) -> bool {            // false past the end
+    if (g >= total) return false;
+    while (g >= sg_gbase[c.si + 1]) ++c.si;
     return true;
   };
   // this half-warp's query of group g (-1: none)
-  auto query_of = [&](const Cursor& c, int64_t g, bool in) -> int64_t {
+  auto query_of = [&](const Cursor& c, int g, bool in) -> int64_t {
     if (!in) return -1;
-    const int64_t q = p.seg[c.si].q_begin + (g - c.base) * kQB + qslot;
-    return q < p.seg[c.si].q_end ? q : -1;
+    const int ql = (g - sg_gbase[c.si]) * kQB + qslot;
+    return ql < sg_nq[c.si] ? (int64_t)(sg_q0[c.si] + ql) : -1;
   };
   // sub-lanes 0..na-1 of a half hold the anchor indices of its query, sub-lanes 8, 9 its target indices
   // (9 repeats target 0 when T == 1).
   const int tslot = sl == 9 && T > 1 ? 1 : 0;
-  auto lane_mode = [&](const SegDev& sg) -> int {        // this lane's node type in a query of `sg`, -1: none
-    if (sl < sg.n_anchor) return sg.anc_mode[sl];
-    if (sl == 8 || sl == 9) return sg.tgt_mode;
+  auto lane_mode = [&](int si) -> int {                    // this lane's node type in a query of segment si, -1: none
+    const int w = sg_mode[si];
+    if (sl < (int)((unsigned)w >> 28)) return (w >> (4 * sl)) & 15;
+    if (sl == 8 || sl == 9) return (w >> 12) & 15;
     return -1;
   };
-  auto fetch_raw = [&](int64_t q, const SegDev& sg) -> int32_t {
+  auto fetch_raw = [&](int64_t q, int si) -> int32_t {
     if (q < 0) return 0;
-    if (sl < sg.n_anchor) return __ldg(p.anchor_rows + (int64_t)sl * p.anchor_stride + q);
+    if (sl < (int)((unsigned)sg_mode[si] >> 28)) return __ldg(p.anchor_rows + (int64_t)sl * p.anchor_stride + q);
     if (sl == 8 || sl == 9) return __ldg(p.target_rows + q * T + tslot);
     return 0;
   };
@@ -263,30 +283,31 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
   // [Measured, not kept: requesting the NEXT groups' rows into L2 (prefetch.global.L2 right behind
   // the lookup, or one iteration later with a four-stage pipeline) is 4-8 % slower on both the
   // 10 GB and the L2-resident tables -- profiles/r02_vec_experiments.md.]
-  Cursor c0{0, 0}, c1{0, 0}, c2{0, 0};
-  int64_t g = blockIdx.x;
-  bool in0 = locate(c0, g), in1 = locate(c1, g + gridDim.x);
-  int64_t q = query_of(c0, g, in0), q1 = query_of(c1, g + gridDim.x, in1);
-  int32_t raw_cur = in0 ? fetch_raw(q, p.seg[c0.si]) : 0, raw_nxt = in1 ? fetch_raw(q1, p.seg[c1.si]) : 0;
+  Cursor c0{0}, c1{0}, c2{0};
+  int t = 0;
+  bool in0 = locate(c0, group_of(0)), in1 = locate(c1, group_of(1));
+  int64_t q = query_of(c0, group_of(0), in0), q1 = query_of(c1, group_of(1), in1);
+  int32_t raw_cur = in0 ? fetch_raw(q, c0.si) : 0, raw_nxt = in1 ? fetch_raw(q1, c1.si) : 0;
   int32_t cand = 0;
   if (q >= 0) {
-    const int m = lane_mode(p.seg[c0.si]);
+    const int m = lane_mode(c0.si);
     if (m >= 0) cand = index_lookup(p.mode[m], raw_cur, ik);
   }
-  for (; in0; g += gridDim.x) {
+  for (; in0; ++t) {
     const SegDev& s = p.seg[c0.si];
     int32_t idx = 0;
     if (q >= 0) {
-      const int my_mode = lane_mode(s);
+      const int my_mode = lane_mode(c0.si);
       if (my_mode >= 0) idx = index_check(p.mode[my_mode], my_mode, cand, raw_cur, ik, p.err);
     }
     // the later groups' indices travel while this group's rows do
-    const bool in2 = locate(c2, g + 2 * (int64_t)gridDim.x);
-    const int64_t q2 = query_of(c2, g + 2 * (int64_t)gridDim.x, in2);
-    const int32_t raw_nxt2 = in2 ? fetch_raw(q2, p.seg[c2.si]) : 0;
+    const int g2 = group_of(t + 2);
+    const bool in2 = locate(c2, g2);
+    const int64_t q2 = query_of(c2, g2, in2);
+    const int32_t raw_nxt2 = in2 ? fetch_raw(q2, c2.si) : 0;
     int32_t cand_nxt = 0;
     if (q1 >= 0) {
-      const int m = lane_mode(p.seg[c1.si]);
+      const int m = lane_mode(c1.si);
       if (m >= 0) cand_nxt = index_lookup(p.mode[m], raw_nxt, ik);
     }
     if (rel_of != c0.si) {             // the block's first group (block-uniform: c0 depends on blockIdx and the loop counter only)
@@ -372,6 +393,8 @@ __global__ void __launch_bounds__(kVecThreads, (D >= 256 ? GQE_VEC_BLOCKS_D256 :
 
 template <int D>
 cudaError_t launch_vec_t(const LaunchParams& lp, cudaStream_t st) {
+  for (int i = 0; i < lp.n_segs; ++i)    // (the kernel keeps query positions as 32-bit words)
+    if (lp.seg[i].q_end >= 0x7fffffffLL) return cudaErrorInvalidValue;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
