@@ -159,6 +159,14 @@ __device__ __forceinline__ const uint8_t* step_matrix(const SegDev& s, int mat) 
   return reinterpret_cast<const uint8_t*>(p);  // packed bf16 planes on this path
 }
 
+// 16 bytes of a table row: read once per tile, so kept out of L1 (what IS re-read through L1 -- index
+// arrays, node maps -- then stays there).  Works on peer (NVLink-mapped) addresses like a plain load.
+__device__ __forceinline__ float4 ld_row(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // ---- small math helpers -----------------------------------------------------------
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -212,7 +220,7 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
       okv[u] = row >= 0;
       const float4* src = reinterpret_cast<const float4*>(table + (size_t)(okv[u] ? row : 0) * D);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[u][j] = okv[u] ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NV; ++j) v[u][j] = okv[u] ? ld_row(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -436,7 +444,7 @@ __device__ __forceinline__ void score_frag(const LaunchParams& p, Ctl* ctl, floa
       for (int rs = 0; rs < 2; ++rs)
 #pragma unroll
         for (int b = 0; b < 2; ++b)
-          av[r][rs][b] = ok[rs] ? __ldg(reinterpret_cast<const float4*>(pr[rs] + 32 * (c + r) + 16 * b)) : zero4;
+          av[r][rs][b] = ok[rs] ? ld_row(reinterpret_cast<const float4*>(pr[rs] + 32 * (c + r) + 16 * b)) : zero4;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       uint32_t raw[16];
@@ -912,8 +920,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           const float4* b_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)(ok ? (T > 1 ? rb : ra[u]) : 0) * D);
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
-            ta[u][j] = ok ? __ldg(a_src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            tb[u][j] = ok ? __ldg(b_src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ta[u][j] = ok ? ld_row(a_src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tb[u][j] = ok ? ld_row(b_src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         float red[SU][5];  // |q|^2, q.a, |a|^2, q.b, |b|^2
