@@ -583,6 +583,9 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
           }
         }
       }
+      if (use_tc)
+        build_program(s->prog, g.plan.structure, c->inter == GQE_INTER_DEEPSETS_MEAN || c->inter == GQE_INTER_DEEPSETS_MIN,
+                      s->composed != 0);
       if (first_structure < 0) first_structure = g.plan.structure;
       else if (first_structure != g.plan.structure) uniform = false;
       ++n;

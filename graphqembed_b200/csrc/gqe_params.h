@@ -40,6 +40,82 @@ struct ModeDev {
 };
 enum { IDX_ERR_NONE = 0, IDX_ERR_UNKNOWN_NODE = 1, IDX_ERR_ROW_RANGE = 2 };
 
+// ---- the per-structure program of the tensor-core kernel (gqe_tc.cuh) ---------------------------
+// Built by the host once per formula of a launch (SegDev::prog); the kernel's three roles walk it.
+constexpr int kMaxSteps = 8;
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#endif
+enum { G_NONE = 7, G_TARGET = 3 };                       // gather source: anchor 0..2, target, none
+enum { M_REL0 = 0, M_REL1 = 1, M_REL2 = 2, M_PRE = 3, M_POST = 4 };
+// epilogue kinds (E_KIND masks them) and flags.  E_NONE: the accumulator is left in TMEM, raw,
+// for the NEXT step's epilogue (first DeepSets branch).  F_MMA_ALT: this step's MMAs write the
+// tile's second TMEM region, so that the raw first branch (F_AGG_RAW) or the running aggregate
+// in the first region survives; the epilogue then combines the two and keeps the aggregate in
+// the first region.
+enum { E_TO_A = 0, E_AGG = 1, E_SCORE = 2, E_NONE = 3, E_KIND = 3, F_RELU = 4, F_FIRST = 8, F_LAST = 16, F_DEST_ACC = 32,
+       F_AGG_RAW = 64, F_MMA_ALT = 128 };
+
+struct Prog {
+  int n;
+  uint8_t mat[kMaxSteps];
+  uint8_t gather[kMaxSteps];
+  uint8_t epi[kMaxSteps];
+};
+
+// Operator order of reference netquery/model.py:70-109 (see include/gqe.h gqe_plan).
+// `composed`: the host pre-multiplied every run of consecutive linear operators of this
+// formula into one matrix (gqe_compose, fp32), so a run is ONE contraction here:
+//   chains          act.mm(M1).mm(M2).mm(M3)      -> act.mm(M1 M2 M3)          rel[0]
+//   DeepSets branch relu(pre.mm(R.mm(e)))         -> relu((pre R).mm(e))       rel[b]
+//   3-inter_chain   pre.mm(R2a.mm(R2b.mm(e)))     -> (pre R2a R2b).mm(e)       rel[1]
+//   3-chain_inter   R1.mm(post.mm(combined))      -> (R1 post).mm(combined)    post
+// Same algebra, different fp32 rounding (~1e-7 relative), far inside the 1e-4 bound.
+inline __host__ __device__ void build_program(Prog& pg, int structure, bool deepsets, bool composed) {
+  int n = 0;
+  auto push = [&](int mat, int gather, int epi) {
+    pg.mat[n] = (uint8_t)mat;
+    pg.gather[n] = (uint8_t)gather;
+    pg.epi[n] = (uint8_t)epi;
+    ++n;
+  };
+  if (structure <= GQE_CHAIN3) {
+    const int hops = composed ? 1 : structure + 1;
+    for (int h = 0; h < hops; ++h) push(h, h == 0 ? G_TARGET : G_NONE, h == hops - 1 ? E_SCORE : E_TO_A);
+  } else {
+    const int nb = structure == GQE_INTER3 ? 3 : 2;
+    for (int b = 0; b < nb; ++b) {
+      const int pos = (b == 0 ? F_FIRST : 0) | (b == nb - 1 ? F_LAST : 0);
+      const int agg_simple = E_AGG | pos | ((b == nb - 1 && structure != GQE_CHAIN_INTER3) ? F_DEST_ACC : 0);
+      if (composed) {
+        // DeepSets: the first branch has no epilogue of its own -- its accumulator stays in TMEM
+        // and the second branch's epilogue applies relu to both (one TMEM pass and one
+        // workers <-> issuer round trip less per tile)
+        if (deepsets) push(b, b, b == 0 ? E_NONE : (E_AGG | F_RELU | F_MMA_ALT | (b == 1 ? F_AGG_RAW : 0) | (b == nb - 1 ? F_LAST : 0)));
+        else push(b, b, agg_simple);
+        continue;
+      }
+      if (structure == GQE_INTER_CHAIN3 && b == 1) {
+        push(M_REL1, b, E_TO_A);                               // reverse(r2b) first (model.py:85)
+        push(M_REL2, G_NONE, deepsets ? E_TO_A : agg_simple);  // then reverse(r2a)
+      } else {
+        push(b, b, deepsets ? E_TO_A : agg_simple);
+      }
+      if (deepsets) push(M_PRE, G_NONE, E_AGG | F_RELU | pos);  // relu(pre.mm(e)) decoders.py:289-292
+    }
+    if (composed) {
+      if (deepsets) push(M_POST, G_NONE, E_SCORE);                          // post, or R1 post for 3-chain_inter
+      else if (structure == GQE_CHAIN_INTER3) push(M_REL2, G_NONE, E_SCORE);
+    } else {
+      if (deepsets) push(M_POST, G_NONE, structure == GQE_CHAIN_INTER3 ? E_TO_A : E_SCORE);  // decoders.py:299
+      if (structure == GQE_CHAIN_INTER3) push(M_REL2, G_NONE, E_SCORE);                      // model.py:107
+    }
+  }
+  pg.n = n;
+}
+
+
 // One formula's slice of a launch, fully resolved to device pointers.
 struct SegDev {
   int32_t structure;
@@ -55,6 +131,7 @@ struct SegDev {
   const float* post;
   int64_t q_begin, q_end;          // query range in the concatenated arrays
   int64_t tile_begin;              // first tile of this segment inside the launch
+  Prog prog;                       // tensor-core path: the contractions of this formula, in reference order
 };
 
 struct LaunchParams {

@@ -43,7 +43,6 @@ namespace tc {
 constexpr int kRows = 128;     // rows per tile = UMMA M
 constexpr int kKBlock = 64;    // bf16 per 128-byte swizzle row
 constexpr int kStages = 3;     // weight ring depth
-constexpr int kMaxSteps = 8;
 
 template <int D>
 struct Cfg {
@@ -85,75 +84,8 @@ struct Ctl {
 };
 static_assert(sizeof(Ctl) <= 512, "control block");
 
-// ---- the per-structure program --------------------------------------------------
-enum { G_NONE = 7, G_TARGET = 3 };                       // gather source: anchor 0..2, target, none
-enum { M_REL0 = 0, M_REL1 = 1, M_REL2 = 2, M_PRE = 3, M_POST = 4 };
-// epilogue kinds (E_KIND masks them) and flags.  E_NONE: the accumulator is left in TMEM, raw,
-// for the NEXT step's epilogue (first DeepSets branch).  F_MMA_ALT: this step's MMAs write the
-// tile's second TMEM region, so that the raw first branch (F_AGG_RAW) or the running aggregate
-// in the first region survives; the epilogue then combines the two and keeps the aggregate in
-// the first region.
-enum { E_TO_A = 0, E_AGG = 1, E_SCORE = 2, E_NONE = 3, E_KIND = 3, F_RELU = 4, F_FIRST = 8, F_LAST = 16, F_DEST_ACC = 32,
-       F_AGG_RAW = 64, F_MMA_ALT = 128 };
-
-struct Prog {
-  int n;
-  uint8_t mat[kMaxSteps];
-  uint8_t gather[kMaxSteps];
-  uint8_t epi[kMaxSteps];
-};
-
-// Operator order of reference netquery/model.py:70-109 (see include/gqe.h gqe_plan).
-// `composed`: the host pre-multiplied every run of consecutive linear operators of this
-// formula into one matrix (gqe_compose, fp32), so a run is ONE contraction here:
-//   chains          act.mm(M1).mm(M2).mm(M3)      -> act.mm(M1 M2 M3)          rel[0]
-//   DeepSets branch relu(pre.mm(R.mm(e)))         -> relu((pre R).mm(e))       rel[b]
-//   3-inter_chain   pre.mm(R2a.mm(R2b.mm(e)))     -> (pre R2a R2b).mm(e)       rel[1]
-//   3-chain_inter   R1.mm(post.mm(combined))      -> (R1 post).mm(combined)    post
-// Same algebra, different fp32 rounding (~1e-7 relative), far inside the 1e-4 bound.
-__device__ __forceinline__ void build_program(Prog& pg, int structure, bool deepsets, bool composed) {
-  int n = 0;
-  auto push = [&](int mat, int gather, int epi) {
-    pg.mat[n] = (uint8_t)mat;
-    pg.gather[n] = (uint8_t)gather;
-    pg.epi[n] = (uint8_t)epi;
-    ++n;
-  };
-  if (structure <= GQE_CHAIN3) {
-    const int hops = composed ? 1 : structure + 1;
-    for (int h = 0; h < hops; ++h) push(h, h == 0 ? G_TARGET : G_NONE, h == hops - 1 ? E_SCORE : E_TO_A);
-  } else {
-    const int nb = structure == GQE_INTER3 ? 3 : 2;
-    for (int b = 0; b < nb; ++b) {
-      const int pos = (b == 0 ? F_FIRST : 0) | (b == nb - 1 ? F_LAST : 0);
-      const int agg_simple = E_AGG | pos | ((b == nb - 1 && structure != GQE_CHAIN_INTER3) ? F_DEST_ACC : 0);
-      if (composed) {
-        // DeepSets: the first branch has no epilogue of its own -- its accumulator stays in TMEM
-        // and the second branch's epilogue applies relu to both (one TMEM pass and one
-        // workers <-> issuer round trip less per tile)
-        if (deepsets) push(b, b, b == 0 ? E_NONE : (E_AGG | F_RELU | F_MMA_ALT | (b == 1 ? F_AGG_RAW : 0) | (b == nb - 1 ? F_LAST : 0)));
-        else push(b, b, agg_simple);
-        continue;
-      }
-      if (structure == GQE_INTER_CHAIN3 && b == 1) {
-        push(M_REL1, b, E_TO_A);                               // reverse(r2b) first (model.py:85)
-        push(M_REL2, G_NONE, deepsets ? E_TO_A : agg_simple);  // then reverse(r2a)
-      } else {
-        push(b, b, deepsets ? E_TO_A : agg_simple);
-      }
-      if (deepsets) push(M_PRE, G_NONE, E_AGG | F_RELU | pos);  // relu(pre.mm(e)) decoders.py:289-292
-    }
-    if (composed) {
-      if (deepsets) push(M_POST, G_NONE, E_SCORE);                          // post, or R1 post for 3-chain_inter
-      else if (structure == GQE_CHAIN_INTER3) push(M_REL2, G_NONE, E_SCORE);
-    } else {
-      if (deepsets) push(M_POST, G_NONE, structure == GQE_CHAIN_INTER3 ? E_TO_A : E_SCORE);  // decoders.py:299
-      if (structure == GQE_CHAIN_INTER3) push(M_REL2, G_NONE, E_SCORE);                      // model.py:107
-    }
-  }
-  pg.n = n;
-}
-
+// (the per-structure program -- Prog, build_program, the G_* / M_* / E_* / F_* codes -- lives in
+// gqe_params.h: the host builds it once per formula into SegDev::prog)
 __device__ __forceinline__ const uint8_t* step_matrix(const SegDev& s, int mat) {
   const float* p = mat <= M_REL2 ? s.rel[mat] : (mat == M_PRE ? s.pre : s.post);
   return reinterpret_cast<const uint8_t*>(p);  // packed bf16 planes on this path
@@ -307,6 +239,13 @@ __device__ __forceinline__ int seg_of_tile(const LaunchParams& p, int64_t tile) 
   }
   return si;
 }
+
+// What travels through the tile ring: the tile id in the low 40 bits, its segment above.  The scheduler
+// thread does the segment scan ONCE per tile (it needs the segment itself); the 576 consumers would
+// otherwise each repeat it -- up to 32 dynamically indexed constant-bank loads per tile and thread.
+__device__ __forceinline__ int64_t ring_pack(int64_t tile, int seg) { return tile | ((int64_t)seg << 40); }
+__device__ __forceinline__ int64_t ring_tile(int64_t v) { return v & ((1ll << 40) - 1); }
+__device__ __forceinline__ int ring_seg(int64_t v) { return (int)(v >> 40); }
 
 struct TileRing {  // consumer side of the tile-id ring
   uint32_t k = 0;
@@ -601,9 +540,10 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
   int32_t carry_row = -1;                          // this lane's first-gather row of the NEXT tile, resolved one tile ahead
   if (lane == 0) ctl->bad[wid] = 0;
   for (;;) {
-    const int64_t tile = ring.take(ctl);
+    const int64_t tile_v = ring.take(ctl);
+    const int64_t tile = ring_tile(tile_v);
     if (tile >= p.n_tiles) break;
-    const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
+    const SegDev& s = p.seg[ring_seg(tile_v)];
     const int structure = STRUCT >= 0 ? STRUCT : s.structure;
     const bool chain = structure <= GQE_CHAIN3;
     const int n_branch = s.n_anchor;
@@ -623,8 +563,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     const int64_t row_end = chain ? s.q_end * T : s.q_end;
     const int n_valid = (int)min((int64_t)kRows, row_end - row_begin);
 
-    Prog pg;
-    build_program(pg, structure, deepsets, s.composed != 0);
+    const Prog& pg = s.prog;
 
     // diagnostics: per-tile phase stamps of worker thread 0 (tools/phase_report.py)
     int n_stamp = 0;
@@ -716,13 +655,14 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       if (st == 0) {
         // while the first contraction runs: the raw first-gather index of the NEXT tile of this CTA
         // (its id was published by the scheduler while this tile's first gather ran) ...
-        const int64_t nt = ring.peek(ctl, 0);
+        const int64_t nt_v = ring.peek(ctl, 0);
+        const int64_t nt = ring_tile(nt_v);
         int32_t raw_n = 0, m2 = 0;
         bool has_n = false, remote2 = true;
         const float* tab2 = nullptr;
 
         if (nt < p.n_tiles) {
-          const SegDev& s2 = p.seg[seg_of_tile<STRUCT>(p, nt)];
+          const SegDev& s2 = p.seg[ring_seg(nt_v)];
           const bool chain2 = (STRUCT >= 0 ? STRUCT : s2.structure) <= GQE_CHAIN3;
           const int64_t rb2 = (chain2 ? s2.q_begin * T : s2.q_begin) + (nt - s2.tile_begin) * kRows;
           const int64_t re2 = chain2 ? s2.q_end * T : s2.q_end;
@@ -865,7 +805,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     // Scored straight from TMEM (score_frag) -- when this CTA has a next tile, only after that
     // tile's first contraction has been handed to the tensor pipe.
     if (frag) {
-      if (ring.peek(ctl, 0) < p.n_tiles) {
+      if (ring_tile(ring.peek(ctl, 0)) < p.n_tiles) {
         pend = cur;
       } else {
         score_frag<D>(p, ctl, scratch, tmem_base, cur, wid, lane);
@@ -1029,17 +969,18 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
     ptx::mbar_arrive(ptx::smem_u32(&ctl->sched_full[k & 1]));
   };
   int64_t tile = blockIdx.x;
-  publish(0, tile);
+  int si = tile < p.n_tiles ? seg_of_tile<STRUCT>(p, tile) : 0;
+  publish(0, ring_pack(tile, si));
   // The packed weights come from gqe_pack, the kernel before this one in the stream; this kernel
   // is launched programmatically dependent on it, so that the set-up and the first gathers of
   // the workers (tables and indices only) overlap its tail.  Only this thread reads weights.
   ptx::griddep_wait();
   for (uint32_t k = 0; tile < p.n_tiles; ++k) {
     const int64_t next = PAIR ? tile + (int64_t)gridDim.x : (int64_t)gridDim.x + (int64_t)atomicAdd(p.tile_counter, 1u);
-    publish(k + 1, next < p.n_tiles ? next : p.n_tiles);
-    const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
-    Prog pg;
-    build_program(pg, STRUCT >= 0 ? STRUCT : s.structure, deepsets, s.composed != 0);
+    const int si_next = next < p.n_tiles ? seg_of_tile<STRUCT>(p, next) : 0;
+    publish(k + 1, next < p.n_tiles ? ring_pack(next, si_next) : p.n_tiles);
+    const SegDev& s = p.seg[si];
+    const Prog& pg = s.prog;
     for (int st = 0; st < pg.n; ++st) {
       const uint8_t* src = step_matrix(s, pg.mat[st]);
 #pragma unroll 1
@@ -1060,6 +1001,7 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
       }
     }
     tile = next;
+    si = si_next;
   }
 }
 
@@ -1076,12 +1018,12 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
   uint32_t slot = 0, phase = 0, gs = 0;
   TileRing ring;
   for (;;) {
-    const int64_t tile = ring.take(ctl);
+    const int64_t tile_v = ring.take(ctl);
+    const int64_t tile = ring_tile(tile_v);
     if (tile >= p.n_tiles) break;
-    const SegDev& s = p.seg[seg_of_tile<STRUCT>(p, tile)];
+    const SegDev& s = p.seg[ring_seg(tile_v)];
     const int structure = STRUCT >= 0 ? STRUCT : s.structure;
-    Prog pg;
-    build_program(pg, structure, deepsets, s.composed != 0);
+    const Prog& pg = s.prog;
     // the accumulator / aggregate roles of the two TMEM regions alternate per tile (see worker())
     const uint32_t tmem_main = tmem_base + ((ring.k - 1) & 1u) * D;
     const uint32_t tmem_alt = tmem_base + (ring.k & 1u) * D;
