@@ -20,6 +20,17 @@ lookup = gqe.RowLookup(wl.kg.node_ids)
 mode_ids = {m: i for i, m in enumerate(wl.kg.modes)}
 rel_ids = {r: i for i, r in enumerate(wl.kg.rel_keys)}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=device)     # 256 MiB read after the write: evicts the dirty lines
+FLUSH = os.environ.get("AB_FLUSH", "write")                                # write | wr (write, then read) | none
+
+
+def do_flush():
+    if FLUSH != "none":
+        flush.zero_()
+    if FLUSH == "wr":
+        flush_rd.sum()
+
+
 d_loss = torch.zeros(1, device=device)
 stream = torch.cuda.current_stream()
 for nodes in (False, True, False, True):
@@ -38,12 +49,13 @@ for nodes in (False, True, False, True):
     def step():
         ctx.score_grouped_device(segs, wl.n_queries, da.data_ptr(), dt.data_ptr(), 2, None, 1.0, d_loss.data_ptr(), nodes=nodes)
     for _ in range(5):
-        flush.zero_(); step()
+        do_flush(); step()
     torch.cuda.synchronize()
     n = 100
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
     for e0, e1 in evs:
-        flush.zero_(); e0.record(stream); step(); e1.record(stream)
+        do_flush(); e0.record(stream); step(); e1.record(stream)
     torch.cuda.synchronize()
     ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+    print("flush=%s " % FLUSH, end="")
     print("%s %s: mean %.4f ms  median %.4f  min %.4f  loss %.7f" % (name, "nodes" if nodes else "rows ", sum(ts) / n, ts[n // 2], ts[0], d_loss.item()))
