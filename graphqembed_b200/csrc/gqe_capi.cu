@@ -638,6 +638,10 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
         c->launches += 1;
         c->weight_preps += n_pack;
       }
+      // indices fetched by gqe_fetch_indices right in front of this launch: the kernel waits for it itself
+      // (with weight preparation in between, the ordinary stream order has already done that)
+      lp.wait_prev = (c->idx_by_kernel && n_pack == 0 && n_cw[0] == 0 && n_cw[1] == 0) ? 1 : 0;
+      c->idx_by_kernel = false;
       GQE_CUDA(c, launch_fused_tc(c->d, structure, lp, tiles, c->stream));
       c->launches += 1;
       if (lp.err_host) c->err_posted = true;
@@ -766,6 +770,11 @@ static const size_t kInPlaceIndexBytes = [] {   // GQE_INPLACE_BYTES in the envi
   return e ? (size_t)atoll(e) : (size_t)128 << 10;
 }();
 
+static const bool kFetchKernel = [] {
+  const char* e = getenv("GQE_FETCH_KERNEL");
+  return e ? atoi(e) != 0 : true;
+}();
+
 static int max_anchors(const gqe_segment* segs, int n) {
   int m = 0;
   for (int i = 0; i < n; ++i) m = std::max(m, n_anchors_of(segs[i].plan.structure));
@@ -811,7 +820,45 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
     }
     (void)cudaGetLastError();    // (a pageable pointer is an error to the query on some drivers)
   }
-  if (nq > 0 && !zc_anchor) {
+  // Larger calls on pinned (mapped) buffers: ONE kernel copies every range over PCIe (gqe_fetch_indices)
+  // instead of one copy-engine operation per range (GQE_FETCH_KERNEL=0: always the copy engine).
+  bool fetched = false;
+  c->idx_by_kernel = false;
+  if (nq > 0 && !zc_anchor && kFetchKernel && anchor_rows && target_rows) {
+    cudaPointerAttributes pa, pt, po;
+    const bool ok = cudaPointerGetAttributes(&pa, anchor_rows) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+                    cudaPointerGetAttributes(&pt, target_rows) == cudaSuccess && pt.type == cudaMemoryTypeHost && pt.devicePointer &&
+                    (!target_offsets || (cudaPointerGetAttributes(&po, target_offsets) == cudaSuccess &&
+                                         po.type == cudaMemoryTypeHost && po.devicePointer));
+    (void)cudaGetLastError();
+    if (ok) {
+      FetchParams fp;
+      fp.count = 0;
+      auto add = [&](const void* src_dev, void* dst, int64_t words) {
+        if (words <= 0) return;
+        fp.src[fp.count] = (const int32_t*)src_dev;
+        fp.dst[fp.count] = (int32_t*)dst;
+        fp.n[fp.count] = words;
+        ++fp.count;
+      };
+      for (int k = 0; k < na; ++k) {     // per slot, the query range of the segments that read it (see below)
+        int64_t lo = nq, hi = 0;
+        for (int32_t i = 0; i < n_segs; ++i)
+          if (n_anchors_of(segs[i].plan.structure) > k && segs[i].query_end > segs[i].query_begin) {
+            lo = std::min(lo, std::max<int64_t>(segs[i].query_begin, 0));
+            hi = std::max(hi, std::min<int64_t>(segs[i].query_end, nq));
+          }
+        add((const int32_t*)pa.devicePointer + (size_t)k * nq + lo, (int32_t*)c->stage[ST_ANCHOR] + (size_t)k * nq + lo, hi - lo);
+      }
+      add(pt.devicePointer, c->stage[ST_TARGET], n_pairs);
+      if (target_offsets) add(po.devicePointer, c->stage[ST_OFFSETS], 2 * (nq + 1));
+      GQE_CUDA(c, launch_fetch_indices(fp, c->stream));
+      c->launches += 1;
+      c->idx_by_kernel = true;
+      fetched = true;
+    }
+  }
+  if (nq > 0 && !zc_anchor && !fetched) {
     if (!anchor_rows || !target_rows) return fail(c, GQE_ERR_INVALID, "index arrays are null");
     // in stream order, in front of the kernels: with the packed weights cached there is nothing
     // to overlap the copies with, and a second stream would only add event traffic to the call
@@ -840,6 +887,7 @@ static int run_fused_host(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, i
                  zc_target ? zc_target : (const int32_t*)c->stage[ST_TARGET],
                  target_offsets ? (const int64_t*)c->stage[ST_OFFSETS] : nullptr, T,
                  out_scores ? (float*)c->stage[ST_SCORES] : nullptr, margin, loss_dst, index_kind, c->h_err_dev);
+  c->idx_by_kernel = false;
   if (rc != GQE_OK) return rc;
   if (out_scores && n_pairs > 0)
     GQE_CUDA(c, cudaMemcpyAsync(out_scores, c->stage[ST_SCORES], sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost,

@@ -60,6 +60,10 @@ struct gqe_ctx {
   unsigned long long* h_err = nullptr;
   unsigned long long* h_err_dev = nullptr;
 
+  // a *_host call copied its index arrays with gqe_fetch_indices: the next tensor-core launch waits for that
+  // kernel itself (LaunchParams::wait_prev)
+  bool idx_by_kernel = false;
+
   // diagnostics: per-tile phase stamps of the tensor-core kernel
   unsigned long long* phase_log = nullptr;
   int64_t phase_cap = 0;

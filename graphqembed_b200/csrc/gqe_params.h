@@ -169,6 +169,8 @@ struct LaunchParams {
   unsigned long long* err;      // DEVICE [2]: (kind << 32 | mode, offending value) of the first bad index
   unsigned long long* err_host; // mapped pinned copy written by the last CTA of a *_host call, or null
   int32_t pair;                 // tensor-core path: launched as clusters of two CTAs (tiles padded to pairs per segment)
+  int32_t wait_prev;            // tensor-core path: the index arrays are written by the kernel in front of this one in
+                                // the stream (gqe_fetch_indices): every thread waits for it before its first index load
   ModeDev mode[kMaxModes];
 };
 constexpr int kPhaseSlots = 32;
@@ -216,6 +218,14 @@ struct ComposeEntry {
 constexpr int kMaxCompose = 3 * kMaxSegs;  // a structure needs at most three products
 struct ComposeParams {
   ComposeEntry e[kMaxCompose];
+};
+// gqe_fetch_indices: index arrays of a *_host call copied from MAPPED pinned host memory by the SMs
+constexpr int kMaxFetch = 6;
+struct FetchParams {
+  const int32_t* src[kMaxFetch];  // device alias of the caller's pinned host array
+  int32_t* dst[kMaxFetch];
+  int64_t n[kMaxFetch];           // 32-bit words
+  int32_t count;
 };
 // gqe_score_pairs: one formula segment's (query, target) pairs against stored query embeddings
 struct PairSeg {

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "gqe_launch.h"
+#include "gqe_ptx.cuh"
 
 namespace gqe {
 
@@ -52,6 +53,50 @@ cudaError_t launch_gather_rows(const float* table, const int32_t* rows, int64_t 
   const int64_t want = (n + 31) / 32;  // 8 warps x 4 rows per CTA pass
   const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
   gqe_gather_rows<<<grid, 256, 0, st>>>(table, rows, n, d / 4, out, table_rows, err);
+  return cudaGetLastError();
+}
+
+// ---- index arrays of a *_host call ------------------------------------------------------------------
+// The caller's int32 arrays live in pinned host memory.  A copy-engine transfer costs ~6-10 us of fixed
+// latency EACH (three anchor slots + the targets = four of them in front of a 125 us kernel); here the SMs
+// read all ranges over PCIe in one launch instead (16 bytes per thread per request, every thread's requests
+// in flight together), and the scoring kernel -- launched programmatically dependent on this one -- sets
+// itself up meanwhile (LaunchParams::wait_prev).  blockIdx.y = range.
+__global__ void __launch_bounds__(256) gqe_fetch_indices(const __grid_constant__ FetchParams p) {
+  ptx::griddep_launch_dependents();
+  const int r = blockIdx.y;
+  const int32_t* __restrict__ src = p.src[r];
+  int32_t* __restrict__ dst = p.dst[r];
+  const int64_t n = p.n[r];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const uintptr_t sa = reinterpret_cast<uintptr_t>(src), da = reinterpret_cast<uintptr_t>(dst);
+  if (((sa ^ da) & 15u) != 0) {     // differently aligned: word by word
+    for (int64_t i = tid; i < n; i += nth) dst[i] = __ldcv(src + i);
+    return;
+  }
+  int64_t head = (int64_t)(((16u - (unsigned)(da & 15u)) & 15u) >> 2);
+  if (head > n) head = n;
+  const int64_t n4 = (n - head) >> 2, tail = head + 4 * n4;
+  if (tid < head) dst[tid] = __ldcv(src + tid);
+  if (tid < n - tail) dst[tail + tid] = __ldcv(src + tail + tid);
+  const int4* __restrict__ s4 = reinterpret_cast<const int4*>(src + head);
+  int4* __restrict__ d4 = reinterpret_cast<int4*>(dst + head);
+  int64_t i = tid;
+  for (; i + 3 * nth < n4; i += 4 * nth) {     // four requests in flight per thread
+    const int4 a = __ldcv(s4 + i), b = __ldcv(s4 + i + nth), c = __ldcv(s4 + i + 2 * nth), d = __ldcv(s4 + i + 3 * nth);
+    d4[i] = a; d4[i + nth] = b; d4[i + 2 * nth] = c; d4[i + 3 * nth] = d;
+  }
+  for (; i < n4; i += nth) d4[i] = __ldcv(s4 + i);
+}
+
+cudaError_t launch_fetch_indices(const FetchParams& fp, cudaStream_t st) {
+  if (fp.count <= 0) return cudaSuccess;
+  int64_t most = 0;
+  for (int i = 0; i < fp.count; ++i) most = fp.n[i] > most ? fp.n[i] : most;
+  // 16 bytes per thread and pass; a range of 256 K words (1 MiB) gets 64 blocks
+  int64_t bx = (most / 4 + 1023) / 1024;
+  bx = bx < 1 ? 1 : (bx > 96 ? 96 : bx);
+  gqe_fetch_indices<<<dim3((unsigned)bx, (unsigned)fp.count), 256, 0, st>>>(fp);
   return cudaGetLastError();
 }
 

@@ -1101,6 +1101,9 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (PAIR) ptx::cluster_sync();   // the partner's barriers exist before anything is sent to them
+  // the index arrays come from gqe_fetch_indices, the kernel in front of this one (a *_host call on pinned
+  // buffers): this kernel was launched while that one ran; its writes are visible after the wait
+  if (p.wait_prev) ptx::griddep_wait();
   ptx::tc_fence_after_sync();
   if (threadIdx.x == 0) cta_stamp(p, 1);
 
