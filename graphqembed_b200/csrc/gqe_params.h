@@ -15,7 +15,7 @@ constexpr int kRowsPerWarp = kTileRows / kWarps;  // 8
 constexpr int kPanelK = 16;
 constexpr int kRowStride = kTileRows + 4;  // 68 floats: 16B-aligned rows, 4-bank skew
 #ifndef GQE_MAX_SEGS
-#define GQE_MAX_SEGS 32
+#define GQE_MAX_SEGS 96
 #endif
 #ifndef GQE_MAX_MODES
 #define GQE_MAX_MODES 16

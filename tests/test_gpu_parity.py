@@ -177,7 +177,7 @@ def test_grouped_launch_matches_per_formula_calls():
     model = build_package_model(case)
     batches, per_scores, per_n = [], [], []
     rng = np.random.RandomState(3)
-    for rep in range(6):                     # 42 segments > 32 (kMaxSegs): two launches, one loss accumulator
+    for rep in range(15):                    # 105 segments > 96 (kMaxSegs): two launches, one loss accumulator
         for s in STRUCTURES:
             b = case.batches[s]
             n = int(rng.randint(1, 150))
