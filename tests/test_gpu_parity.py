@@ -230,6 +230,69 @@ def test_host_buffer_entry_points_match_device_ones(small):
         np.testing.assert_allclose(out2, dev, rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("decoder,d", [("bilinear", 128), ("transe", 64)])
+@pytest.mark.parametrize("shift", [0, 1, 3])
+def test_host_entry_points_on_pinned_buffers(decoder, d, shift):
+    """Index arrays in PINNED host memory above the in-place threshold are copied by gqe_fetch_indices (one
+    kernel reading every range over PCIe, the scoring kernel launched programmatically dependent on it): same
+    bits as the device entry point, for 16-byte aligned and unaligned host arrays, per-slot sub-ranges (chains in
+    front of intersections) and the ragged layout's offsets."""
+    n = 9000
+    case = make_case(seed=91, d=d, decoder=decoder, inter="mean" if decoder == "bilinear" else "min-simple",
+                     n_queries=n, n_neg=1, nodes_per_mode=700)
+    model = build_package_model(case)
+    ctx = model.context()
+    keep = []
+
+    def pinned(a):
+        t = torch.empty(a.size + shift, dtype=torch.int64 if a.dtype == np.int64 else torch.int32).pin_memory()
+        keep.append(t)
+        v = t.numpy()[shift:].reshape(a.shape)
+        v[...] = a
+        return v
+
+    order = ("2-chain", "3-inter", "1-chain", "2-inter")
+    nq = n * len(order)
+    a3 = np.zeros((3, nq), dtype=np.int32)
+    t2 = np.zeros(2 * nq, dtype=np.int32)
+    seg_list = []
+    for i, s in enumerate(order):
+        b = case.batches[s]
+        batch = query_batch(case, s, np.stack([b["target"], b["negs"][:, 0]], 1))
+        a, t = model.lower_batch(batch)
+        a3[:a.shape[0], i * n:(i + 1) * n] = a
+        t2[2 * i * n:2 * (i + 1) * n] = t
+        seg_list.append((model.plan(batch.formula), i * n, (i + 1) * n))
+    segs = gqe.make_segments(seg_list)
+    d_a, d_t = torch.from_numpy(a3).cuda(), torch.from_numpy(t2).cuda()
+    d_sc, d_loss = torch.empty(2 * nq, device="cuda"), torch.zeros(1, device="cuda")
+    ctx.score_grouped_device(segs, nq, d_a.data_ptr(), d_t.data_ptr(), 2, d_sc.data_ptr(), 1.0, d_loss.data_ptr())
+    torch.cuda.synchronize()
+    h_a, h_t = pinned(a3), pinned(t2)
+    for rep in range(2):
+        sc = np.full(2 * nq, np.nan, dtype=np.float32)
+        loss = np.zeros(1, dtype=np.float32)
+        ctx.score_grouped_host(segs, h_a, h_t, 2, sc, 1.0, loss)
+        np.testing.assert_array_equal(sc, _np(d_sc))
+        assert loss[0] == d_loss.item()
+        if rep == 0:                                        # new contents in the SAME pinned buffer are seen
+            h_t[:] = h_t.reshape(-1, 2)[:, ::-1].reshape(-1).copy()
+            d_t = torch.from_numpy(np.ascontiguousarray(h_t)).cuda()
+            ctx.score_grouped_device(segs, nq, d_a.data_ptr(), d_t.data_ptr(), 2, d_sc.data_ptr(), 1.0, d_loss.data_ptr())
+            torch.cuda.synchronize()
+    # single formula, ragged targets: the offsets travel the same way
+    b = case.batches["3-chain"]
+    batch = query_batch(case, "3-chain", np.stack([b["target"], b["negs"][:, 0]], 1))
+    plan = model.plan(batch.formula)
+    a, t = model.lower_batch(batch)
+    offsets = np.arange(batch.n_queries + 1, dtype=np.int64) * 2
+    want = np.empty(batch.n_pairs, dtype=np.float32)
+    ctx.score_host(plan, a, t, offsets, want)                       # pageable: copy engine
+    got = np.empty(batch.n_pairs, dtype=np.float32)
+    ctx.score_host(plan, pinned(a), pinned(t), pinned(offsets), got)
+    np.testing.assert_array_equal(got, want)
+
+
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("decoder", DECODERS)
 @pytest.mark.parametrize("inter", INTERS)
