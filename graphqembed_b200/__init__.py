@@ -12,9 +12,9 @@ from . import _lib
 from ._lib import Context, GqeError, GqeIndexError, Plan, Segment, build, load, make_segments
 from .lowering import RowLookup, lower_formula, relation_order
 from .query import Formula, Query, QueryBatch, reverse_relation
-from .store import FormulaBlock, QueryStore, StoreSlice
+from .store import DeviceQueryStore, DeviceSlice, FormulaBlock, QueryStore, StoreSlice
 
-__all__ = ["Context", "GqeError", "GqeIndexError", "QueryStore", "StoreSlice", "FormulaBlock", "SparseRowAdam", "NativeAdam", "Plan", "Segment", "build", "load", "make_segments", "RowLookup", "lower_formula",
+__all__ = ["Context", "GqeError", "GqeIndexError", "QueryStore", "StoreSlice", "FormulaBlock", "DeviceQueryStore", "DeviceSlice", "SparseRowAdam", "NativeAdam", "Plan", "Segment", "build", "load", "make_segments", "RowLookup", "lower_formula",
            "relation_order", "Formula", "Query", "QueryBatch", "reverse_relation", "DirectEncoder",
            "BilinearMetapathDecoder", "TransEMetapathDecoder", "BilinearDiagMetapathDecoder", "SetIntersection",
            "SimpleSetIntersection", "QueryEncoderDecoder", "get_encoder", "get_metapath_decoder",

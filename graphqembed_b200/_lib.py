@@ -35,7 +35,7 @@ DECODER_ID = {"bilinear": 0, "transe": 1, "bilinear-diag": 2}
 INTER_ID = {"mean": 0, "min": 1, "mean-simple": 2, "min-simple": 3}
 PRECISION_ID = {"bf16x3": 0, "fp32": 1}
 COMPOSE_ID = {"off": 0, "auto": 1, "always": 2}
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 GQE_ERR_INDEX = -6
@@ -77,6 +77,12 @@ class Segment(C.Structure):
     _fields_ = [("plan", Plan), ("query_begin", C.c_int64), ("query_end", C.c_int64)]
 
 
+class StoreSliceC(C.Structure):
+    """gqe_store_slice: one formula's slice of a device-resident query store (device pointers)."""
+    _fields_ = [("anchors", C.c_void_p), ("targets", C.c_void_p), ("neg_ptr", C.c_void_p), ("negs", C.c_void_p),
+                ("block_queries", C.c_int64), ("start", C.c_int64), ("pool_size", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/gqe.h declares.
 _P = C.c_void_p
 _SIGNATURES = {
@@ -107,6 +113,8 @@ _SIGNATURES = {
     "gqe_margin_loss_nodes_device": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
     "gqe_score_grouped_nodes_device": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.c_int64, _P, _P, C.c_int32, _P,
                                                  C.c_float, _P]),
+    "gqe_margin_loss_store_device": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.POINTER(StoreSliceC), C.c_uint64,
+                                               C.c_float, _P, _P, _P]),
     "gqe_score_nodes_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, C.c_int64, _P, _P, _P]),
     "gqe_margin_loss_nodes_host": (C.c_int, [_P, C.POINTER(Plan), C.c_int64, _P, _P, C.c_float, _P, _P]),
     "gqe_score_grouped_nodes_host": (C.c_int, [_P, C.POINTER(Segment), C.c_int32, C.c_int64, _P, _P, C.c_int32, _P,
@@ -331,6 +339,11 @@ class Context(object):
         fn = self._lib.gqe_score_grouped_nodes_device if nodes else self._lib.gqe_score_grouped_device
         self._check(fn(self._h, segments, len(segments), n_queries_total, anchor_rows, target_rows, targets_per_query,
                        out_scores, float(margin), out_loss))
+
+    def margin_loss_store_device(self, segments, slices, seed, margin, out_loss, out_scores=None, out_pairs=None):
+        """segments: gqe_segment array; slices: StoreSliceC array (same length); device pointers out."""
+        self._check(self._lib.gqe_margin_loss_store_device(self._h, segments, len(segments), slices, int(seed) & (2 ** 64 - 1),
+                                                           float(margin), out_loss, out_scores, out_pairs))
 
     # -- fused path, host buffers (numpy arrays) -----------------------------------
     def score_host(self, plan, anchor_rows, target_rows, target_offsets, out_scores, nodes=False):

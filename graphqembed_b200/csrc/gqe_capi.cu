@@ -327,6 +327,8 @@ static int index_error_from(gqe_ctx* c, unsigned long long w0, unsigned long lon
   const long long value = (long long)w1;
   if (kind == IDX_ERR_UNKNOWN_NODE)
     return fail(c, GQE_ERR_INDEX, "unknown node: id %lld is not in the node map of mode %d", value, mode);
+  if (kind == IDX_ERR_NO_NEGATIVE)
+    return fail(c, GQE_ERR_INDEX, "query %lld of the call has no negative sample to draw from", value);
   return fail(c, GQE_ERR_INDEX, "row index out of range: %lld is outside the table of mode %d", value, mode);
 }
 
@@ -752,6 +754,69 @@ extern "C" int gqe_score_grouped_nodes_device(gqe_ctx* c, const gqe_segment* seg
                    target_nodes, nullptr, targets_per_query, out_scores, margin, out_loss, 1);
 }
 
+// ---- device-resident query store ---------------------------------------------------
+enum { ST_ANCHOR = 0, ST_TARGET = 1, ST_OFFSETS = 2, ST_SCORES = 3, ST_LOSS = 4 };
+extern "C" int gqe_margin_loss_store_device(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs,
+                                            const gqe_store_slice* slices, uint64_t seed, float margin, float* out_loss,
+                                            float* out_scores, int32_t* out_pairs) {
+  if (!c) return GQE_ERR_INVALID;
+  if (!segs || !slices || n_segs <= 0) return fail(c, GQE_ERR_INVALID, "no segments");
+  if (!out_loss) return fail(c, GQE_ERR_INVALID, "gqe_margin_loss_store_device: out_loss is null");
+  if (c->node_maps.empty()) return fail(c, GQE_ERR_UNBOUND, "node maps are not bound (gqe_bind_node_maps)");
+  GQE_CUDA(c, cudaSetDevice(c->device));
+  int64_t nq = 0;
+  for (int32_t i = 0; i < n_segs; ++i) {
+    if (segs[i].query_begin < 0 || segs[i].query_end < segs[i].query_begin)
+      return fail(c, GQE_ERR_INVALID, "segment %d: bad query range", i);
+    nq = std::max<int64_t>(nq, segs[i].query_end);
+  }
+  if (nq == 0) {
+    GQE_CUDA(c, cudaMemsetAsync(out_loss, 0xff, sizeof(float), c->stream));   // mean of nothing: NaN, like torch
+    return GQE_OK;
+  }
+  int rc;
+  if ((rc = gqe_stage_reserve(c, ST_ANCHOR, sizeof(int32_t) * (size_t)GQE_MAX_ANCHORS * nq)) != GQE_OK) return rc;
+  if ((rc = gqe_stage_reserve(c, ST_TARGET, sizeof(int32_t) * (size_t)2 * nq)) != GQE_OK) return rc;
+  for (int32_t i0 = 0; i0 < n_segs; i0 += kMaxSegs) {
+    StoreBatchParams sp;
+    sp.count = 0;
+    sp.nq_total = nq;
+    sp.seed = seed;
+    sp.anchors_out = (int32_t*)c->stage[ST_ANCHOR];
+    sp.pairs_out = (int32_t*)c->stage[ST_TARGET];
+    sp.err = c->d_err;
+    int64_t max_n = 0;
+    for (int32_t i = i0; i < std::min<int32_t>(n_segs, i0 + kMaxSegs); ++i) {
+      const int64_t n = segs[i].query_end - segs[i].query_begin;
+      if (n == 0) continue;
+      const gqe_store_slice& g = slices[i];
+      const int na = n_anchors_of(segs[i].plan.structure);
+      if (na <= 0) return fail(c, GQE_ERR_INVALID, "segment %d: unknown query structure", i);
+      if (!g.anchors || !g.targets || !g.negs || g.start < 0 || g.start + n > g.block_queries)
+        return fail(c, GQE_ERR_INVALID, "segment %d: store slice [%lld,%lld) outside its block of %lld queries", i,
+                    (long long)g.start, (long long)(g.start + n), (long long)g.block_queries);
+      StoreSliceDev& d = sp.s[sp.count++];
+      d.anchors = g.anchors; d.targets = g.targets; d.neg_ptr = g.neg_ptr; d.negs = g.negs;
+      d.block_q = g.block_queries; d.start = g.start; d.n = n; d.out_q0 = segs[i].query_begin; d.pool_n = g.pool_size;
+      d.n_anchor = na;
+      d.tgt_mode = segs[i].plan.target_mode;
+      max_n = std::max(max_n, n);
+    }
+    if (sp.count > 0) {
+      GQE_CUDA(c, launch_store_batch(sp, max_n, c->stream));
+      c->launches += 1;
+    }
+  }
+  if (out_pairs)
+    GQE_CUDA(c, cudaMemcpyAsync(out_pairs, c->stage[ST_TARGET], sizeof(int32_t) * (size_t)2 * nq, cudaMemcpyDeviceToDevice, c->stream));
+  else
+    c->idx_by_kernel = true;   // the scoring kernel, launched programmatically dependent, waits for the batch kernel itself
+  rc = run_fused(c, segs, n_segs, nq, (const int32_t*)c->stage[ST_ANCHOR], 2 * nq, (const int32_t*)c->stage[ST_TARGET], nullptr,
+                 2, out_scores, margin, out_loss, 1);
+  c->idx_by_kernel = false;
+  return rc;
+}
+
 // ---- host-buffer variants ------------------------------------------------------
 int gqe_stage_reserve(gqe_ctx* c, int slot, size_t bytes) {
   if (bytes <= c->stage_cap[slot]) return GQE_OK;
@@ -764,7 +829,6 @@ int gqe_stage_reserve(gqe_ctx* c, int slot, size_t bytes) {
   c->stage_cap[slot] = cap;
   return GQE_OK;
 }
-enum { ST_ANCHOR = 0, ST_TARGET = 1, ST_OFFSETS = 2, ST_SCORES = 3, ST_LOSS = 4 };
 static const size_t kInPlaceIndexBytes = [] {   // GQE_INPLACE_BYTES in the environment overrides (0 = always copy)
   const char* e = getenv("GQE_INPLACE_BYTES");
   return e ? (size_t)atoll(e) : (size_t)128 << 10;

@@ -29,6 +29,9 @@ cudaError_t launch_gather_rows(const float* table, const int32_t* rows, int64_t 
 // index arrays of a host call: mapped pinned host memory -> device staging, all ranges in ONE launch (gqe_rows.cu)
 cudaError_t launch_fetch_indices(const FetchParams& fp, cudaStream_t st);
 
+// batches out of a device-resident query store (gqe_rows.cu)
+cudaError_t launch_store_batch(const StoreBatchParams& sp, int64_t max_n, cudaStream_t st);
+
 // (query, target) pair scoring against stored query embeddings (gqe_pairs.cu)
 cudaError_t launch_score_pairs(int d, const PairParams& pp, int64_t n_pairs_total, cudaStream_t st);
 

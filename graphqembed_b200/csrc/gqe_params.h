@@ -227,6 +227,27 @@ struct FetchParams {
   int64_t n[kMaxFetch];           // 32-bit words
   int32_t count;
 };
+// gqe_store_batch: the slices of a device-resident query store gathered into the index arrays of a call,
+// with one negative drawn per query (gqe_margin_loss_store_device)
+struct StoreSliceDev {
+  const int32_t* anchors;   // [n_anchor][block_q] node ids
+  const int32_t* targets;   // [block_q]
+  const int64_t* neg_ptr;   // CSR offsets [block_q + 1], or null: every query draws from the pool negs[0 .. pool_n)
+  const int32_t* negs;
+  int64_t block_q, start, n, out_q0, pool_n;
+  int32_t n_anchor;
+  int32_t tgt_mode;         // for the error report
+};
+struct StoreBatchParams {
+  StoreSliceDev s[kMaxSegs];
+  int32_t count;
+  int64_t nq_total;
+  unsigned long long seed;
+  int32_t* anchors_out;     // [GQE_MAX_ANCHORS][nq_total]
+  int32_t* pairs_out;       // [nq_total][2]
+  unsigned long long* err;
+};
+enum { IDX_ERR_NO_NEGATIVE = 3 };
 // gqe_score_pairs: one formula segment's (query, target) pairs against stored query embeddings
 struct PairSeg {
   const float* tgt_table;

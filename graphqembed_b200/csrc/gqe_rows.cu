@@ -100,4 +100,45 @@ cudaError_t launch_fetch_indices(const FetchParams& fp, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// ---- batches out of a device-resident query store ------------------------------------------------
+// blockIdx.y = slice.  Query i of a slice: its anchors and its positive target are copied into the call's
+// concatenated index arrays, its negative is element floor(u * len) of its stored list, u = the upper 32 bits
+// of splitmix64(seed, position of the query in the call) / 2^32 (bias len / 2^32).  The reference draws with
+// random.choice per query (model.py:116-120): the same uniform distribution over the same lists.
+__device__ __forceinline__ uint32_t draw32(unsigned long long seed, unsigned long long pos) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (pos + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__global__ void __launch_bounds__(256) gqe_store_batch(const __grid_constant__ StoreBatchParams p) {
+  const StoreSliceDev& s = p.s[blockIdx.y];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = s.start + i, out = s.out_q0 + i;
+    for (int k = 0; k < s.n_anchor; ++k) p.anchors_out[(int64_t)k * p.nq_total + out] = __ldg(s.anchors + (int64_t)k * s.block_q + q);
+    const int32_t pos = __ldg(s.targets + q);
+    const uint32_t u = draw32(p.seed, (unsigned long long)out);
+    int32_t neg = pos;
+    if (s.neg_ptr) {
+      const int64_t lo = __ldg(s.neg_ptr + q), len = __ldg(s.neg_ptr + q + 1) - lo;
+      if (len > 0) neg = __ldg(s.negs + lo + (int64_t)(((unsigned long long)u * (unsigned long long)len) >> 32));
+      else report_index(p.err, IDX_ERR_NO_NEGATIVE, s.tgt_mode, (int32_t)out);
+    } else if (s.pool_n > 0) {
+      neg = __ldg(s.negs + (int64_t)(((unsigned long long)u * (unsigned long long)s.pool_n) >> 32));
+    } else {
+      report_index(p.err, IDX_ERR_NO_NEGATIVE, s.tgt_mode, (int32_t)out);
+    }
+    reinterpret_cast<int2*>(p.pairs_out)[out] = make_int2(pos, neg);
+  }
+}
+
+cudaError_t launch_store_batch(const StoreBatchParams& sp, int64_t max_n, cudaStream_t st) {
+  if (sp.count <= 0 || max_n <= 0) return cudaSuccess;
+  int64_t bx = (max_n + 255) / 256;
+  bx = bx > 64 ? 64 : bx;
+  gqe_store_batch<<<dim3((unsigned)bx, (unsigned)sp.count), 256, 0, st>>>(sp);
+  return cudaGetLastError();
+}
+
 }  // namespace gqe

@@ -26,7 +26,7 @@ from . import _lib
 from .lowering import lower_formula
 from .operators import DirectEncoder, SetIntersection, SimpleSetIntersection, _MetapathDecoder, _require_cuda
 from .query import QUERY_TYPES, QueryBatch
-from .store import StoreSlice
+from .store import DeviceSlice, StoreSlice
 
 
 class QueryEncoderDecoder(nn.Module):
@@ -65,6 +65,11 @@ class QueryEncoderDecoder(nn.Module):
         # the reference's own global-``random`` draws when reference_negatives is set
         self.negative_rng = None
         self.reference_negatives = False
+        # negatives of DeviceSlice batches are drawn on the GPU by a counter-based generator: the seed of call k
+        # is negative_seed + k (None: a random base taken once per model)
+        self.negative_seed = None
+        self._store_calls = 0
+        self._store_cache = {}  # descriptors of recent DeviceSlice calls: (key) -> (segments, slices, n, keep-alive)
         # training with optim.SparseRowAdam: table gradients as (row, gradient) pairs and a hook
         # called with the rows a differentiable forward is about to gather
         self.sparse_table_grads = False
@@ -331,6 +336,10 @@ class QueryEncoderDecoder(nn.Module):
             affs = self.forward(formula, queries, [q.target_node for q in queries])
             neg_affs = self.forward(formula, queries, neg_nodes)
             return torch.clamp(margin - (affs - neg_affs), min=0).mean()
+        if isinstance(queries, DeviceSlice):
+            if self._store_on_device():
+                return self._margin_loss_store([(formula, queries)], hard_negatives, margin)
+            queries = queries.host()        # training / no node maps on the device: the host arrays of the same slice
         if isinstance(queries, StoreSlice):
             if "inter" not in formula.query_type and hard_negatives:
                 raise Exception("Hard negative examples can only be used with intersection queries")
@@ -376,6 +385,10 @@ class QueryEncoderDecoder(nn.Module):
         the mean hinge over all queries of all slices (= the size-weighted mean of the per-formula
         losses).  What a loop over ``margin_loss`` costs per formula -- a host call, an H2D copy, a
         small kernel, a loss read -- is paid once."""
+        if items and all(isinstance(sl, DeviceSlice) for _, sl in items):
+            if self._store_on_device():
+                return self._margin_loss_store(items, hard_negatives, margin)
+            items = [(f, sl.host()) for f, sl in items]
         batches = []
         for formula, sl in items:
             if "inter" not in formula.query_type and hard_negatives:
@@ -383,6 +396,69 @@ class QueryEncoderDecoder(nn.Module):
             full = self._full_array(formula.target_mode) if formula.query_type == "1-chain" else None
             batches.append(sl.margin_batch(sl.draw_negatives(hard_negatives, full, self.negative_rng, self.reference_negatives)))
         return self.margin_loss_grouped(batches, margin)
+
+    # ---- device-resident store ---------------------------------------------------------
+    def _store_on_device(self):
+        """DeviceSlice batches run natively when this is a scoring call (no autograd graph wanted)
+        and the context holds the node maps (the store holds node ids)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._lists()[0]):
+            return False
+        self.context()
+        return bool(self._state[4])
+
+    def _full_device(self, mode):
+        cache = self.__dict__.setdefault("_full_dev", {})
+        t = cache.get(mode)
+        if t is None or t.device != self.device:
+            t = cache[mode] = torch.from_numpy(np.ascontiguousarray(self._full_array(mode), dtype=np.int32)).to(self.device)
+        return t
+
+    def _margin_loss_store(self, items, hard_negatives=False, margin=1, return_pairs=False, return_scores=False):
+        """[(formula, DeviceSlice)] -> loss (0-d device tensor) through gqe_margin_loss_store_device:
+        slices gathered and negatives drawn by one small kernel, the fused scoring kernel behind it."""
+        ctx = self.context()
+        key = (hard_negatives,) + tuple((f, id(sl.block), sl.start, sl.stop) for f, sl in items)
+        ent = self._store_cache.get(key)
+        if ent is None:
+            seg_items, q0, keep = [], 0, []
+            arr = (_lib.StoreSliceC * len(items))()
+            for i, (formula, sl) in enumerate(items):
+                if "inter" not in formula.query_type and hard_negatives:
+                    raise Exception("Hard negative examples can only be used with intersection queries")
+                if sl.block.anchors.device != self.device:
+                    raise ValueError("the store lives on %s, the model on %s" % (sl.block.anchors.device, self.device))
+                b = sl.block
+                arr[i].anchors, arr[i].targets = b.anchors.data_ptr(), b.targets.data_ptr()
+                arr[i].block_queries, arr[i].start, arr[i].pool_size = b.n, sl.start, 0
+                if hard_negatives:
+                    arr[i].neg_ptr, arr[i].negs = b.hard_ptr.data_ptr(), b.hards.data_ptr()
+                elif formula.query_type == "1-chain":     # any node of the target mode (model.py:118-119)
+                    pool = self._full_device(formula.target_mode)
+                    keep.append(pool)
+                    arr[i].neg_ptr, arr[i].negs, arr[i].pool_size = None, pool.data_ptr(), pool.numel()
+                else:
+                    arr[i].neg_ptr, arr[i].negs = b.neg_ptr.data_ptr(), b.negs.data_ptr()
+                seg_items.append((self.plan(formula), q0, q0 + len(sl)))
+                q0 += len(sl)
+                keep.append(b)
+            if len(self._store_cache) >= 64:
+                self._store_cache.clear()
+            ent = self._store_cache[key] = (_lib.make_segments(seg_items), arr, q0, keep)
+        segs, arr, nq, _ = ent
+        if self.negative_seed is None:
+            self.negative_seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0]) >> 1
+        seed = self.negative_seed + self._store_calls
+        self._store_calls += 1
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        pairs = torch.empty((nq, 2), dtype=torch.int32, device=self.device) if return_pairs else None
+        scores = torch.empty((nq, 2), dtype=torch.float32, device=self.device) if return_scores else None
+        ctx.margin_loss_store_device(segs, arr, seed, margin, loss.data_ptr(),
+                                     None if scores is None else scores.data_ptr(),
+                                     None if pairs is None else pairs.data_ptr())
+        self._check_indices(ctx, True)
+        if return_pairs or return_scores:
+            return loss, pairs, scores
+        return loss
 
     def margin_loss_grouped(self, batches, margin=1, return_scores=False):
         """One call for many formulas (the "full mix" workload): mean hinge over

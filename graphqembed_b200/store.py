@@ -20,6 +20,11 @@ same ``np.random.multinomial`` draw and the same wrapping window
 (train_helpers.py:96-105); negatives are uniform over the same stored lists
 (``reference_stream=True`` additionally consumes the global ``random`` stream exactly
 like ``random.choice`` per query, for bit-for-bit comparisons with the reference).
+
+``QueryStore.to_device(device)`` uploads every block once; slices of the resulting
+``DeviceQueryStore`` are descriptors of device memory, and ``margin_loss`` on them is one
+native call (``gqe_margin_loss_store_device``): a small kernel gathers the slices and draws the
+negatives on the GPU, the fused scoring kernel follows -- no index array crosses PCIe per step.
 """
 import pickle
 import random
@@ -67,6 +72,53 @@ class FormulaBlock(object):
 
     def all(self):
         return StoreSlice(self, 0, len(self))
+
+
+class DeviceBlock(object):
+    """A ``FormulaBlock`` uploaded to a GPU (torch int32 / int64 tensors; the host block stays
+    reachable as ``.host``)."""
+
+    __slots__ = ("formula", "host", "anchors", "targets", "neg_ptr", "negs", "hard_ptr", "hards", "n")
+
+    def __init__(self, block, device):
+        import torch
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.formula, self.host, self.n = block.formula, block, len(block)
+        self.anchors, self.targets = up(block.anchors), up(block.targets)
+        self.neg_ptr, self.negs = up(block.neg_ptr), up(block.negs if block.negs.size else np.zeros(1, np.int32))
+        self.hard_ptr, self.hards = up(block.hard_ptr), up(block.hards if block.hards.size else np.zeros(1, np.int32))
+
+    def __len__(self):
+        return self.n
+
+    def window(self, start, stop):
+        return DeviceSlice(self, int(start), int(stop))
+
+    def all(self):
+        return DeviceSlice(self, 0, self.n)
+
+
+class DeviceSlice(object):
+    """Queries [start, stop) of a ``DeviceBlock``: a descriptor, nothing is copied or drawn on the
+    host.  Accepted by ``QueryEncoderDecoder.margin_loss`` / ``margin_loss_mix``."""
+
+    __slots__ = ("block", "start", "stop")
+
+    def __init__(self, block, start, stop):
+        if not 0 <= start <= stop <= block.n:
+            raise IndexError("slice [%d, %d) outside a block of %d queries" % (start, stop, block.n))
+        self.block, self.start, self.stop = block, start, stop
+
+    def __len__(self):
+        return self.stop - self.start
+
+    @property
+    def formula(self):
+        return self.block.formula
+
+    def host(self):
+        """The same queries as a host ``StoreSlice``."""
+        return StoreSlice(self.block.host, self.start, self.stop)
 
 
 class StoreSlice(object):
@@ -171,6 +223,11 @@ class QueryStore(object):
     def __getitem__(self, formula):
         return self.blocks[formula]
 
+    def to_device(self, device):
+        """Upload every block once -> ``DeviceQueryStore`` (same sampling interface; its slices
+        never touch host memory again)."""
+        return DeviceQueryStore(self, device)
+
     # ---- construction ---------------------------------------------------------
     @classmethod
     def from_records(cls, records, select=None):
@@ -218,3 +275,15 @@ class QueryStore(object):
         which = int(np.argmax(np.random.multinomial(1, sizes / sizes.sum())))
         block = self.blocks[formulas[which]]
         return block.window(*batch_window(iter_count, batch_size, len(block)))
+
+
+class DeviceQueryStore(QueryStore):
+    """A ``QueryStore`` whose blocks live in GPU memory (``QueryStore.to_device``).  ``sample_batch``
+    draws the formula exactly like the host store (same ``np.random.multinomial`` call) and returns
+    a ``DeviceSlice``."""
+
+    def __init__(self, store, device):
+        self.host = store
+        self.device = device
+        self.blocks = {f: DeviceBlock(b, device) for f, b in store.blocks.items()}
+        self.by_type = {t: list(fs) for t, fs in store.by_type.items()}

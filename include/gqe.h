@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GQE_ABI_VERSION 5
+#define GQE_ABI_VERSION 6
 #define GQE_MAX_ANCHORS 3
 #define GQE_MAX_RELS 3
 
@@ -273,6 +273,36 @@ int gqe_score_grouped_nodes_device(gqe_ctx* ctx, const gqe_segment* segments, in
                                    int64_t n_queries_total, const int32_t* anchor_nodes,
                                    const int32_t* target_nodes, int32_t targets_per_query,
                                    float* out_scores, float margin, float* out_loss);
+
+/* Margin loss straight from a DEVICE-RESIDENT query store: what replaces, per training / evaluation-loss step,
+ * the batch slicing of netquery/train_helpers.py:95-107 and the per-query random.choice of the negative
+ * target (netquery/model.py:113-120) -- no index array crosses PCIe.  A store block is one formula's queries as
+ * flat arrays uploaded once (graphqembed_b200/store.py); slice i supplies the queries of segments[i]:
+ *   anchors        DEVICE int32 [n_anchor][block_queries], slot-major node ids of the whole block
+ *   targets        DEVICE int32 [block_queries] positive target node ids
+ *   neg_ptr, negs  DEVICE CSR (int64 [block_queries + 1], int32 values): the stored (or hard) negatives of every
+ *                  query; or neg_ptr == NULL and negs = a pool of pool_size candidates every query draws from
+ *                  (1-chain: every node of the target mode, model.py:118-119)
+ *   start          first query of the slice inside the block; its length is the segment's query range
+ * One kernel gathers the slices into the call's index arrays and draws, per query, one negative uniformly
+ * from its list (counter-based generator: query position and `seed` -> the same draw whatever the launch
+ * shape; pass a new seed every step); the fused scoring kernel follows in the same stream.  A query without
+ * negatives is reported as GQE_ERR_INDEX (gqe_index_error), like the reference's IndexError.
+ *   out_loss    DEVICE fp32 [1];  out_scores DEVICE fp32 [n_queries_total][2] or NULL
+ *   out_pairs   DEVICE int32 [n_queries_total][2] or NULL: the (positive, negative) node ids that were scored
+ * Needs gqe_bind_node_maps (the store holds node ids). */
+typedef struct gqe_store_slice {
+  const int32_t* anchors;
+  const int32_t* targets;
+  const int64_t* neg_ptr;
+  const int32_t* negs;
+  int64_t block_queries;
+  int64_t start;
+  int64_t pool_size;
+} gqe_store_slice;
+int gqe_margin_loss_store_device(gqe_ctx* ctx, const gqe_segment* segments, int32_t n_segments,
+                                 const gqe_store_slice* slices, uint64_t seed, float margin,
+                                 float* out_loss, float* out_scores, int32_t* out_pairs);
 
 /* Host-buffer variants: same semantics, HOST index arrays in, HOST results
  * out; the H2D / D2H copies and a stream synchronise happen inside the call.

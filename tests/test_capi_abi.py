@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), "libgqe_b200.so does not export %s" % n
     assert set(names) == set(_lib.EXPORTED_SYMBOLS)
-    assert lib.gqe_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.gqe_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_struct_layouts_match_header():
