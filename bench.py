@@ -503,6 +503,53 @@ def measure_python_surface(args, tm, res, steps=20):
         step_mix()
         model.context().index_error()
     mix_ms = (time.perf_counter() - t0) * 1e3 / steps
+    # the same store uploaded once (QueryStore.to_device): batches sliced and negatives drawn on the GPU
+    from graphqembed_b200.store import DeviceBlock
+    dblocks = [DeviceBlock(blk, device) for blk in blocks]
+    model.negative_seed = 2024
+
+    def step_dev_store():
+        with torch.no_grad():
+            return float(model.margin_loss_mix([(blk.formula, blk.all()) for blk in dblocks]))
+    for _ in range(3):
+        step_dev_store()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tm.flush.zero_()
+        torch.cuda.synchronize(device)
+        step_dev_store()
+        model.context().index_error()
+    # (the flush + synchronise are inside this loop as in Timed.host_ms; subtract nothing: an upper bound)
+    dev_store_ms = (time.perf_counter() - t0) * 1e3 / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tm.flush.zero_()
+        torch.cuda.synchronize(device)
+    flush_ms = (time.perf_counter() - t0) * 1e3 / steps
+    dev_store_ms -= flush_ms
+    # the reference's training batch: ONE formula, 512 queries (train_helpers.py:95-107), host time per call
+    small = dblocks[0].window(0, min(512, len(dblocks[0])))
+    with torch.no_grad():
+        for _ in range(20):
+            model.margin_loss(small.formula, small)
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        n_small = 300
+        for _ in range(n_small):
+            model.margin_loss(small.formula, small)
+        small_host_us = (time.perf_counter() - t0) * 1e6 / n_small
+        torch.cuda.synchronize(device)
+        small_us = (time.perf_counter() - t0) * 1e6 / n_small
+        small_h = blocks[0].window(0, len(small))
+        for _ in range(20):
+            model.margin_loss(small.formula, small_h)
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(n_small):
+            model.margin_loss(small.formula, small_h)
+        torch.cuda.synchronize(device)
+        small_h_us = (time.perf_counter() - t0) * 1e6 / n_small
     # lists of Query objects
     qlists = []
     for blk in blocks:
@@ -527,6 +574,19 @@ def measure_python_surface(args, tm, res, steps=20):
                                     "ms_per_step": round(mix_ms, 4),
                                     "call": "QueryEncoderDecoder.margin_loss_mix([(formula, StoreSlice)] x %d): the same in ONE "
                                             "grouped launch" % len(blocks)},
+            "from_device_store": {"value": round(wl.n_queries / (dev_store_ms * 1e-3), 1), "unit": UNIT,
+                                  "ms_per_step": round(dev_store_ms, 4), "h2d_bytes_per_step": 0,
+                                  "call": "QueryEncoderDecoder.margin_loss_mix([(formula, DeviceSlice)] x %d) on a store "
+                                          "uploaded once (QueryStore.to_device): gqe_margin_loss_store_device = batch "
+                                          "slicing + negative draw in one kernel, then the fused kernel; loss read "
+                                          "back" % len(blocks),
+                                  "batch_512": {"us_per_call_device_store": round(small_us, 1),
+                                                "us_per_call_device_store_host_side": round(small_host_us, 1),
+                                                "us_per_call_host_store": round(small_h_us, 1),
+                                                "what": "margin_loss(formula, slice of 512 queries), back-to-back calls, "
+                                                        "check_indices off: wall time per call incl. the final "
+                                                        "synchronise / CPU time until the call returns / the same slice "
+                                                        "as host arrays (vectorised draw + pinned H2D)"}},
             "from_query_objects": {"value": round(wl.n_queries / (obj_ms * 1e-3), 1), "unit": UNIT,
                                    "ms_per_step": round(obj_ms, 4),
                                    "call": "QueryEncoderDecoder.margin_loss(formula, [Query]) x %d formulas: the reference's "

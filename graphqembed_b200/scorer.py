@@ -403,7 +403,8 @@ class QueryEncoderDecoder(nn.Module):
         and the context holds the node maps (the store holds node ids)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._lists()[0]):
             return False
-        self.context()
+        if self._state is None:
+            self.context()
         return bool(self._state[4])
 
     def _full_device(self, mode):
