@@ -108,6 +108,7 @@ extern "C" void gqe_destroy(gqe_ctx* c) {
   cudaFree(c->partials);
   cudaFree(c->packed);
   cudaFree(c->qbuf);
+  cudaFree(c->stage_buf);
   cudaFree(c->compose_buf);
   cudaFree(c->loss_acc);
   cudaFree(c->d_err);
@@ -375,6 +376,14 @@ static int ensure_weight_buffers(gqe_ctx* c) {
 // The one launcher behind every fused entry point.  index_kind: 0 = the index arrays hold table
 // rows, 1 = node ids (mapped through gqe_bind_node_maps inside the kernels).  err_host: mapped
 // pinned word the last CTA copies the index-error word to (the *_host calls), or null.
+static const bool kStageRemote = [] {
+  const char* e = getenv("GQE_STAGE");
+  return e ? atoi(e) != 0 : true;
+}();
+static const int kForceStage = [] {
+  const char* e = getenv("GQE_FORCE_STAGE");
+  return e ? atoi(e) : 0;
+}();
 static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_t nq_total,
                      const int32_t* anchor_rows, int64_t n_pairs, const int32_t* target_rows,
                      const int64_t* target_offsets, int32_t T, float* out_scores, float margin, float* out_loss,
@@ -639,6 +648,33 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
         GQE_CUDA(c, launch_pack(c->d, pp, n_pack, c->stream));
         c->launches += 1;
         c->weight_preps += n_pack;
+      }
+      // Node-type-sharded tables (some operand rows live in a peer GPU's HBM), grouped d = 256 kernel: the
+      // instantiation whose helper warps fetch those rows into a local staging area a tile or two ahead
+      // (GQE_STAGE=0: gather them in place as round 1 did; GQE_FORCE_STAGE=1: treat every table as remote --
+      // a single-GPU test of the mechanism)
+      lp.stage_on = 0;
+      if (kStageRemote && c->d == 256 && structure < 0 && !lp.pair) {
+        bool any = kForceStage >= 2;      // 2: the STAGE instantiation with nothing to stage (its fixed cost)
+        for (int k = 0; k < n; ++k) {
+          if (kForceStage == 1) lp.seg[k].remote_mask = 0xFu;
+          any = any || lp.seg[k].remote_mask != 0;
+        }
+        if (any) {
+          int sms = 148;
+          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+          const size_t need = (size_t)sms * tc_stage_bytes_per_cta(c->d);
+          if (c->stage_buf_cap < need) {
+            GQE_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->stage_buf);
+            c->stage_buf = nullptr;
+            c->stage_buf_cap = 0;
+            GQE_CUDA(c, cudaMalloc(&c->stage_buf, need));
+            c->stage_buf_cap = need;
+          }
+          lp.stage = c->stage_buf;
+          lp.stage_on = kForceStage == 3 ? 2 : 1;   // 3: the STAGE instantiation with its helper warp idle (diagnostics)
+        }
       }
       // indices fetched by gqe_fetch_indices right in front of this launch: the kernel waits for it itself
       // (with weight preparation in between, the ordinary stream order has already done that)

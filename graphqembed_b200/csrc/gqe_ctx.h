@@ -60,6 +60,10 @@ struct gqe_ctx {
   unsigned long long* h_err = nullptr;
   unsigned long long* h_err_dev = nullptr;
 
+  // staging area of the fused kernel's helper warps (rows of peer GPUs' tables, node-type-sharded tables)
+  float* stage_buf = nullptr;
+  size_t stage_buf_cap = 0;
+
   // a *_host call copied its index arrays with gqe_fetch_indices: the next tensor-core launch waits for that
   // kernel itself (LaunchParams::wait_prev)
   bool idx_by_kernel = false;

@@ -77,6 +77,8 @@ cudaError_t launch_compose(int d, const ComposeParams& cp, int n_entries, cudaSt
 int score_col_src_host(int n);   // tc::score_col_src (gqe_tc.cuh) for the host side
 
 inline bool tc_dim_supported(int d) { return d == 128 || d == 256; }
+// staging area of the STAGE instantiation of the fused kernel (d = 256, grouped kernel): bytes per CTA
+inline size_t tc_stage_bytes_per_cta(int d) { return (size_t)4 * 5 * 128 * d * sizeof(float); }
 // CTA pairs sharing the weight stream (gqe_tc.cuh, PAIR): an experiment, on only with GQE_PAIR=1 in the environment
 int tc_use_pair(int d, int64_t tiles);
 inline size_t tc_packed_bytes(int d) { return (size_t)4 * d * d; }

@@ -169,6 +169,8 @@ struct LaunchParams {
   unsigned long long* err;      // DEVICE [2]: (kind << 32 | mode, offending value) of the first bad index
   unsigned long long* err_host; // mapped pinned copy written by the last CTA of a *_host call, or null
   int32_t pair;                 // tensor-core path: launched as clusters of two CTAs (tiles padded to pairs per segment)
+  int32_t stage_on;             // tensor-core path (STAGE kernel): helper warps copy rows of peer GPUs' tables into `stage`
+  float* stage;                 // [CTAs][4 tiles][5 operands][128 rows][d] fp32, local memory
   int32_t wait_prev;            // tensor-core path: the index arrays are written by the kernel in front of this one in
                                 // the stream (gqe_fetch_indices): every thread waits for it before its first index load
   ModeDev mode[kMaxModes];

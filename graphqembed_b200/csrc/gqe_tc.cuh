@@ -51,6 +51,16 @@ struct Cfg {
   static constexpr int kWorkerWarps = 4 * kColGroups;  // 4 TMEM lane quarters x column groups
   static constexpr int kWorkerThreads = kWorkerWarps * 32;
   static constexpr int kThreads = kWorkerThreads + 64;
+  // STAGE instantiation (node-type-sharded tables, d = 256): one more warp -- a CTA's 18 warps are allocated
+  // as 20 anyway -- that fetches the rows of the NEXT tiles from PEER GPUs into a local staging area while the
+  // current tile is worked on (helper()).  It moves rows with TMA bulk copies through the third weight stage's
+  // 32 KiB of shared memory (the weight ring of this instantiation has two stages): kStageRingRows rows in flight
+  static constexpr int kHelperWarps = 1;
+  static constexpr int kStageRingRows = 32;
+  static_assert(kStageRingRows * D * 4 <= D * 128, "the helper's row ring lives in one weight stage");
+  static constexpr int kStageOps = 5;      // staged operands of a tile: first gather, anchors 1, 2, scoring rows 0, 1
+  static constexpr int kStageDepth = 4;    // tiles a staged row set stays valid for (ring look-ahead 2 + deferred chain score)
+  static constexpr size_t kStageFloatsPerCta = (size_t)kStageDepth * kStageOps * kRows * D;
   static constexpr int kKB = D / kKBlock;
   static constexpr int kABlockBytes = kRows * 128;     // one 64-wide K block of the A tile
   static constexpr int kAPlaneBytes = kKB * kABlockBytes;
@@ -59,7 +69,7 @@ struct Cfg {
   static constexpr int kOffAlo = kAPlaneBytes;
   static constexpr int kOffB = 2 * kAPlaneBytes;
   static constexpr int kOffCtl = kOffB + kStages * kStageBytes;
-  static constexpr int kCtlBytes = 512;
+  static constexpr int kCtlBytes = 1024;
   static constexpr int kOffScratch = kOffCtl + kCtlBytes;  // [128 rows][3] fp32 partial sums (score_frag)
   static constexpr int kScratchBytes = kRows * 3 * 4;
   static constexpr int kSmemBytes = kOffScratch + kScratchBytes;
@@ -70,8 +80,8 @@ struct Cfg {
 };
 
 struct Ctl {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kStages + 1];    // (the STAGE instantiation runs a ring of four half stages)
+  uint64_t empty[kStages + 1];
   uint64_t a_ready;
   uint64_t acc_full;
   uint64_t sched_full[2];   // tile-id ring: scheduler (producer thread) -> workers, MMA issuer
@@ -81,8 +91,10 @@ struct Ctl {
   uint32_t tmem_base;
   int last;
   uint8_t bad[32];          // per worker warp: bit 0 = a lane saw a bad index in this tile, bit 1 = in the carried row
+  uint64_t stage_ready[4][5];   // STAGE: helper warp -> workers: staged operand o of tile (k mod 4) has landed
+  uint64_t row_bar[32];         // STAGE: TMA completion of the helper's row-ring slots
 };
-static_assert(sizeof(Ctl) <= 512, "control block");
+static_assert(sizeof(Ctl) <= 1024, "control block");
 
 // (the per-structure program -- Prog, build_program, the G_* / M_* / E_* / F_* codes -- lives in
 // gqe_params.h: the host builds it once per formula into SegDev::prog)
@@ -97,6 +109,27 @@ __device__ __forceinline__ float4 ld_row(const float4* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
+}
+
+// the same from the staging area the helper warps fill while this kernel runs: through L2, never the
+// non-coherent path, never L1 (a staging slot is rewritten every four tiles)
+__device__ __forceinline__ float4 ld_row_staged(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// Which operands of a tile are fetched from a peer GPU by the helper warps (bit o of the result; the
+// workers and the helpers evaluate this for every tile of the CTA, in the same order):
+//   o = 0 first gather (chain: targets, else anchor 0)   1, 2 anchors 1, 2   3, 4 scoring rows (chain:
+//   anchor 0; else the two targets)
+// The CTA's FIRST tile (kseq = 0) is gathered in place: nothing could have been fetched ahead of it, and the
+// workers' own 64 KiB in flight beat the helper's 32 on a single operand.
+__device__ __forceinline__ uint32_t staged_ops(uint32_t kseq, bool chain, uint32_t rm, int n_branch, int T, bool q_out) {
+  if (kseq == 0) return 0u;
+  if (chain) return ((rm & 8u) ? 1u : 0u) | ((rm & 1u) ? 8u : 0u);
+  uint32_t m = (rm & 1u) | (rm & 2u) | ((n_branch > 2 && (rm & 4u)) ? 4u : 0u);
+  if ((rm & 8u) && !q_out && T <= 2) m |= 8u | (T > 1 ? 16u : 0u);
+  return m;
 }
 
 // ---- small math helpers -----------------------------------------------------------
@@ -134,7 +167,7 @@ __device__ __forceinline__ uint32_t a_chunk_off(int r, int kb, int c) {
 // (Measured: 8 rows in flight at d = 256 -- as a non-inlined function, so that the loads do not
 // spill -- is SLOWER, 4.4 us per gather against 3.6: the phase is not bound by the loads a warp
 // has in flight.)
-template <int D>
+template <int D, bool STAGED = false>
 __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restrict__ table, int32_t my_row, int wid,
                                             int lane) {
   using C = Cfg<D>;
@@ -152,7 +185,8 @@ __device__ __forceinline__ void gather_to_a(uint8_t* smem, const float* __restri
       okv[u] = row >= 0;
       const float4* src = reinterpret_cast<const float4*>(table + (size_t)(okv[u] ? row : 0) * D);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[u][j] = okv[u] ? ld_row(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NV; ++j)
+        v[u][j] = okv[u] ? (STAGED ? ld_row_staged(src + lane + 32 * j) : ld_row(src + lane + 32 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -347,6 +381,8 @@ struct PendTile {
   int32_t n_valid;
   uint32_t region;      // TMEM region (0 / 1) holding the tile's final accumulator
   bool valid;
+  uint32_t stage_info;  // STAGE: 0, or `table` is the tile's staging slot and idx = positions: bit 0 set, bit 1 = the parity
+                        // of stage_ready[slot][3] to wait for, bits 2-3 = slot
 };
 
 // this thread's two accumulator rows in the fragment layout
@@ -354,10 +390,12 @@ __device__ __forceinline__ int frag_row(int wid, int lane, int rs) {
   return 32 * (wid & 3) + 16 * ((wid >> 2) & 1) + (lane >> 2) + 8 * rs;
 }
 
-template <int D>
+template <int D, bool STAGE = false>
 __device__ __forceinline__ void score_frag(const LaunchParams& p, Ctl* ctl, float* scratch, uint32_t tmem_base,
                                            const PendTile& pt, int wid, int lane) {
   using C = Cfg<D>;
+  const bool st_rows = STAGE && pt.stage_info != 0;
+  if (st_rows) ptx::mbar_wait(ptx::smem_u32(&ctl->stage_ready[(pt.stage_info >> 2) & 3u][3]), (pt.stage_info >> 1) & 1u);
   constexpr int NCH = C::kColGroups / 2;   // warps sharing one 16-lane half (1 at d=128, 2 at d=256)
   constexpr int COLS = D / NCH;            // columns per warp (128)
   const int ch = wid >> 3;
@@ -383,7 +421,9 @@ __device__ __forceinline__ void score_frag(const LaunchParams& p, Ctl* ctl, floa
       for (int rs = 0; rs < 2; ++rs)
 #pragma unroll
         for (int b = 0; b < 2; ++b)
-          av[r][rs][b] = ok[rs] ? ld_row(reinterpret_cast<const float4*>(pr[rs] + 32 * (c + r) + 16 * b)) : zero4;
+          av[r][rs][b] = ok[rs] ? (st_rows ? ld_row_staged(reinterpret_cast<const float4*>(pr[rs] + 32 * (c + r) + 16 * b))
+                                           : ld_row(reinterpret_cast<const float4*>(pr[rs] + 32 * (c + r) + 16 * b)))
+                                : zero4;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       uint32_t raw[16];
@@ -513,7 +553,7 @@ __device__ __noinline__ void diagnose_indices(const LaunchParams& p, const SegDe
 }
 
 // ---- worker warps ---------------------------------------------------------------------
-template <int D, int STRUCT>
+template <int D, int STRUCT, bool STAGE = false>
 __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
   constexpr int NCH = C::kColsPerThread / 16;      // 16-column TMEM chunks per thread
@@ -595,6 +635,19 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     const bool mine = lane < RPW && my_r < n_valid;
     const uint32_t rm = s.remote_mask;
     const int ik = p.index_kind;
+    // STAGE: the operands of this tile that the helper warps fetch from peer GPUs into the CTA's staging slot
+    // (tile number kseq of this CTA; the helpers count the same way) -- read from there, by POSITION in the tile
+    // (all of it recomputed where it is used: nothing here stays live across the tile.)  The helper arrives on
+    // EVERY stage_ready[k mod 4][o] once per tile, staged or not, so the parity to wait for is bit 2 of k.
+    auto staged = [&](int o) -> bool {
+      return STAGE && p.stage_on == 1 && ((staged_ops(ring.k - 1, chain, rm, n_branch, T, p.q_out != nullptr) >> o) & 1u);
+    };
+    auto stage_ptr = [&](int o) -> const float* {
+      return p.stage + (((size_t)blockIdx.x * C::kStageDepth + ((ring.k - 1) & 3u)) * C::kStageOps + (size_t)o) * (size_t)(kRows * D);
+    };
+    auto stage_wait = [&](int o) {
+      ptx::mbar_wait(ptx::smem_u32(&ctl->stage_ready[(ring.k - 1) & 3u][o]), ((ring.k - 1) >> 2) & 1u);
+    };
 #define m_tgt (s.tgt_mode)
 #define m_a0 (s.anc_mode[0])
 #define m_a1 (s.anc_mode[1])
@@ -628,10 +681,15 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     }
     PendTile cur;
     cur.valid = false;
+    cur.stage_info = 0;
     if (frag) {
       cur.tile = tile; cur.row_begin = row_begin; cur.n_valid = n_valid; cur.region = region;
       cur.valid = true;
       cur.table = s.anc_table[0];
+      if (staged(3)) {     // the anchor rows come from the staging slot (awaited in score_frag)
+        cur.table = stage_ptr(3);
+        cur.stage_info = 1u | ((((ring.k - 1) >> 2) & 1u) << 1) | (((ring.k - 1) & 3u) << 2);
+      }
 #pragma unroll
       for (int rs = 0; rs < 2; ++rs) {
         const int r = frag_row(wid, lane, rs);
@@ -642,7 +700,11 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     for (int st = 0; st < pg.n; ++st, ++gs) {
       const int g = pg.gather[st];
       if (g != G_NONE) {
-        if (g == G_TARGET) gather_to_a<D>(smem, s.tgt_table, gsrc0, wid, lane);
+        const int so = g == G_TARGET ? 0 : g;      // staging operand of this gather
+        if (staged(so)) {
+          stage_wait(so);
+          gather_to_a<D, true>(smem, stage_ptr(so), mine ? my_r : -1, wid, lane);
+        } else if (g == G_TARGET) gather_to_a<D>(smem, s.tgt_table, gsrc0, wid, lane);
         else gather_to_a<D>(smem, s.anc_table[g], g == 0 ? gsrc0 : (g == 1 ? gsrc1 : gsrc2), wid, lane);
         stamp(2);
       }
@@ -690,7 +752,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
         // ... the score of the previous tile, straight from its TMEM region ...
         if (pend.valid) {
           stamp(9);
-          score_frag<D>(p, ctl, scratch, tmem_base, pend, wid, lane);
+          score_frag<D, STAGE>(p, ctl, scratch, tmem_base, pend, wid, lane);
           pend.valid = false;
           stamp(8);
         }
@@ -715,6 +777,8 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           for (int rs = 0; rs < 2; ++rs) {
             const int32_t c = cur.idx[rs];   // (the same anchor indices were checked through ssrc0 above)
             cur.idx[rs] = (uint32_t)c < p.mode[m_a0].rows ? c : 0;
+            // staged: the position in the tile instead (rows 2i, 2i+1 of a (pos, neg) pair share the anchor of 2i)
+            if (STAGE && cur.stage_info) cur.idx[rs] = T == 2 ? (frag_row(wid, lane, rs) & ~1) : frag_row(wid, lane, rs);
           }
         }
         // ... and the first-gather rows of the NEXT tile, carried into it in a register, so that
@@ -808,7 +872,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
       if (ring_tile(ring.peek(ctl, 0)) < p.n_tiles) {
         pend = cur;
       } else {
-        score_frag<D>(p, ctl, scratch, tmem_base, cur, wid, lane);
+        score_frag<D, STAGE>(p, ctl, scratch, tmem_base, cur, wid, lane);
         stamp(6);
       }
       stamp(7);
@@ -847,6 +911,11 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     } else {
       constexpr int SU = 4 / NV;
       static_assert(RPW % SU == 0, "score batch");
+      const bool st3 = staged(3);     // the target rows come from the staging slot
+      if (st3) {
+        stage_wait(3);
+        if (staged(4)) stage_wait(4);
+      }
 #pragma unroll 1
       for (int u0 = 0; u0 < RPW; u0 += SU) {
         float4 ta[SU][NV], tb[SU][NV];
@@ -858,10 +927,15 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
           const bool ok = ra[u] >= 0;
           const float4* a_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)(ok ? ra[u] : 0) * D);
           const float4* b_src = reinterpret_cast<const float4*>(s.tgt_table + (size_t)(ok ? (T > 1 ? rb : ra[u]) : 0) * D);
+          if (st3) {
+            const size_t pos = (size_t)(wid * RPW + u0 + u);
+            a_src = reinterpret_cast<const float4*>(stage_ptr(3) + pos * D);
+            b_src = reinterpret_cast<const float4*>(stage_ptr(T > 1 ? 4 : 3) + pos * D);
+          }
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
-            ta[u][j] = ok ? ld_row(a_src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            tb[u][j] = ok ? ld_row(b_src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ta[u][j] = ok ? (st3 ? ld_row_staged(a_src + lane + 32 * j) : ld_row(a_src + lane + 32 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tb[u][j] = ok ? (st3 ? ld_row_staged(b_src + lane + 32 * j) : ld_row(b_src + lane + 32 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         float red[SU][5];  // |q|^2, q.a, |a|^2, q.b, |b|^2
@@ -938,9 +1012,99 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 #undef m_a0
 #undef m_a1
 #undef m_a2
-  if (pend.valid) score_frag<D>(p, ctl, scratch, tmem_base, pend, wid, lane);  // (never: a deferred tile has a successor)
+  if (pend.valid) score_frag<D, STAGE>(p, ctl, scratch, tmem_base, pend, wid, lane);  // (never: a deferred tile has a successor)
   if (threadIdx.x == 0) cta_stamp(p, 3);
   loss_finish<D>(p, ctl, smem, wid, lane);
+}
+
+// ---- STAGE: helper warp -----------------------------------------------------------------
+// Node-type-sharded tables: rows that live in a PEER GPU's HBM cost an NVLink round trip (~2-3 us) per
+// dependent load, cannot be prefetched into the local L2 (peer lines bypass it), and the workers have only a
+// few rows in flight -- the first remote gather of every tile was exposed.  The helper
+// warp consumes the tile ring like the workers, but as early as the scheduler publishes a tile (up to two
+// tiles ahead of the workers), and copies every REMOTE operand row of that tile into the CTA's staging slot in
+// local memory, by position in the tile.  Registers cannot hold enough rows in flight for that (8 rows per
+// warp at this kernel's 96 registers, and spilling serialises the loads), so the rows travel by TMA: lane i
+// owns slot i of a 32-row ring in shared memory (the third weight stage), fetches its row with cp.async.bulk
+// (peer -> shared, completion on the slot's mbarrier) and writes it on with a bulk store (shared -> the local
+// staging area): 32 KiB in flight per SM, 4.7 MB per GPU -- the link's bandwidth-delay product twice over.
+// The workers then gather those operands from the staging slot (L2 hits, ld.global.cg) after waiting on
+// stage_ready[slot][operand].  Index resolution is the workers' own (raw index -> node map -> bounds check, a
+// bad index reads row 0; reporting stays with the workers).  Chain anchors of (pos, neg) pairs are fetched
+// once per pair.
+template <int D, int STRUCT>
+__device__ __forceinline__ void helper(const LaunchParams& p, uint8_t* smem, Ctl* ctl, int lane) {
+  using C = Cfg<D>;
+  constexpr int NG = kRows / 32;                    // groups of 32 rows per operand
+  constexpr uint32_t kRowBytes = D * 4;
+  const int T = p.T, ik = p.index_kind;
+  const uint32_t my_slot = ptx::smem_u32(smem + C::kOffB + 2 * C::kStageBytes) + (uint32_t)lane * kRowBytes;
+  const uint32_t my_bar = ptx::smem_u32(&ctl->row_bar[lane]);
+  uint32_t my_phase = 0;
+  uint32_t k = 0;
+  for (;; ++k) {
+    ptx::mbar_wait(ptx::smem_u32(&ctl->sched_full[k & 1]), (k >> 1) & 1);
+    const int64_t tile_v = *reinterpret_cast<volatile int64_t*>(&ctl->tile_id[k & 1]);
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->sched_empty[k & 1]));
+    const int64_t tile = ring_tile(tile_v);
+    if (tile >= p.n_tiles) break;
+    const SegDev& s = p.seg[ring_seg(tile_v)];
+    const bool chain = (STRUCT >= 0 ? STRUCT : s.structure) <= GQE_CHAIN3;
+    const int64_t row_begin = (chain ? s.q_begin * T : s.q_begin) + (tile - s.tile_begin) * kRows;
+    const int64_t row_end = chain ? s.q_end * T : s.q_end;
+    const int n_valid = (int)min((int64_t)kRows, row_end - row_begin);
+    const uint32_t sops = staged_ops(k, chain, s.remote_mask, s.n_anchor, T, p.q_out != nullptr);
+    float* slot = p.stage + ((size_t)blockIdx.x * C::kStageDepth + (k & 3u)) * (size_t)(C::kStageOps * kRows * D);
+#pragma unroll 1
+    for (int o = 0; o < C::kStageOps; ++o) {
+      if (!((sops >> o) & 1u)) {   // nothing to fetch: the barrier still completes once per tile (the workers' parity rule)
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->stage_ready[k & 3u][o]));
+        continue;
+      }
+      const bool from_targets = chain ? (o == 0) : (o >= 3);
+      const int ak = (chain || o >= 3) ? 0 : o;
+      const int mode = from_targets ? s.tgt_mode : s.anc_mode[ak];
+      const float* table = from_targets ? s.tgt_table : s.anc_table[ak];
+      const bool dedupe = chain && o == 3 && T == 2;
+      // the rows of the whole operand first (two dependent local loads each), then the copies
+      int32_t row[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int r = 32 * g + lane;
+        row[g] = -1;
+        if (r < n_valid && !(dedupe && (r & 1))) {
+          int32_t raw;
+          if (chain) raw = o == 0 ? __ldg(p.target_rows + row_begin + r)
+                                  : __ldg(p.anchor_rows + (T == 2 ? (row_begin + r) >> 1 : (row_begin + r) / T));
+          else raw = o < 3 ? __ldg(p.anchor_rows + (int64_t)o * p.anchor_stride + row_begin + r)
+                           : __ldg(p.target_rows + (row_begin + r) * T + (o - 3));
+          const int32_t cand = index_lookup(p.mode[mode], raw, ik);
+          row[g] = (uint32_t)cand < p.mode[mode].rows ? cand : 0;
+        }
+      }
+      float* dst_op = slot + (size_t)o * kRows * D;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if (row[g] < 0) continue;
+        // the bulk store that last read this lane's ring slot has finished reading it
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        ptx::mbar_arrive_expect_tx(my_bar, kRowBytes);
+        ptx::tma_bulk_g2s(my_slot, table + (size_t)row[g] * D, kRowBytes, my_bar);
+        ptx::mbar_wait(my_bar, my_phase);
+        my_phase ^= 1u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_op + (size_t)(32 * g + lane) * D),
+                     "r"(my_slot), "r"(kRowBytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      // every store of this operand has landed in the staging slot: hand it to the workers
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->stage_ready[k & 3u][o]));
+    }
+  }
 }
 
 // ---- TMA producer + tile scheduler: streams the packed planes of every step's matrix ---
@@ -953,9 +1117,15 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
 // sequence in both CTAs.  Result on the benchmark mix: bit-identical scores, 0.146 ms against 0.132 -- the
 // contractions are not bound by the weight stream (halving it changes their duration by < 2 %), and the
 // round-robin deal loses 12 us to imbalance that the dynamic scheduler does not have.
-template <int D, int STRUCT, bool PAIR>
+// HALF (the STAGE instantiation): the ring holds FOUR HALF stages -- output rows [0, d/2) and [d/2, d) of a
+// K-block plane, 16 KiB each, contiguous in the packed image -- in the first 64 KiB of the weight region, so
+// that its last 32 KiB are free for the helper warp's row ring while the weight stream still runs three
+// copies ahead of the tensor pipe (a ring of two full stages costs 17 % of the step: measured).
+template <int D, int STRUCT, bool PAIR, bool HALF = false>
 __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
+  constexpr int NST = HALF ? 4 : kStages;
+  constexpr uint32_t kCopyBytes = HALF ? C::kStageBytes / 2 : C::kStageBytes;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
   uint32_t slot = 0, phase = 0;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
@@ -984,11 +1154,13 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
     for (int st = 0; st < pg.n; ++st) {
       const uint8_t* src = step_matrix(s, pg.mat[st]);
 #pragma unroll 1
-      for (int i = 0; i < 2 * C::kKB; ++i) {
+      for (int i = 0; i < (HALF ? 4 : 2) * C::kKB; ++i) {
         const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
         ptx::mbar_wait(empty, phase ^ 1);          // PAIR: released by BOTH CTAs' MMA issuers (the copy lands in both rings)
-        ptx::mbar_arrive_expect_tx(full, C::kStageBytes);
-        if (PAIR) {
+        ptx::mbar_arrive_expect_tx(full, kCopyBytes);
+        if (HALF) {
+          ptx::tma_bulk_g2s(ptx::smem_u32(smem + C::kOffB + slot * kCopyBytes), src + (size_t)i * kCopyBytes, kCopyBytes, full);
+        } else if (PAIR) {
           constexpr uint32_t kHalf = C::kStageBytes / 2;
           const uint32_t off = rank * kHalf;
           ptx::tma_bulk_g2s_multicast(ptx::smem_u32(smem + C::kOffB + slot * C::kStageBytes) + off,
@@ -997,7 +1169,7 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
           ptx::tma_bulk_g2s(ptx::smem_u32(smem + C::kOffB + slot * C::kStageBytes), src + (size_t)i * C::kStageBytes,
                             C::kStageBytes, full);
         }
-        if (++slot == kStages) { slot = 0; phase ^= 1; }
+        if (++slot == NST) { slot = 0; phase ^= 1; }
       }
     }
     tile = next;
@@ -1006,11 +1178,14 @@ __device__ __forceinline__ void producer(const LaunchParams& p, uint8_t* smem, C
 }
 
 // ---- MMA issuer ------------------------------------------------------------------------
-template <int D, int STRUCT, bool PAIR>
+template <int D, int STRUCT, bool PAIR, bool HALF = false>
 __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem, Ctl* ctl) {
   using C = Cfg<D>;
+  constexpr int NST = HALF ? 4 : kStages;
+  constexpr int NH = HALF ? 2 : 1;                         // column halves of the accumulator, one ring slot each
+  constexpr uint32_t kSlotBytes = C::kStageBytes / NH;
   const bool deepsets = p.inter == GQE_INTER_DEEPSETS_MEAN || p.inter == GQE_INTER_DEEPSETS_MIN;
-  constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, D);
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, D / NH);
   const uint32_t tmem_base = ctl->tmem_base;
   const uint32_t a_hi = ptx::smem_u32(smem + C::kOffAhi), a_lo = ptx::smem_u32(smem + C::kOffAlo);
   const uint32_t b0 = ptx::smem_u32(smem + C::kOffB);
@@ -1033,35 +1208,39 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
       ptx::tc_fence_after_sync();
 #pragma unroll 1
       for (int kb = 0; kb < C::kKB; ++kb) {
-        // plane 0 of this K block: B_hi, used by A_hi and A_lo
-        {
+        // plane 0 of this K block: B_hi, used by A_hi and A_lo (HALF: output columns [0, d/2), then [d/2, d))
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
           const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
           ptx::mbar_wait(full, phase);
           ptx::tc_fence_after_sync();
-          const uint32_t b = b0 + slot * C::kStageBytes;
+          const uint32_t b = b0 + slot * kSlotBytes;
+          const uint32_t acc = tmem_acc + h * (D / NH);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
+            ptx::umma_bf16_ss(acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
                               ptx::umma_desc_sw128(b + 32 * k), idesc, (kb | k) != 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_lo + kb * C::kABlockBytes + 32 * k),
+            ptx::umma_bf16_ss(acc, ptx::umma_desc_sw128(a_lo + kb * C::kABlockBytes + 32 * k),
                               ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
           if (PAIR) ptx::umma_commit_multicast(empty, (uint16_t)3); else ptx::umma_commit(empty);
-          if (++slot == kStages) { slot = 0; phase ^= 1; }
+          if (++slot == NST) { slot = 0; phase ^= 1; }
         }
         // plane 1: B_lo, used by A_hi
-        {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
           const uint32_t full = ptx::smem_u32(&ctl->full[slot]), empty = ptx::smem_u32(&ctl->empty[slot]);
           ptx::mbar_wait(full, phase);
           ptx::tc_fence_after_sync();
-          const uint32_t b = b0 + slot * C::kStageBytes;
+          const uint32_t b = b0 + slot * kSlotBytes;
+          const uint32_t acc = tmem_acc + h * (D / NH);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_ss(tmem_acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
+            ptx::umma_bf16_ss(acc, ptx::umma_desc_sw128(a_hi + kb * C::kABlockBytes + 32 * k),
                               ptx::umma_desc_sw128(b + 32 * k), idesc, 1u);
           if (PAIR) ptx::umma_commit_multicast(empty, (uint16_t)3); else ptx::umma_commit(empty);
-          if (++slot == kStages) { slot = 0; phase ^= 1; }
+          if (++slot == NST) { slot = 0; phase ^= 1; }
         }
       }
       ptx::umma_commit(bar_acc_full);
@@ -1073,8 +1252,9 @@ __device__ __forceinline__ void mma_issuer(const LaunchParams& p, uint8_t* smem,
 // STRUCT >= 0: the single-formula kernel of that query structure; STRUCT < 0: the grouped
 // kernel, which looks its tile's structure up at run time (CTA-uniform).  Persistent:
 // launched with min(n_tiles, SMs x CTAs/SM) CTAs.
-template <int D, int STRUCT, bool PAIR = false>
-__global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fused_tc(const __grid_constant__ LaunchParams p) {
+template <int D, int STRUCT, bool PAIR = false, bool STAGE = false>
+__global__ void __launch_bounds__(Cfg<D>::kThreads + (STAGE ? 32 * Cfg<D>::kHelperWarps : 0), Cfg<D>::kCtasPerSm)
+    gqe_fused_tc(const __grid_constant__ LaunchParams p) {
   using C = Cfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + C::kOffCtl);
@@ -1083,7 +1263,7 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
 
   if (wid == C::kWorkerWarps && lane == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kStages + 1; ++i) {
       ptx::mbar_init(ptx::smem_u32(&ctl->full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&ctl->empty[i]), PAIR ? 2 : 1);
     }
@@ -1091,7 +1271,13 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
     ptx::mbar_init(ptx::smem_u32(&ctl->acc_full), 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&ctl->sched_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&ctl->sched_empty[i]), C::kWorkerThreads + 1);  // workers + MMA issuer
+      // workers + MMA issuer (+ lane 0 of every helper warp)
+      ptx::mbar_init(ptx::smem_u32(&ctl->sched_empty[i]), C::kWorkerThreads + 1 + ((STAGE && p.stage_on == 1) ? C::kHelperWarps : 0));
+    }
+    if (STAGE)
+    {
+      for (int i = 0; i < 4 * 5; ++i) ptx::mbar_init(ptx::smem_u32(&ctl->stage_ready[i / 5][i % 5]), C::kHelperWarps);
+      for (int i = 0; i < 32; ++i) ptx::mbar_init(ptx::smem_u32(&ctl->row_bar[i]), 1);
     }
     ptx::fence_mbar_init();
   } else if (wid == C::kWorkerWarps + 1) {
@@ -1108,13 +1294,23 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads, Cfg<D>::kCtasPerSm) gqe_fuse
   if (threadIdx.x == 0) cta_stamp(p, 1);
 
   if (wid < C::kWorkerWarps) {
-    worker<D, STRUCT>(p, smem, ctl);
+    worker<D, STRUCT, STAGE>(p, smem, ctl);
   } else if (wid == C::kWorkerWarps) {
-    if (lane == 0) producer<D, STRUCT, PAIR>(p, smem, ctl);
+#ifdef GQE_STAGE_FULLRING   // diagnostics: the STAGE instantiation with the ordinary weight ring (no room for the row ring: GQE_FORCE_STAGE=2 only)
+    if (lane == 0) producer<D, STRUCT, PAIR, false>(p, smem, ctl);
+#else
+    if (lane == 0) producer<D, STRUCT, PAIR, STAGE>(p, smem, ctl);
+#endif
     __syncwarp();
-  } else {
-    if (lane == 0) mma_issuer<D, STRUCT, PAIR>(p, smem, ctl);
+  } else if (wid == C::kWorkerWarps + 1) {
+#ifdef GQE_STAGE_FULLRING
+    if (lane == 0) mma_issuer<D, STRUCT, PAIR, false>(p, smem, ctl);
+#else
+    if (lane == 0) mma_issuer<D, STRUCT, PAIR, STAGE>(p, smem, ctl);
+#endif
     __syncwarp();
+  } else if (STAGE) {
+    if (p.stage_on == 1) helper<D, STRUCT>(p, smem, ctl, lane);
   }
 
   ptx::tc_fence_before_sync();

@@ -72,6 +72,29 @@ static cudaError_t tc_launch_one(const LaunchParams& lp, int64_t tiles, cudaStre
   }
   if (lp.pair == 1) return tc_launch_pair<D, STRUCT>(lp, tiles, slots[dev], st);
   const int64_t grid = tiles < slots[dev] ? tiles : slots[dev];
+  if constexpr (D == 256 && STRUCT < 0) {
+    // node-type-sharded tables: the instantiation with two helper warps per CTA that stage remote rows
+    if (lp.stage_on) {
+      auto skern = tc::gqe_fused_tc<D, STRUCT, false, true>;
+      static bool sconf[64] = {false};
+      if (!sconf[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<D>::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        sconf[dev] = true;
+      }
+      cudaLaunchConfig_t scfg = {};
+      scfg.gridDim = dim3((unsigned)grid);
+      scfg.blockDim = dim3(tc::Cfg<D>::kThreads + 32 * tc::Cfg<D>::kHelperWarps);
+      scfg.dynamicSmemBytes = tc::Cfg<D>::kSmemBytes;
+      scfg.stream = st;
+      cudaLaunchAttribute sattr[1];
+      sattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      sattr[0].val.programmaticStreamSerializationAllowed = 1;
+      scfg.attrs = sattr;
+      scfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&scfg, skern, lp);
+    }
+  }
   // programmatic dependent launch on gqe_pack (see tc::producer); GQE_PDL=0 in the environment
   // turns it off (diagnostics: measured 2.6 us per call on the benchmark mix)
   cudaLaunchConfig_t cfg = {};
