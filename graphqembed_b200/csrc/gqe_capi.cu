@@ -380,6 +380,10 @@ static const bool kStageRemote = [] {
   const char* e = getenv("GQE_STAGE");
   return e ? atoi(e) != 0 : true;
 }();
+static const uint32_t kStageMask = [] {   // GQE_STAGE_MASK=0x..: operands the helper warp stages (default: all five)
+  const char* e = getenv("GQE_STAGE_MASK");
+  return e ? (uint32_t)strtoul(e, nullptr, 0) : 0x1Fu;
+}();
 static const int kForceStage = [] {
   const char* e = getenv("GQE_FORCE_STAGE");
   return e ? atoi(e) : 0;
@@ -673,6 +677,7 @@ static int run_fused(gqe_ctx* c, const gqe_segment* segs, int32_t n_segs, int64_
             c->stage_buf_cap = need;
           }
           lp.stage = c->stage_buf;
+          lp.stage_mask = kStageMask;
           lp.stage_on = kForceStage == 3 ? 2 : 1;   // 3: the STAGE instantiation with its helper warp idle (diagnostics)
         }
       }

@@ -171,6 +171,7 @@ struct LaunchParams {
   int32_t pair;                 // tensor-core path: launched as clusters of two CTAs (tiles padded to pairs per segment)
   int32_t stage_on;             // tensor-core path (STAGE kernel): helper warps copy rows of peer GPUs' tables into `stage`
   float* stage;                 // [CTAs][4 tiles][5 operands][128 rows][d] fp32, local memory
+  uint32_t stage_mask;          // operands the helper may stage (bit o as in tc::staged_ops); the others are gathered in place
   int32_t wait_prev;            // tensor-core path: the index arrays are written by the kernel in front of this one in
                                 // the stream (gqe_fetch_indices): every thread waits for it before its first index load
   ModeDev mode[kMaxModes];

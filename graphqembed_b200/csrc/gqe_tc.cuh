@@ -640,7 +640,7 @@ __device__ __forceinline__ void worker(const LaunchParams& p, uint8_t* smem, Ctl
     // (all of it recomputed where it is used: nothing here stays live across the tile.)  The helper arrives on
     // EVERY stage_ready[k mod 4][o] once per tile, staged or not, so the parity to wait for is bit 2 of k.
     auto staged = [&](int o) -> bool {
-      return STAGE && p.stage_on == 1 && ((staged_ops(ring.k - 1, chain, rm, n_branch, T, p.q_out != nullptr) >> o) & 1u);
+      return STAGE && p.stage_on == 1 && (((staged_ops(ring.k - 1, chain, rm, n_branch, T, p.q_out != nullptr) & p.stage_mask) >> o) & 1u);
     };
     auto stage_ptr = [&](int o) -> const float* {
       return p.stage + (((size_t)blockIdx.x * C::kStageDepth + ((ring.k - 1) & 3u)) * C::kStageOps + (size_t)o) * (size_t)(kRows * D);
@@ -1054,9 +1054,35 @@ __device__ __forceinline__ void helper(const LaunchParams& p, uint8_t* smem, Ctl
     const int64_t row_begin = (chain ? s.q_begin * T : s.q_begin) + (tile - s.tile_begin) * kRows;
     const int64_t row_end = chain ? s.q_end * T : s.q_end;
     const int n_valid = (int)min((int64_t)kRows, row_end - row_begin);
-    const uint32_t sops = staged_ops(k, chain, s.remote_mask, s.n_anchor, T, p.q_out != nullptr);
+    const uint32_t sops = staged_ops(k, chain, s.remote_mask, s.n_anchor, T, p.q_out != nullptr) & p.stage_mask;
     float* slot = p.stage + ((size_t)blockIdx.x * C::kStageDepth + (k & 3u)) * (size_t)(C::kStageOps * kRows * D);
-#pragma unroll 1
+    // The rows of EVERY staged operand first (two dependent local loads each, all operands' in flight together),
+    // then the copies.  Lane l handles tile rows l, l + 32, ...; the anchors of a chain tile, which (pos, neg)
+    // pairs share, are fetched once per pair: lane l handles rows 2l, 2l + 64.
+    int32_t row[C::kStageOps][NG];
+#pragma unroll
+    for (int o = 0; o < C::kStageOps; ++o) {
+      const bool on = (sops >> o) & 1u;
+      const bool from_targets = chain ? (o == 0) : (o >= 3);
+      const int ak = (chain || o >= 3) ? 0 : o;
+      const int mode = from_targets ? s.tgt_mode : s.anc_mode[ak];
+      const bool dedupe = chain && o == 3 && T == 2;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int r = dedupe ? 2 * (32 * g + lane) : 32 * g + lane;
+        row[o][g] = -1;
+        if (on && r < n_valid) {
+          int32_t raw;
+          if (chain) raw = o == 0 ? __ldg(p.target_rows + row_begin + r)
+                                  : __ldg(p.anchor_rows + (T == 2 ? (row_begin + r) >> 1 : (row_begin + r) / T));
+          else raw = o < 3 ? __ldg(p.anchor_rows + (int64_t)o * p.anchor_stride + row_begin + r)
+                           : __ldg(p.target_rows + (row_begin + r) * T + (o - 3));
+          const int32_t cand = index_lookup(p.mode[mode], raw, ik);
+          row[o][g] = (uint32_t)cand < p.mode[mode].rows ? cand : 0;
+        }
+      }
+    }
+#pragma unroll
     for (int o = 0; o < C::kStageOps; ++o) {
       if (!((sops >> o) & 1u)) {   // nothing to fetch: the barrier still completes once per tile (the workers' parity rule)
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->stage_ready[k & 3u][o]));
@@ -1064,37 +1090,21 @@ __device__ __forceinline__ void helper(const LaunchParams& p, uint8_t* smem, Ctl
       }
       const bool from_targets = chain ? (o == 0) : (o >= 3);
       const int ak = (chain || o >= 3) ? 0 : o;
-      const int mode = from_targets ? s.tgt_mode : s.anc_mode[ak];
       const float* table = from_targets ? s.tgt_table : s.anc_table[ak];
       const bool dedupe = chain && o == 3 && T == 2;
-      // the rows of the whole operand first (two dependent local loads each), then the copies
-      int32_t row[NG];
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const int r = 32 * g + lane;
-        row[g] = -1;
-        if (r < n_valid && !(dedupe && (r & 1))) {
-          int32_t raw;
-          if (chain) raw = o == 0 ? __ldg(p.target_rows + row_begin + r)
-                                  : __ldg(p.anchor_rows + (T == 2 ? (row_begin + r) >> 1 : (row_begin + r) / T));
-          else raw = o < 3 ? __ldg(p.anchor_rows + (int64_t)o * p.anchor_stride + row_begin + r)
-                           : __ldg(p.target_rows + (row_begin + r) * T + (o - 3));
-          const int32_t cand = index_lookup(p.mode[mode], raw, ik);
-          row[g] = (uint32_t)cand < p.mode[mode].rows ? cand : 0;
-        }
-      }
       float* dst_op = slot + (size_t)o * kRows * D;
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
-        if (row[g] < 0) continue;
+        if (row[o][g] < 0) continue;
+        const int r = dedupe ? 2 * (32 * g + lane) : 32 * g + lane;
         // the bulk store that last read this lane's ring slot has finished reading it
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         ptx::mbar_arrive_expect_tx(my_bar, kRowBytes);
-        ptx::tma_bulk_g2s(my_slot, table + (size_t)row[g] * D, kRowBytes, my_bar);
+        ptx::tma_bulk_g2s(my_slot, table + (size_t)row[o][g] * D, kRowBytes, my_bar);
         ptx::mbar_wait(my_bar, my_phase);
         my_phase ^= 1u;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_op + (size_t)(32 * g + lane) * D),
-                     "r"(my_slot), "r"(kRowBytes)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_op + (size_t)r * D), "r"(my_slot),
+                     "r"(kRowBytes)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -1296,18 +1306,10 @@ __global__ void __launch_bounds__(Cfg<D>::kThreads + (STAGE ? 32 * Cfg<D>::kHelp
   if (wid < C::kWorkerWarps) {
     worker<D, STRUCT, STAGE>(p, smem, ctl);
   } else if (wid == C::kWorkerWarps) {
-#ifdef GQE_STAGE_FULLRING   // diagnostics: the STAGE instantiation with the ordinary weight ring (no room for the row ring: GQE_FORCE_STAGE=2 only)
-    if (lane == 0) producer<D, STRUCT, PAIR, false>(p, smem, ctl);
-#else
     if (lane == 0) producer<D, STRUCT, PAIR, STAGE>(p, smem, ctl);
-#endif
     __syncwarp();
   } else if (wid == C::kWorkerWarps + 1) {
-#ifdef GQE_STAGE_FULLRING
-    if (lane == 0) mma_issuer<D, STRUCT, PAIR, false>(p, smem, ctl);
-#else
     if (lane == 0) mma_issuer<D, STRUCT, PAIR, STAGE>(p, smem, ctl);
-#endif
     __syncwarp();
   } else if (STAGE) {
     if (p.stage_on == 1) helper<D, STRUCT>(p, smem, ctl, lane);
