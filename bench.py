@@ -230,7 +230,7 @@ def measure(args, name, tables_mode, tm, rank, world, local_rank, sampler=None, 
     """One workload on this process group.  tables_mode:
          replicated  every rank holds every table; pure data parallel, no data-path collective
          p2p         tables sharded by node type, peers mapped with CUDA IPC, the fused kernel
-                     gathers remote rows in place over NVLink
+                     reads remote rows over NVLink itself (a TMA helper warp stages them a tile ahead; GQE_STAGE=0: in place)
          staged      tables sharded by node type, rows fetched by an NCCL all-to-all exchange
                      into staging tables before the same fused kernel runs
        The index arrays are NODE IDS (int32) -- mapped to table rows inside the kernels through the
@@ -1047,7 +1047,9 @@ def run_native(args):
                        "weights": "packed / pre-multiplied operator matrices cached across steps (parameters unchanged "
                                   "between steps; `weights_live` = re-prepared every step)",
                        "tables": {"replicated": "replicated per GPU (Bio-size); queries sharded, no collective",
-                                  "p2p": "sharded by node type; remote rows gathered in place over NVLink (CUDA IPC)",
+                                  "p2p": "sharded by node type; remote rows read over NVLink (CUDA IPC peer mappings) inside the fused kernel: "
+                                         "fetched a tile ahead by its TMA helper warp into a local staging area "
+                                         "(GQE_STAGE=0: gathered in place)",
                                   "staged": "sharded by node type; NCCL all-to-all row exchange"}[tables_mode],
                        "l2": "flushed before every step (256 MiB write)"},
             "e2e": {"value": round(world * nq / (res["e2e_ms"] * 1e-3), 1), "unit": UNIT,
