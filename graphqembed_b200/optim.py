@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from .query import QueryBatch
-from .store import StoreSlice
+from .store import DeviceSlice, StoreSlice
 
 
 class NativeAdam(object):
@@ -40,7 +40,8 @@ class NativeAdam(object):
     update (dense torch.optim.Adam trajectory; the tables are updated row-wise with exact catch-up,
     see ``SparseRowAdam``) without returning to Python between kernels.  The model's parameters are
     updated in place; the optimiser state lives in the model's native context.  ``queries``: a list of
-    ``Query`` objects or a ``StoreSlice``; negatives are drawn exactly as ``margin_loss`` draws them.
+    ``Query`` objects, a ``StoreSlice`` or a ``DeviceSlice`` (its host arrays are used); negatives are drawn exactly as
+    ``margin_loss`` draws them from a host slice.
     """
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
@@ -77,6 +78,8 @@ class NativeAdam(object):
     def _run(self, formula, queries, hard_negatives, margin, weight):
         m = self.model
         ctx = m.context()
+        if isinstance(queries, DeviceSlice):       # the training call takes host index arrays: the same slice of the host block
+            queries = queries.host()
         if isinstance(queries, StoreSlice):
             if "inter" not in formula.query_type and hard_negatives:
                 raise Exception("Hard negative examples can only be used with intersection queries")

@@ -138,3 +138,34 @@ def test_row_lookup_dense_and_sparse_agree():
     ptrs, bases, lens, keep = L.device_maps(["d"], [len(dense_ids) + 2], "cpu")
     assert bases == [int(dense_ids.min())] and lens == [int(dense_ids.max() - dense_ids.min() + 1)] and ptrs[0] != 0
     assert RowLookup(None).device_maps(["a", "b"], [10, 20], "cpu")[:3] == ([0, 0], [-1, -1], [10, 20])
+
+
+def test_device_store_descriptors_on_cpu(case_and_records):
+    """QueryStore.to_device (here onto the CPU device: the descriptor logic needs no GPU): same blocks, same
+    batch sampling as the host store, slices that map back to the host views."""
+    import torch
+    from graphqembed_b200.store import DeviceQueryStore, DeviceSlice
+    case, raw = case_and_records
+    store = QueryStore.from_records(raw)
+    dstore = store.to_device(torch.device("cpu"))
+    assert isinstance(dstore, DeviceQueryStore) and len(dstore) == len(store)
+    assert dstore.formulas() == store.formulas()
+    for f in store.formulas():
+        blk, dblk = store[f], dstore[f]
+        assert len(dblk) == len(blk)
+        np.testing.assert_array_equal(dblk.anchors.numpy(), blk.anchors)
+        np.testing.assert_array_equal(dblk.targets.numpy(), blk.targets)
+        np.testing.assert_array_equal(dblk.neg_ptr.numpy(), blk.neg_ptr)
+        assert dblk.anchors.dtype == torch.int32 and dblk.neg_ptr.dtype == torch.int64
+        sl = dblk.window(1, len(blk))
+        assert isinstance(sl, DeviceSlice) and len(sl) == len(blk) - 1 and sl.formula == f
+        np.testing.assert_array_equal(sl.host().targets, blk.targets[1:])
+        with pytest.raises(IndexError):
+            dblk.window(0, len(blk) + 1)
+    qt = next(iter(store.by_type))
+    np.random.seed(11)
+    a = [store.sample_batch(qt, i, 4) for i in range(6)]
+    np.random.seed(11)
+    b = [dstore.sample_batch(qt, i, 4) for i in range(6)]
+    for x, y in zip(a, b):
+        assert x.formula == y.formula and (x.start, x.stop) == (y.start, y.stop)
