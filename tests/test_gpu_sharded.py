@@ -39,10 +39,13 @@ def _worker(rank, world, port, d, ret):
         kg = SynthKG(["a", "b", "c"], [700, 500, 900], n_rel_pairs=6, seed=5, self_loops=False)
         rng = np.random.RandomState(50 + rank)
         batches = []
+        # d = 256: enough tiles (> 2 per SM) that the CTAs of the grouped kernel work through several each -- the
+        # helper warp of its STAGE instantiation then fetches the peer rows of every tile but a CTA's first
+        scale = 48 if d == 256 else 1
         for s, n in (("1-chain", 130), ("3-chain", 77), ("2-inter", 200), ("3-inter", 129), ("3-inter_chain", 64),
                      ("3-chain_inter", 31)):
             rels = kg.sample_rels(s, rng)
-            b = kg.sample_batch(s, rels, n, 1, rng)
+            b = kg.sample_batch(s, rels, n * scale, 1, rng)
             batches.append(QueryBatch(Formula(s, rels), b["anchors"], np.stack([b["target"], b["negs"][:, 0]], 1).reshape(-1)))
         wl = Workload("toy", kg, d, "bilinear", "mean", batches)
         g = torch.Generator(device=device).manual_seed(99)
