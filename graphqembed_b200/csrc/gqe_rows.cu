@@ -1,10 +1,14 @@
-// gqe_rows.cu -- raw embedding-row gather for the sharded-table exchange.
+// gqe_rows.cu -- the small data movers around the scoring kernels.
 //
-// The owner of a node-type shard copies the requested rows of its table,
-// un-normalised, into a dense [n, d] block that is then shipped to the scoring
-// rank (NCCL) -- the staged alternative to reading the rows in place over
-// NVLink.  Pure HBM traffic: n * d * 4 bytes read + written, 128-bit accesses,
-// one warp per row, grid sized to the SM count.
+//   gqe_gather_rows    raw embedding-row gather for the staged sharded-table exchange: the owner of a
+//                      node-type shard copies the requested rows of its table, un-normalised, into a dense
+//                      [n, d] block that is then shipped to the scoring rank (NCCL) -- the comparison point of
+//                      reading the rows over NVLink inside the fused kernel.  Pure HBM traffic: n * d * 4 bytes
+//                      read + written, 128-bit accesses, one warp per row, grid sized to the SM count.
+//   gqe_fetch_indices  index arrays of a *_host call: pinned host memory -> device staging over PCIe, every
+//                      range in one launch (instead of one copy-engine operation per range).
+//   gqe_store_batch    batches out of a device-resident query store: slices gathered, one negative drawn per
+//                      query (netquery/train_helpers.py:95-107, netquery/model.py:113-120).
 #include <cuda_runtime.h>
 #include <stdint.h>
 

@@ -28,7 +28,9 @@
 //
 // Warp roles: warps [0, W) workers (W = d/16: four TMEM lane quarters x d/64 column
 // groups, thread == one row x 64 columns), warp W = TMA producer, warp W+1 = MMA
-// issuer + TMEM owner.
+// issuer + TMEM owner; in the STAGE instantiation (d = 256, grouped kernel, tables sharded
+// over several GPUs) warp W+2 = helper: fetches the operand rows that live in a PEER GPU's
+// HBM by TMA, up to two tiles ahead of the workers, into a local staging area (helper()).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
