@@ -31,6 +31,9 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Plan) == 9 * 4
     assert ctypes.sizeof(_lib.Segment) == 40 + 16      # plan padded to 8-byte alignment
     assert _lib.Segment.query_begin.offset == 40
+    # gqe_store_slice: four device pointers, three int64
+    assert ctypes.sizeof(_lib.StoreSliceC) == 7 * 8
+    assert _lib.StoreSliceC.block_queries.offset == 32 and _lib.StoreSliceC.pool_size.offset == 48
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
