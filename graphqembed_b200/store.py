@@ -74,6 +74,20 @@ class FormulaBlock(object):
         return StoreSlice(self, 0, len(self))
 
 
+def device_draw(seed, positions, lens):
+    """The pick of ``gqe_store_batch`` (csrc/gqe_rows.cu) restated on the host: for the query at position
+    ``positions[i]`` of a call with ``seed``, the index floor(u * lens[i]) into its negative list, u = the upper 32
+    bits of splitmix64(seed + golden * (position + 1)) / 2^32.  int64 array; for tests and for reproducing a
+    device-side draw on the host."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & (2 ** 64 - 1)) + np.uint64(0x9E3779B97F4A7C15) * (np.asarray(positions, dtype=np.uint64) + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        u = z >> np.uint64(32)
+        return ((u * np.asarray(lens, dtype=np.uint64)) >> np.uint64(32)).astype(np.int64)
+
+
 class DeviceBlock(object):
     """A ``FormulaBlock`` uploaded to a GPU (torch int32 / int64 tensors; the host block stays
     reachable as ``.host``)."""

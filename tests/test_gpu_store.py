@@ -75,6 +75,13 @@ def test_draw_is_a_function_of_the_seed_and_uniform_over_the_lists(setup):
         _, p3, _ = model._margin_loss_store([(f, sl)], return_pairs=True)      # the next call: seed + 1
         assert torch.equal(p1, p2)
         assert not torch.equal(p1, p3)
+        # index work is held to the bit: the host restatement of the generator picks the same negatives
+        from graphqembed_b200.store import device_draw
+        n = len(blk)
+        pick = device_draw(77, np.arange(n), np.diff(blk.neg_ptr))
+        np.testing.assert_array_equal(p1.cpu().numpy()[:, 1], blk.negs[blk.neg_ptr[:-1] + pick])
+        pick3 = device_draw(78, np.arange(n), np.diff(blk.neg_ptr))
+        np.testing.assert_array_equal(p3.cpu().numpy()[:, 1], blk.negs[blk.neg_ptr[:-1] + pick3])
         # every position of a 6-long list is drawn about equally often over many seeds
         lens = np.diff(blk.neg_ptr)
         six = np.array([q for q in np.nonzero(lens == 6)[0] if len(set(blk.negs[blk.neg_ptr[q]:blk.neg_ptr[q] + 6].tolist())) == 6])

@@ -169,3 +169,17 @@ def test_device_store_descriptors_on_cpu(case_and_records):
     b = [dstore.sample_batch(qt, i, 4) for i in range(6)]
     for x, y in zip(a, b):
         assert x.formula == y.formula and (x.start, x.stop) == (y.start, y.stop)
+
+
+def test_device_draw_restatement_is_uniform_and_in_range():
+    from graphqembed_b200.store import device_draw
+    lens = np.array([1, 2, 3, 7, 1000, 1 << 20] * 5000)
+    pick = device_draw(123456789, np.arange(lens.size), lens)
+    assert pick.dtype == np.int64 and (pick >= 0).all() and (pick < lens).all()
+    sevens = pick[lens == 7]
+    share = np.bincount(sevens, minlength=7) / sevens.size
+    assert share.min() > 0.12 and share.max() < 0.17
+    assert not np.array_equal(pick, device_draw(123456790, np.arange(lens.size), lens))
+    # splitmix64 known answer: seed 0, position 0 -> first output of the generator seeded with 0
+    z = device_draw(0, [0], [1 << 32])[0]
+    assert z == 0xE220A8397B1DCDAF >> 32
