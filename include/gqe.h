@@ -249,7 +249,8 @@ int gqe_margin_loss_device(gqe_ctx* ctx, const gqe_plan* plan, int64_t n_queries
                            const int32_t* anchor_rows, const int32_t* pair_rows,
                            float margin, float* out_loss, float* out_scores);
 
-/* Grouped variant: many formulas in one call (the "full mix" workload).
+/* Grouped variant: many formulas in one call (the "full mix" workload); any number of segments, one
+ * launch per 96 formulas (one loss accumulator across the launches).
  *   segments      HOST array; segment s owns queries [query_begin, query_end)
  *   anchor_rows   DEVICE int32 [GQE_MAX_ANCHORS][n_queries_total]
  *   target_rows   DEVICE int32 [n_queries_total][targets_per_query]
