@@ -132,13 +132,13 @@ def pick_batch(train_queries, iter_count, batch_size):
     """The batch ``run_batch`` scores (train_helpers.py:96-105): ONE formula drawn
     ~ multinomial(#queries per formula) from numpy's global RNG, then a contiguous, wrapping
     window of its queries.  ``train_queries``: {Formula: list-like of queries} (lists of
-    ``Query`` or ``FormulaBlock``s).  -> (formula, queries)"""
+    ``Query``, ``FormulaBlock``s or ``DeviceBlock``s).  -> (formula, queries)"""
     formulas = list(train_queries)
     sizes = np.array([len(train_queries[f]) for f in formulas], dtype=np.float64)
     formula = formulas[int(np.argmax(np.random.multinomial(1, sizes / sizes.sum())))]
     pool = train_queries[formula]
     start, stop = batch_window(iter_count, batch_size, len(pool))
-    return formula, (pool.window(start, stop) if isinstance(pool, FormulaBlock) else pool[start:stop])
+    return formula, (pool.window(start, stop) if hasattr(pool, "window") else pool[start:stop])   # store blocks (host or device)
 
 
 def run_batch(train_queries, enc_dec, iter_count, batch_size, hard_negatives=False):
